@@ -1,0 +1,89 @@
+"""ctypes binding of libcetpick_sm100a.so (include/cetpick.h).  No CPU fallback: if the library
+cannot be loaded, or a compute call is made without a CUDA device, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcetpick_sm100a.so")
+
+OK = 0
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_STATE, ERR_SHAPE = -1, -2, -3, -4, -5, -6
+NMS_NONE, NMS_3D, NMS_FIBER, NMS_XY, NMS_Z = 0, 1, 2, 3, 4
+EPI_BF16_NHWC, EPI_UPCONV_2X2, EPI_F32_ROWMAJOR, EPI_F32_L2NORM_NCDHW = 0, 1, 2, 3
+
+_i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
+
+# every symbol include/cetpick.h declares: (restype, argtypes)
+SIGNATURES = {
+    "cetpick_version": (_int, []),
+    "cetpick_strerror": (C.c_char_p, [_int]),
+    "cetpick_last_cuda_error": (C.c_char_p, []),
+    "cetpick_decode_workspace_bytes": (_int, [_i64, _i64, _i64, _int, C.POINTER(_sz)]),
+    "cetpick_decode_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cetpick_decode_status": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_i64)]),
+    "cetpick_nms_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
+    "cetpick_sigmoid_clamp_f32": (_int, [_vp, _i64, _vp]),
+    "cetpick_unet_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
+    "cetpick_unet_destroy": (None, [_vp]),
+    "cetpick_unet_set_param": (_int, [_vp, C.c_char_p, _vp, _i64]),
+    "cetpick_unet_finalize": (_int, [_vp]),
+    "cetpick_unet_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _int, C.POINTER(_sz)]),
+    "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
+    "cetpick_last_launch_count": (_i64, []),
+    "cetpick_selftest_gemm_bf16": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
+    "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
+                                 _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class CetpickError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: {detail}" if detail else where)
+
+
+def lib() -> C.CDLL:
+    """Load the shared library once; raise loudly when it is missing (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing: build it with `python -m cet_pick_b200.build` "
+                        "(cet_pick_b200 has no CPU/PyTorch fallback)")
+                h = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(h, name)          # AttributeError if the symbol is not exported
+                    fn.restype, fn.argtypes = res, args
+                _lib = h
+    return _lib
+
+
+def check(code: int, where: str):
+    if code == OK:
+        return
+    L = lib()
+    msg = L.cetpick_strerror(code).decode()
+    if code == ERR_CUDA:
+        msg += " (" + L.cetpick_last_cuda_error().decode() + ")"
+    exc = ValueError if code in (ERR_BAD_ARG, ERR_SHAPE) else \
+        NotImplementedError if code == ERR_UNSUPPORTED else RuntimeError
+    raise exc(f"{where}: {msg}")
+
+
+def require_cuda(t, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; cet_pick_b200 runs on CUDA (sm_100a) only "
+                           "and has no CPU fallback")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,48 @@
+// Shared helpers for libcetpick_sm100a.so (sm_100a only; no multi-arch dispatch).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include "../../include/cetpick.h"
+
+namespace cetpick {
+
+extern thread_local int64_t g_launches;        // kernels enqueued by the current API call
+extern thread_local std::string g_cuda_err;    // text of the last CUDA failure on this thread
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  g_cuda_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return CETPICK_ERR_CUDA;
+}
+
+#define CETPICK_CUDA(call)                                            \
+  do {                                                                \
+    cudaError_t e__ = (call);                                         \
+    if (e__ != cudaSuccess) return ::cetpick::cuda_fail(e__, #call);  \
+  } while (0)
+
+#define CETPICK_LAUNCH_CHECK()                                                 \
+  do {                                                                         \
+    ++::cetpick::g_launches;                                                   \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) return ::cetpick::cuda_fail(e__, "kernel launch"); \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace cetpick

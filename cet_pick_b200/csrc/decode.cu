@@ -1,0 +1,866 @@
+// Heat-map decode for sm_100a: 3-D max-pool NMS + exact top-K + pick writer.
+//
+// Replaces cet_pick/models/decode.py:11-41,82-92,123-155 (and models/utils.py:171-193 for `reg`).
+// HBM-bound design (DESIGN.md "decode"): the fp32 map is streamed ONCE by `scan_kernel` in COLLECT
+// mode; a voxel's NMS output o = heat*(maxpool==heat) is never materialised.  What is selected is
+// decided by an exact radix select:
+//   1. HIST passes over a small, L2-resident z-range (the "sample") give t0 = K-th largest o in the
+//      sample, a guaranteed lower bound of the global K-th largest o;
+//   2. COLLECT streams the whole map once and appends every voxel with o > t0 as a 64-bit composite
+//      (monotone key(o) << 32 | ~linear_index) and counts voxels with o == t0 per plane;
+//   3. if fewer than K were appended, EQ appends the o == t0 voxels of the first planes that are
+//      needed to fill K in ascending index order;
+//   4. a 6-digit radix select over the composites finds the exact K-th, the K survivors are
+//      compacted, bitonic-sorted (score desc, index asc) and written with the reference's fp32
+//      index arithmetic.
+// If the candidate buffer would overflow (adversarial map), the same HIST passes run over the whole
+// volume (exact, 3 extra reads) -- every kernel is always enqueued and exits early on device-side
+// state, so the call never synchronises the host.
+#include "common.cuh"
+#include <algorithm>
+
+namespace cetpick {
+
+namespace {
+
+constexpr uint32_t KEY_ZERO = 0x80000000u;  // key of +0.0 (-0.0 is canonicalised onto it)
+constexpr int TX = 128, TY = 32, PITCH = TX + 8, XH = 4;  // tile, smem row pitch, x halo (aligned)
+constexpr int SCAN_THREADS = 256;
+constexpr int HIST_BINS = 2048;
+constexpr int MAX_ZC = 64;
+constexpr int SORT_SMEM_MAX = 16384;  // composites sortable in one CTA's shared memory
+
+enum { MODE_HIST = 0, MODE_COLLECT = 1, MODE_EQ = 2 };
+enum { FLAG_NAN = 1, FLAG_FALLBACK = 2, FLAG_INTERNAL = 4 };
+
+struct DecodeState {
+  uint32_t t0key;          // COLLECT appends okey > t0key
+  uint32_t sel_prefix;     // volume radix select: bits chosen so far (right aligned)
+  uint32_t sel_kleft;      // rank still to resolve inside the prefix class
+  uint32_t flags;
+  uint32_t cand_count;     // entries appended to cand[] (may exceed capacity => overflow)
+  uint32_t n_gt;
+  uint32_t need_fallback;
+  uint32_t eq_need;        // how many o == t0 voxels are still needed (0 = none)
+  int32_t eq_zc;           // last plane EQ has to visit
+  uint32_t done_ctr;       // last-block ticket
+  uint32_t csel_kleft;
+  uint32_t out_count;
+  unsigned long long csel_prefix;  // candidate radix select prefix (right aligned)
+  unsigned long long kth_comp;     // exact K-th largest composite
+  uint32_t n_final;        // number of candidates the final select saw
+  uint32_t pad[3];
+};
+
+struct ScanParams {
+  const float* heat;
+  int D, H, W;
+  int zlo, zhi;        // planes whose voxels are emitted
+  int mode;            // MODE_*
+  int nms_mode;        // CETPICK_NMS_NONE / 3D / FIBER
+  int shift, bits;     // HIST digit
+  int last_pass;       // HIST: this pass resolves the last digit
+  int ZC;              // planes per work item
+  int gate;            // 1: run only when state->need_fallback
+  int phase;           // 0 = first COLLECT (may request fallback), 1 = fallback COLLECT
+  int collect_all;     // COLLECT: append every voxel (small volumes)
+  int vec_ok;          // rows are 16-byte aligned: use 16-byte cp.async
+  int K;
+  uint32_t k_select;   // HIST pass 0: rank to select
+  uint32_t cap_gt;     // capacity reserved for COLLECT entries
+  uint32_t cap_total;
+  DecodeState* st;
+  uint32_t* hist;      // HIST_BINS global bins
+  uint32_t* eqcnt;     // D per-plane counts of o == t0
+  unsigned long long* cand;
+};
+
+__device__ __forceinline__ uint32_t f2key(float v) {
+  uint32_t b = __float_as_uint(v);
+  uint32_t k = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return k == 0x7FFFFFFFu ? KEY_ZERO : k;
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* g) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(g));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Select step shared by the volume and candidate radix selects: walk `nb` bins from the top until
+// the cumulative count reaches kleft.  Runs in ONE CTA (the last one to finish a HIST pass).
+// Returns the chosen digit and the rank left inside it through shared memory.
+__device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* s_hist,
+                             uint32_t* s_out /*[2]*/) {
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    s_hist[i] = ghist[i];
+    ghist[i] = 0;  // ready for the next pass
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int per = nb / 32;  // nb is a multiple of 32
+    const int lane = threadIdx.x;
+    // lane l owns bins [nb - (l+1)*per, nb - l*per): lane 0 holds the top bins
+    uint32_t sum = 0;
+    for (int i = 0; i < per; ++i) sum += s_hist[nb - 1 - lane * per - i];
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t excl = incl - sum;
+    bool mine = (excl < kleft) && (incl >= kleft);
+    unsigned who = __ballot_sync(0xffffffffu, mine);
+    if (who == 0) {  // fewer than kleft elements in total: take the lowest non-empty bin
+      if (lane == 0) { s_out[0] = 0; s_out[1] = 0xffffffffu; }
+    } else if (lane == __ffs(who) - 1) {
+      uint32_t cum = excl;
+      int d = nb - 1 - lane * per;
+      for (int i = 0; i < per; ++i, --d) {
+        uint32_t h = s_hist[d];
+        if (cum + h >= kleft) break;
+        cum += h;
+      }
+      s_out[0] = (uint32_t)d;
+      s_out[1] = kleft - cum;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan_kernel: streams z-chunks of (TY x TX) tiles through shared memory (cp.async double buffer),
+// keeps the (k x k) in-plane maxima of three consecutive planes in registers and emits per voxel
+// the monotone key of o = heat * (maxpool3d(heat) == heat).
+// ---------------------------------------------------------------------------------------------
+template <int P>
+struct PlaneRegs {
+  float a[4][4];  // in-plane (2P+1)^2 max (or, fiber, the xy-suppressed value)
+  float c[4][4];  // centre value compared in z
+};
+
+template <int P>
+__device__ __forceinline__ void load_plane(float* buf, const float* plane, int y0, int x0, int H,
+                                           int W, int vec_ok) {
+  constexpr int ROWS = TY + 2 * P;
+  constexpr int CH = PITCH / 4;  // 16-byte chunks per row
+  const float ninf = -INFINITY;
+  for (int ch = threadIdx.x; ch < ROWS * CH; ch += SCAN_THREADS) {
+    const int r = ch / CH, cc = ch - r * CH;
+    const int gy = y0 - P + r, gx = x0 - XH + 4 * cc;
+    float* dst = buf + r * PITCH + 4 * cc;
+    const bool rowin = (gy >= 0) && (gy < H);
+    if (vec_ok) {
+      if (rowin && gx >= 0 && gx < W) {
+        cp_async16(dst, plane + (size_t)gy * W + gx);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(ninf, ninf, ninf, ninf);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (rowin && gx + e >= 0 && gx + e < W) cp_async4(dst + e, plane + (size_t)gy * W + gx + e);
+        else dst[e] = ninf;
+      }
+    }
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void compute_plane(const float* buf, int fiber, PlaneRegs<P>& out) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float hm[4 + 2 * P][4];
+  float ctr[4][4];
+#pragma unroll
+  for (int rr = 0; rr < 4 + 2 * P; ++rr) {
+    const float* row = buf + (ty * 4 + rr) * PITCH + XH + 4 * tx;
+    float w[4 + 2 * P];
+    const float4 q = *reinterpret_cast<const float4*>(row);
+    w[P] = q.x; w[P + 1] = q.y; w[P + 2] = q.z; w[P + 3] = q.w;
+    if (P == 1) {
+      // halo columns come from the neighbouring lanes; the warp's two edge lanes read smem
+      float l = __shfl_up_sync(0xffffffffu, q.w, 1);
+      float r = __shfl_down_sync(0xffffffffu, q.x, 1);
+      if (tx == 0) l = row[-1];
+      if (tx == 31) r = row[4];
+      w[0] = l; w[5] = r;
+    } else {
+#pragma unroll
+      for (int k = 0; k < P; ++k) { w[k] = row[k - P]; w[P + 4 + k] = row[4 + k]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = w[i];
+#pragma unroll
+      for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, w[i + k]);
+      hm[rr][i] = m;
+    }
+    if (rr >= P && rr < P + 4) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ctr[rr - P][i] = w[P + i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = hm[j][i];
+#pragma unroll
+      for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, hm[j + k][i]);
+      const float v = ctr[j][i];
+      if (fiber) {  // decode.py:11-17 on this plane: o1 = v * (m == v)
+        const float o1 = (v == m) ? v : v * 0.0f;
+        out.a[j][i] = o1;
+        out.c[j][i] = o1;
+      } else {
+        out.a[j][i] = m;
+        out.c[j][i] = v;
+      }
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams p) {
+  constexpr int ROWS = TY + 2 * P;
+  extern __shared__ __align__(16) float smem[];
+  float* bufs[2] = {smem, smem + ROWS * PITCH};
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + 2 * ROWS * PITCH);
+  __shared__ uint32_t s_eq[MAX_ZC];
+  __shared__ uint32_t s_sel[2];
+  __shared__ uint32_t s_ticket;
+
+  DecodeState* st = p.st;
+  if (p.gate && st->need_fallback == 0) return;
+  int zlo = p.zlo, zhi = p.zhi;
+  if (p.mode == MODE_EQ) {
+    if (st->eq_need == 0) return;
+    zhi = min(zhi, st->eq_zc + 1);
+  }
+  const int mode = p.mode;
+  const int H = p.H, W = p.W, D = p.D;
+  const bool znbr = p.nms_mode != CETPICK_NMS_NONE;
+  const int fiber = p.nms_mode == CETPICK_NMS_FIBER;
+  const uint32_t t0key = st->t0key;
+  // HIST filter: keys whose bits above (shift+bits) equal the prefix chosen so far
+  const int hs = p.shift + p.bits;
+  const uint32_t prefix = (hs >= 32) ? 0u : st->sel_prefix;
+  const uint32_t dmask = (1u << p.bits) - 1u;
+
+  if (mode == MODE_HIST) {
+    for (int i = threadIdx.x; i < HIST_BINS; i += SCAN_THREADS) s_hist[i] = 0;
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, lane = tx;
+  const int ntx = ceil_div(W, TX), nty = ceil_div(H, TY);
+  const int nzc = (zhi > zlo) ? ceil_div(zhi - zlo, p.ZC) : 0;
+  const long long items = (long long)ntx * nty * nzc;
+  const size_t plane_sz = (size_t)H * W;
+  uint32_t zero_cnt = 0;   // HIST: voxels with okey == KEY_ZERO seen by this thread
+  bool saw_nan = false;
+
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ix = (int)(item % ntx);
+    const int iy = (int)((item / ntx) % nty);
+    const int iz = (int)(item / ((long long)ntx * nty));
+    const int x0 = ix * TX, y0 = iy * TY;
+    const int z0 = zlo + iz * p.ZC, z1 = min(z0 + p.ZC, zhi);
+    const int nplanes = z1 - z0 + 2;
+    if (mode == MODE_COLLECT) {
+      for (int i = threadIdx.x; i < MAX_ZC; i += SCAN_THREADS) s_eq[i] = 0;
+    }
+    PlaneRegs<P> prev, cur, nxt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { prev.a[j][i] = cur.a[j][i] = -INFINITY; prev.c[j][i] = cur.c[j][i] = 0.f; }
+
+    {
+      const int pz = z0 - 1;
+      if (znbr && pz >= 0) load_plane<P>(bufs[0], p.heat + (size_t)pz * plane_sz, y0, x0, H, W, p.vec_ok);
+      cp_async_commit();
+    }
+    for (int i = 0; i < nplanes; ++i) {
+      const int pz = z0 - 1 + i;
+      const bool interior = (i >= 1) && (i <= nplanes - 2);   // an emitted plane
+      if (i + 1 < nplanes) {
+        const int qz = pz + 1;
+        const bool qint = (i + 1 <= nplanes - 2);
+        if (qz < D && (qint || znbr))
+          load_plane<P>(bufs[(i + 1) & 1], p.heat + (size_t)qz * plane_sz, y0, x0, H, W, p.vec_ok);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const bool have = (pz >= 0) && (pz < D) && (interior || znbr);
+      if (have) {
+        compute_plane<P>(bufs[i & 1], fiber, nxt);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { nxt.a[j][k] = -INFINITY; nxt.c[j][k] = 0.f; }
+      }
+      if (i >= 2) {
+        // ---- emit plane ez = pz - 1 from (prev, cur, nxt) ----
+        const int ez = pz - 1;
+        uint32_t okey[4][4];
+        uint32_t n_gt = 0, n_eq = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float c = cur.c[j][k];
+            const float m3 = fmaxf(fmaxf(prev.a[j][k], cur.a[j][k]), nxt.a[j][k]);
+            const bool valid = (y0 + ty * 4 + j < H) && (x0 + tx * 4 + k < W);
+            uint32_t ok = (c == m3) ? f2key(c) : KEY_ZERO;
+            saw_nan |= valid && (c != c);
+            if (!valid) ok = 0;  // key 0 never matches anything below
+            okey[j][k] = ok;
+            if (mode == MODE_COLLECT) {
+              n_gt += (valid && (p.collect_all || ok > t0key)) ? 1u : 0u;
+              n_eq += (valid && ok == t0key) ? 1u : 0u;
+            } else if (mode == MODE_EQ) {
+              n_gt += (valid && ok == t0key) ? 1u : 0u;
+            }
+          }
+        if (mode == MODE_HIST) {
+          uint32_t run_key = 0, run_cnt = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ok = okey[j][k];
+              if (ok == 0) continue;
+              if (hs < 32 && (ok >> hs) != prefix) continue;
+              if (ok == KEY_ZERO) { ++zero_cnt; continue; }
+              if (ok == run_key) { ++run_cnt; continue; }
+              if (run_cnt) atomicAdd(&s_hist[(run_key >> p.shift) & dmask], run_cnt);
+              run_key = ok; run_cnt = 1;
+            }
+          if (run_cnt) atomicAdd(&s_hist[(run_key >> p.shift) & dmask], run_cnt);
+        } else {
+          if (mode == MODE_COLLECT) {
+            const uint32_t weq = __reduce_add_sync(0xffffffffu, n_eq);
+            if (lane == 0 && weq) atomicAdd(&s_eq[ez - z0], weq);
+          }
+          if (__any_sync(0xffffffffu, n_gt != 0)) {
+            uint32_t incl = n_gt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&st->cand_count, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t off = base + incl - n_gt;
+            const uint32_t cap = p.cap_total;
+            const uint32_t lim = (mode == MODE_COLLECT) ? p.cap_gt : cap;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ok = okey[j][k];
+                const bool take = (ok != 0) && ((mode == MODE_COLLECT) ? (p.collect_all || ok > t0key)
+                                                                        : (ok == t0key));
+                if (take) {
+                  if (off < lim) {
+                    const uint32_t idx = (uint32_t)((size_t)ez * plane_sz +
+                                                    (size_t)(y0 + ty * 4 + j) * W + (x0 + tx * 4 + k));
+                    p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
+                  }
+                  ++off;
+                }
+              }
+          }
+        }
+      }
+      prev = cur;
+      cur = nxt;
+      __syncthreads();
+    }
+    if (mode == MODE_COLLECT) {
+      for (int i = threadIdx.x; i < z1 - z0; i += SCAN_THREADS)
+        if (s_eq[i]) atomicAdd(&p.eqcnt[z0 + i], s_eq[i]);
+      __syncthreads();
+    }
+  }
+
+  if (saw_nan) atomicOr(&st->flags, (uint32_t)FLAG_NAN);
+
+  if (mode == MODE_EQ) return;
+
+  // ---- publish and let the last CTA take the decision for the next kernel ----
+  if (mode == MODE_HIST) {
+    if (zero_cnt && (hs >= 32 || (KEY_ZERO >> hs) == prefix))
+      atomicAdd(&s_hist[(KEY_ZERO >> p.shift) & dmask], zero_cnt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST_BINS; i += SCAN_THREADS)
+      if (s_hist[i]) atomicAdd(&p.hist[i], s_hist[i]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->done_ctr, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+
+  if (mode == MODE_HIST) {
+    const uint32_t kleft = (hs >= 32) ? p.k_select : st->sel_kleft;
+    select_digit(p.hist, 1 << p.bits, kleft, s_hist, s_sel);
+    if (threadIdx.x == 0) {
+      const uint32_t np = (prefix << p.bits) | s_sel[0];
+      st->sel_prefix = np;
+      st->sel_kleft = s_sel[1];
+      if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
+      if (p.last_pass) {
+        st->t0key = np;
+        if (p.gate) {  // fallback select finished: restart the candidate list for COLLECT phase 1
+          st->cand_count = 0;
+        }
+      }
+      st->done_ctr = 0;
+    }
+    if (p.last_pass && p.gate) {
+      for (int i = threadIdx.x; i < D; i += SCAN_THREADS) p.eqcnt[i] = 0;
+    }
+  } else {  // MODE_COLLECT: plan the EQ pass
+    if (threadIdx.x == 0) {
+      const uint32_t n = st->cand_count;
+      st->n_gt = n;
+      st->eq_need = 0;
+      st->eq_zc = -1;
+      st->done_ctr = 0;
+      if (n > p.cap_gt) {
+        if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; }
+        else st->flags |= FLAG_INTERNAL;
+        st->cand_count = 0;
+      } else if (n < (uint32_t)p.K) {
+        const uint32_t need = (uint32_t)p.K - n;
+        uint32_t cum = 0;
+        int zc = -1;
+        for (int z = p.zlo; z < p.zhi; ++z) {
+          cum += p.eqcnt[z];
+          if (cum >= need) { zc = z; break; }
+        }
+        if (zc < 0) {  // the sampled bound was not valid (cannot happen) -> exact path
+          if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; st->cand_count = 0; }
+          else st->flags |= FLAG_INTERNAL;
+        } else {
+          st->eq_need = need;
+          st->eq_zc = zc;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final stage: exact K-th largest composite among the candidates, compaction, sort, write.
+// ---------------------------------------------------------------------------------------------
+constexpr int CAND_THREADS = 256;
+
+__global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
+    const unsigned long long* __restrict__ cand, DecodeState* st, uint32_t* ghist, int shift,
+    int bits, int first, int last, uint32_t cap_total, int K) {
+  __shared__ uint32_t s_hist[HIST_BINS];
+  __shared__ uint32_t s_sel[2];
+  __shared__ uint32_t s_ticket;
+  const uint32_t n = min(st->cand_count, cap_total);
+  const int hs = shift + bits;
+  const unsigned long long prefix = first ? 0ull : st->csel_prefix;
+  const uint32_t dmask = (1u << bits) - 1u;
+  for (int i = threadIdx.x; i < HIST_BINS; i += CAND_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
+    const unsigned long long c = cand[i];
+    if (first || (c >> hs) == prefix) atomicAdd(&s_hist[(uint32_t)(c >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (1 << bits); i += CAND_THREADS)
+    if (s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->done_ctr, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const uint32_t kleft = first ? (uint32_t)K : st->csel_kleft;
+  select_digit(ghist, 1 << bits, kleft, s_hist, s_sel);
+  if (threadIdx.x == 0) {
+    const unsigned long long np = (prefix << bits) | (unsigned long long)s_sel[0];
+    st->csel_prefix = np;
+    st->csel_kleft = s_sel[1];
+    if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
+    if (first) st->n_final = n;
+    if (last) { st->kth_comp = np; st->out_count = 0; }
+    st->done_ctr = 0;
+  }
+}
+
+__global__ void __launch_bounds__(CAND_THREADS) cand_compact_kernel(
+    const unsigned long long* __restrict__ cand, DecodeState* st, unsigned long long* out,
+    uint32_t cap_total, int K) {
+  const uint32_t n = min(st->cand_count, cap_total);
+  const unsigned long long kth = st->kth_comp;
+  for (uint32_t i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
+    const unsigned long long c = cand[i];
+    if (c >= kth) {
+      const uint32_t o = atomicAdd(&st->out_count, 1u);
+      if (o < (uint32_t)K) out[o] = c;
+    }
+  }
+}
+
+// One CTA: bitonic sort (descending) of K composites, then the pick writer
+// (decode.py:35-41 index arithmetic in fp32, :141-154 assembly).
+__global__ void __launch_bounds__(1024) sort_write_kernel(
+    unsigned long long* gbuf, int K, int npad, int use_smem, const float* __restrict__ heat,
+    const float* __restrict__ reg, int D, int H, int W, float* __restrict__ dets,
+    long long* __restrict__ inds) {
+  extern __shared__ unsigned long long s_keys[];
+  unsigned long long* a = use_smem ? s_keys : gbuf;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) a[i] = (i < K) ? gbuf[i] : 0ull;
+  } else {
+    for (int i = K + threadIdx.x; i < npad; i += blockDim.x) a[i] = 0ull;
+  }
+  __syncthreads();
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = a[i], y = a[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (x < y) : (x > y)) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const size_t n_vox = (size_t)D * H * W;
+  const int hw = H * W;
+  const float fhw = (float)hw, fw = (float)W;
+  for (int r = threadIdx.x; r < K; r += blockDim.x) {
+    const unsigned long long c = a[r];
+    const uint32_t key = (uint32_t)(c >> 32);
+    const uint32_t idx = ~(uint32_t)c;
+    float score;
+    if (key == KEY_ZERO) score = copysignf(0.0f, heat[idx]);   // heat*0 keeps the sign of heat
+    else score = key2f(key);
+    const float zf = floorf((float)idx / fhw);                  // decode.py:36 (fp32 division)
+    const int z = (int)zf;
+    const int t = (int)idx - z * hw;                            // decode.py:37 (int32)
+    const float yf = floorf((float)t / fw);                     // decode.py:38 (stays fp32)
+    int x = t % W;                                              // decode.py:39 (sign of divisor)
+    if (x < 0) x += W;
+    float xo, yo;
+    if (reg) { xo = (float)x + reg[idx]; yo = yf + reg[n_vox + idx]; }
+    else { xo = (float)x + 0.25f; yo = yf + 0.25f; }
+    float* d = dets + (size_t)r * 5;
+    d[0] = xo; d[1] = yo; d[2] = (float)z; d[3] = score; d[4] = score;
+    if (inds) inds[r] = (long long)idx;
+  }
+}
+
+__global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqcnt, int D,
+                                  uint32_t t0key) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    DecodeState z = {};
+    z.t0key = t0key;
+    z.eq_zc = -1;
+    *st = z;
+  }
+  if (i < HIST_BINS) hist[i] = 0;
+  for (int k = i; k < D; k += gridDim.x * blockDim.x) eqcnt[k] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone element-wise / reference-shaped ops
+// ---------------------------------------------------------------------------------------------
+__global__ void nms_full_kernel(const float* __restrict__ heat, float* __restrict__ out, int D,
+                                int H, int W, int pz, int py, int px, size_t total) {
+  const size_t n_vox = (size_t)D * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n_vox, r = i - b * n_vox;
+    const int x = (int)(r % W), y = (int)((r / W) % H), z = (int)(r / ((size_t)W * H));
+    const float* hb = heat + b * n_vox;
+    const float v = hb[r];
+    float m = -INFINITY;
+    bool nan = false;
+    for (int dz = -pz; dz <= pz; ++dz) {
+      const int zz = z + dz;
+      if (zz < 0 || zz >= D) continue;
+      for (int dy = -py; dy <= py; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -px; dx <= px; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= W) continue;
+          const float u = hb[((size_t)zz * H + yy) * W + xx];
+          nan |= (u != u);
+          m = fmaxf(m, u);
+        }
+      }
+    }
+    out[i] = (!nan && m == v) ? v : v * 0.0f;
+  }
+}
+
+__global__ void sigmoid_clamp_kernel(float* __restrict__ x, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float y = 1.0f / (1.0f + expf(-x[i]));
+    x[i] = fminf(fmaxf(y, 1e-4f), 1.0f - 1e-4f);
+  }
+}
+
+struct WsLayout {
+  size_t off_state, off_hist, off_eq, off_cand, off_out, total;
+  uint32_t cap_gt, cap_total;
+  int npad;
+};
+
+WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
+  WsLayout L;
+  const uint64_t n = (uint64_t)D * H * W;
+  uint64_t cap_gt = std::max<uint64_t>(1ull << 21, 256ull * (uint64_t)K);
+  if (n <= cap_gt) cap_gt = n;  // collect-all path
+  L.cap_gt = (uint32_t)cap_gt;
+  L.cap_total = (uint32_t)(cap_gt + (uint64_t)H * W + (uint64_t)K + 1024);
+  int npad = 2;
+  while (npad < K) npad <<= 1;
+  L.npad = npad;
+  size_t o = 0;
+  L.off_state = o; o = align_up(o + sizeof(DecodeState), 256);
+  L.off_hist = o;  o = align_up(o + HIST_BINS * sizeof(uint32_t), 256);
+  L.off_eq = o;    o = align_up(o + (size_t)D * sizeof(uint32_t), 256);
+  L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
+  L.off_out = o;   o = align_up(o + (size_t)npad * 8, 256);
+  L.total = o;
+  return L;
+}
+
+template <int P>
+int launch_scan(const ScanParams& p, int grid, cudaStream_t s) {
+  constexpr int ROWS = TY + 2 * P;
+  const size_t smem = (size_t)2 * ROWS * PITCH * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CETPICK_CUDA(cudaFuncSetAttribute(scan_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    attr_done = true;
+  }
+  scan_kernel<P><<<grid, SCAN_THREADS, smem, s>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+int launch_scan_p(int P, const ScanParams& p, int grid, cudaStream_t s) {
+  switch (P) {
+    case 0: return launch_scan<0>(p, grid, s);
+    case 1: return launch_scan<1>(p, grid, s);
+    case 2: return launch_scan<2>(p, grid, s);
+    case 3: return launch_scan<3>(p, grid, s);
+  }
+  return CETPICK_ERR_BAD_ARG;
+}
+
+int scan_grid(int D, int H, int W, int zlo, int zhi, int* ZC_out) {
+  const int slots = num_sms() * 2;
+  const long long xy = (long long)ceil_div(W, TX) * ceil_div(H, TY);
+  const int nz = std::max(1, zhi - zlo);
+  // planes per work item: as long as possible (halo planes are re-read) while keeping >= 4 items
+  // per resident CTA slot
+  int zc = MAX_ZC;
+  while (zc > 4 && xy * ceil_div(nz, zc) < 4LL * slots) zc >>= 1;
+  zc = std::min(zc, nz);
+  *ZC_out = std::max(1, zc);
+  const long long items = xy * ceil_div(nz, *ZC_out);
+  (void)D;
+  return (int)std::max<long long>(1, std::min<long long>(items, slots));
+}
+
+}  // namespace
+
+int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int nms_mode,
+               const float* reg, float* dets, long long* inds, void* ws, cudaStream_t s) {
+  const WsLayout L = ws_layout(D, H, W, K);
+  char* base = static_cast<char*>(ws);
+  DecodeState* st = reinterpret_cast<DecodeState*>(base + L.off_state);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + L.off_hist);
+  uint32_t* eqcnt = reinterpret_cast<uint32_t*>(base + L.off_eq);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(base + L.off_cand);
+  unsigned long long* outb = reinterpret_cast<unsigned long long*>(base + L.off_out);
+  const uint64_t n = (uint64_t)D * H * W;
+  const int P = (nms_mode == CETPICK_NMS_NONE) ? 0 : (kernel_xy - 1) / 2;
+  const bool collect_all = (n <= L.cap_gt);
+
+  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u);
+  CETPICK_LAUNCH_CHECK();
+
+  ScanParams p = {};
+  p.heat = heat; p.D = D; p.H = H; p.W = W;
+  p.nms_mode = nms_mode; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand;
+  p.cap_gt = L.cap_gt; p.cap_total = L.cap_total;
+  p.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
+  const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
+
+  auto run_select = [&](int zlo, int zhi, int gate) -> int {
+    for (int pass = 0; pass < 3; ++pass) {
+      ScanParams q = p;
+      q.mode = MODE_HIST; q.zlo = zlo; q.zhi = zhi; q.gate = gate;
+      q.shift = shifts[pass]; q.bits = nbits[pass]; q.last_pass = (pass == 2);
+      q.k_select = (uint32_t)K;
+      const int grid = scan_grid(D, H, W, zlo, zhi, &q.ZC);
+      int rc = launch_scan_p(P, q, grid, s);
+      if (rc) return rc;
+    }
+    return CETPICK_OK;
+  };
+  auto run_collect = [&](int gate, int phase, int all) -> int {
+    ScanParams q = p;
+    q.mode = MODE_COLLECT; q.zlo = 0; q.zhi = D; q.gate = gate; q.phase = phase; q.collect_all = all;
+    const int grid = scan_grid(D, H, W, 0, D, &q.ZC);
+    return launch_scan_p(P, q, grid, s);
+  };
+
+  int rc;
+  if (collect_all) {
+    if ((rc = run_collect(0, 1, 1))) return rc;
+  } else {
+    // sample: a centred z-range holding >= max(4K, N/64) voxels (>= K is what exactness needs)
+    const uint64_t hw = (uint64_t)H * W;
+    uint64_t want = std::max<uint64_t>(4ull * (uint64_t)K, n / 64);
+    int sp = (int)std::min<uint64_t>((uint64_t)D, ceil_div<uint64_t>(want, hw));
+    sp = std::max(sp, 1);
+    const int zlo = (D - sp) / 2, zhi = zlo + sp;
+    if ((rc = run_select(zlo, zhi, 0))) return rc;
+    if ((rc = run_collect(0, 0, 0))) return rc;
+    // exact fallback (device-gated): full-volume select, then COLLECT again
+    if ((rc = run_select(0, D, 1))) return rc;
+    if ((rc = run_collect(1, 1, 0))) return rc;
+  }
+  {  // EQ pass (device-gated on eq_need)
+    ScanParams q = p;
+    q.mode = MODE_EQ; q.zlo = 0; q.zhi = D; q.gate = 0;
+    const int grid = scan_grid(D, H, W, 0, D, &q.ZC);
+    if ((rc = launch_scan_p(P, q, grid, s))) return rc;
+  }
+  {  // exact K-th composite: digits 11,11,10 over the key and 11,11,10 over ~index
+    const int cs[6] = {53, 42, 32, 21, 10, 0}, cb[6] = {11, 11, 10, 11, 11, 10};
+    const int grid = std::min<int>(num_sms() * 2, std::max<uint32_t>(1, ceil_div<uint32_t>(L.cap_total, CAND_THREADS * 8)));
+    for (int i = 0; i < 6; ++i) {
+      cand_hist_kernel<<<grid, CAND_THREADS, 0, s>>>(cand, st, hist, cs[i], cb[i], i == 0, i == 5,
+                                                     L.cap_total, K);
+      CETPICK_LAUNCH_CHECK();
+    }
+    cand_compact_kernel<<<grid, CAND_THREADS, 0, s>>>(cand, st, outb, L.cap_total, K);
+    CETPICK_LAUNCH_CHECK();
+  }
+  {
+    const int use_smem = L.npad <= SORT_SMEM_MAX;
+    const size_t smem = use_smem ? (size_t)L.npad * 8 : 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+      CETPICK_CUDA(cudaFuncSetAttribute(sort_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        SORT_SMEM_MAX * 8));
+      attr_done = true;
+    }
+    sort_write_kernel<<<1, 1024, smem, s>>>(outb, K, L.npad, use_smem, heat, reg, D, H, W, dets, inds);
+    CETPICK_LAUNCH_CHECK();
+  }
+  return CETPICK_OK;
+}
+
+}  // namespace cetpick
+
+using namespace cetpick;
+
+extern "C" int cetpick_decode_workspace_bytes(int64_t D, int64_t H, int64_t W, int K, size_t* bytes) {
+  if (!bytes || D <= 0 || H <= 0 || W <= 0 || K <= 0) return CETPICK_ERR_BAD_ARG;
+  if ((uint64_t)D * H * W > 0x7fffffffull || (uint64_t)K > (uint64_t)D * H * W) return CETPICK_ERR_BAD_ARG;
+  *bytes = ws_layout(D, H, W, K).total;
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64_t H, int64_t W,
+                                  int kernel_xy, int K, int nms_mode, const float* reg, float* dets,
+                                  int64_t* inds, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  if (!heat || !dets || B <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0) return CETPICK_ERR_BAD_ARG;
+  const uint64_t n = (uint64_t)D * H * W;
+  if (n > 0x7fffffffull || (uint64_t)K > n) return CETPICK_ERR_BAD_ARG;   // torch.topk raises too
+  if (nms_mode < CETPICK_NMS_NONE || nms_mode > CETPICK_NMS_FIBER) return CETPICK_ERR_BAD_ARG;
+  if (nms_mode != CETPICK_NMS_NONE) {
+    if (kernel_xy < 1 || (kernel_xy & 1) == 0) return CETPICK_ERR_BAD_ARG;  // even k breaks the reference
+    if (kernel_xy > 7) return CETPICK_ERR_UNSUPPORTED;
+    if (nms_mode == CETPICK_NMS_FIBER && kernel_xy != 3) return CETPICK_ERR_UNSUPPORTED;
+  }
+  const WsLayout L = ws_layout(D, H, W, K);
+  if (!ws || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return CETPICK_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int64_t b = 0; b < B; ++b) {
+    int rc = decode_one(heat + b * n, (int)D, (int)H, (int)W, kernel_xy, K, nms_mode,
+                        reg ? reg + b * 2 * n : nullptr, dets + b * (int64_t)K * 5,
+                        inds ? reinterpret_cast<long long*>(inds) + b * K : nullptr, ws, s);
+    if (rc) return rc;
+  }
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_candidates) {
+  if (!ws) return CETPICK_ERR_BAD_ARG;
+  DecodeState h;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CETPICK_CUDA(cudaMemcpyAsync(&h, ws, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CETPICK_CUDA(cudaStreamSynchronize(s));
+  if (flags) *flags = (int)h.flags;
+  if (n_candidates) *n_candidates = (int64_t)h.n_final;
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_nms_f32(const float* heat, float* out, int64_t B, int64_t D, int64_t H,
+                               int64_t W, int kernel, int mode, void* stream) {
+  g_launches = 0;
+  if (!heat || !out || B <= 0 || D <= 0 || H <= 0 || W <= 0) return CETPICK_ERR_BAD_ARG;
+  if (kernel < 1 || (kernel & 1) == 0) return CETPICK_ERR_BAD_ARG;
+  const int p = (kernel - 1) / 2;
+  int pz, py, px;
+  if (mode == CETPICK_NMS_3D) { pz = 1; py = px = p; }
+  else if (mode == CETPICK_NMS_XY) { pz = 0; py = px = p; }
+  else if (mode == CETPICK_NMS_Z) { pz = p; py = px = 0; }
+  else return CETPICK_ERR_BAD_ARG;
+  const size_t total = (size_t)B * D * H * W;
+  const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)num_sms() * 16);
+  nms_full_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(heat, out, (int)D, (int)H, (int)W,
+                                                                      pz, py, px, total);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_sigmoid_clamp_f32(float* x, int64_t n, void* stream) {
+  g_launches = 0;
+  if (!x || n < 0) return CETPICK_ERR_BAD_ARG;
+  if (n == 0) return CETPICK_OK;
+  const int grid = (int)std::min<size_t>(ceil_div<size_t>((size_t)n, 256), (size_t)num_sms() * 16);
+  sigmoid_clamp_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (size_t)n);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}

@@ -1,0 +1,107 @@
+"""Mirror of cet_pick/models/decode.py: same names, arguments and return shapes; the arithmetic
+runs in libcetpick_sm100a.so (csrc/decode.cu).  Tie order is (score desc, linear index asc)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _check_heat(heat: torch.Tensor, what: str):
+    _lib.require_cuda(heat, what)
+    if heat.dim() != 5 or heat.dtype != torch.float32:
+        raise ValueError(f"{what}: expected a (B,C,D,H,W) float32 tensor, got {tuple(heat.shape)} {heat.dtype}")
+    return heat.contiguous()
+
+
+def _nms_generic(heat, kernel, mode, what):
+    heat = _check_heat(heat, what)
+    B, Cc, D, H, W = heat.shape
+    out = torch.empty_like(heat)
+    _lib.check(_lib.lib().cetpick_nms_f32(heat.data_ptr(), out.data_ptr(), B * Cc, D, H, W, int(kernel), mode,
+                                          _lib.stream_ptr()), what)
+    return out
+
+
+def _nms(heat, kernel=3):
+    """decode.py:27-33: heat * (max_pool3d(heat,(3,k,k)) == heat)."""
+    return _nms_generic(heat, kernel, _lib.NMS_3D, "_nms")
+
+
+def _nms_xy(heat, kernel=3):
+    """decode.py:11-17."""
+    return _nms_generic(heat, kernel, _lib.NMS_XY, "_nms_xy")
+
+
+def _nms_z(heat, kernel=3):
+    """decode.py:19-25."""
+    return _nms_generic(heat, kernel, _lib.NMS_Z, "_nms_z")
+
+
+def _decode_call(heat, kernel, K, nms_mode, reg, want_inds, what):
+    heat = _check_heat(heat, what)
+    B, Cc, D, H, W = heat.shape
+    if Cc != 1:
+        raise ValueError(f"{what}: the reference's .view(batch, K) needs one heat-map channel, got {Cc}")
+    K = int(K)
+    if reg is not None:
+        _lib.require_cuda(reg, what)
+        if tuple(reg.shape) != (B, 2, D, H, W):
+            raise ValueError(f"{what}: reg must be (B,2,D,H,W)")
+        reg = reg.float().contiguous()
+    L = _lib.lib()
+    nbytes = C.c_size_t(0)
+    _lib.check(L.cetpick_decode_workspace_bytes(D, H, W, K, C.byref(nbytes)), what)
+    ws = _workspace(heat.device, nbytes.value)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    dets = torch.empty((B, K, 5), dtype=torch.float32, device=heat.device)
+    inds = torch.empty((B, K), dtype=torch.int64, device=heat.device) if want_inds else None
+    _lib.check(L.cetpick_decode_f32(heat.data_ptr(), B, D, H, W, int(kernel), K, nms_mode,
+                                    reg.data_ptr() if reg is not None else None, dets.data_ptr(),
+                                    inds.data_ptr() if inds is not None else None, ws_ptr,
+                                    ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()), what)
+    return dets, inds
+
+
+def _topk(scores, K=900):
+    """decode.py:82-92: top-K of the flattened map -> (scores (B,1,K), zs, ys, xs, inds (B,K)).
+    zs/xs int32, ys float32 exactly like _convert_1d_to_3d (decode.py:35-41)."""
+    dets, inds = _decode_call(scores, 1, K, _lib.NMS_NONE, None, True, "_topk")
+    B = dets.shape[0]
+    xs = (dets[:, :, 0] - 0.25).to(torch.int32)
+    ys = dets[:, :, 1] - 0.25
+    zs = dets[:, :, 2].to(torch.int32)
+    return dets[:, :, 3].reshape(B, 1, K).contiguous(), zs, ys, xs, inds
+
+
+def tomo_decode(heat, kernel=3, reg=None, K=900, if_fiber=False):
+    """decode.py:123-155: (B,1,D,H,W) -> (B,K,5) rows [x+0.25|x+reg0, y+0.25|y+reg1, z, score, score]."""
+    mode = _lib.NMS_FIBER if if_fiber else _lib.NMS_3D
+    dets, _ = _decode_call(heat, kernel, K, mode, reg, False, "tomo_decode")
+    return dets
+
+
+def decode_status(device=None):
+    """(flags, n_candidates) of the last decode on the current stream (synchronises)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    ws = _ws_cache.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    if ws is None:
+        return 0, 0
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    flags, n = C.c_int(0), C.c_int64(0)
+    _lib.check(_lib.lib().cetpick_decode_status(ws_ptr, _lib.stream_ptr(), C.byref(flags), C.byref(n)),
+               "decode_status")
+    return flags.value, n.value

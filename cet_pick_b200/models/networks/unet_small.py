@@ -1,0 +1,170 @@
+"""Host-side mirror of cet_pick/models/networks/unet_small.py (TomoConvUNet) for the default
+detector.  The nn.Module below is ONLY a container with the reference's parameter names, shapes,
+registration order and initialisers (so state_dicts and seeded random init are interchangeable
+with the reference); its forward() runs entirely in libcetpick_sm100a.so (csrc/unet.cu,
+csrc/conv_tc.cu).  There is no PyTorch/CPU forward path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from ... import _lib
+
+
+class _DownParams(nn.Module):
+    """Parameters of unet.py:198-249 DownConv(dim=2, normalization='batch', full_norm=True)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1, bias=False)
+        self.norm0 = nn.BatchNorm2d(cout)
+        self.norm1 = nn.BatchNorm2d(cout)
+
+
+class _UpParams(nn.Module):
+    """Parameters of unet.py:319-399 UpConv(merge_mode='concat', up_mode='transpose', dim=2)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.upconv = nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2)
+        self.conv1 = nn.Conv2d(2 * cout, cout, 3, padding=1, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1, bias=False)
+        self.norm0 = nn.BatchNorm2d(cout)
+        self.norm1 = nn.BatchNorm2d(cout)
+        self.norm2 = nn.BatchNorm2d(cout)
+
+
+class _UNetParams(nn.Module):
+    """Parameters of unet.py:538-859 UNet(16, 32, n_blocks, start_filts=32, dim=2)."""
+
+    def __init__(self, n_blocks):
+        super().__init__()
+        self.down_convs = nn.ModuleList()
+        self.up_convs = nn.ModuleList()
+        outs = 16
+        for i in range(n_blocks):
+            ins = 16 if i == 0 else outs
+            outs = 32 * (2 ** i)
+            self.down_convs.append(_DownParams(ins, outs))
+        for i in range(n_blocks - 1):
+            ins = outs
+            outs = ins // 2
+            self.up_convs.append(_UpParams(ins, outs))
+        self.conv_final = nn.Conv2d(outs, 32, kernel_size=1)
+        self.apply(self._weight_init)          # unet.py:850-859
+
+    @staticmethod
+    def _weight_init(m):
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            nn.init.xavier_normal_(m.weight)
+            if getattr(m, "bias") is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class TomoConvUNet(nn.Module):
+    """unet_small.py:30-97.  forward(x) -> [ {'hm': (B,1,D,h,w), 'proj': (B,C,D,h,w)} ]."""
+
+    def __init__(self, n_blocks, heads, head_conv, last_k=3):
+        super().__init__()
+        self.heads = heads
+        self.n_blocks = n_blocks
+        self.head_conv = head_conv
+        self.conv1 = nn.Conv2d(1, 16, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(16)
+        self.unet = _UNetParams(n_blocks)
+        self.feature_head = nn.Sequential(
+            nn.Conv3d(32, head_conv, (3, 3, 3), dilation=(1, 4, 4), padding=(1, 4, 4), bias=False),
+            nn.Identity(),   # ReLU slot (keeps the reference's index 2 for the second conv)
+            nn.Conv3d(head_conv, head_conv, (3, 3, 3), dilation=(1, 4, 4), padding=(1, 4, 4), bias=False),
+            nn.Identity())
+        for m in self.feature_head:                              # fill_fc_weights, unet_small.py:17-28
+            if isinstance(m, nn.Conv3d):
+                nn.init.normal_(m.weight, std=0.001)
+        for head, classes in self.heads.items():
+            fc = nn.Conv3d(head_conv, classes, kernel_size=(3, 1, 1), padding=(1, 0, 0), bias=False)
+            nn.init.normal_(fc.weight, std=0.001)
+            setattr(self, head, fc)
+        self.compute_proj = "proj" in heads      # detectors switch this off (they never read 'proj')
+        self.fuse_sigmoid = False                # TomodetDetector fuses _sigmoid into the hm epilogue
+        self._plan = None
+        self._plan_key = None
+        self._ws = None
+
+    # ------------------------------------------------------------------ plan management
+    def _param_key(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
+
+    def _destroy_plan(self):
+        if self._plan is not None:
+            _lib.lib().cetpick_unet_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def plan(self):
+        """(Re)build the device plan when the parameters changed: BN folding + bf16 packing."""
+        key = self._param_key()
+        if self._plan is not None and key == self._plan_key:
+            return self._plan
+        self._destroy_plan()
+        if self.heads.get("hm", 1) != 1:
+            raise NotImplementedError("cet_pick_b200: the hm head must have one class (opts.py:286-289)")
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.cetpick_unet_create(C.byref(h), self.n_blocks, self.head_conv,
+                                         int(self.heads.get("proj", 0))), "cetpick_unet_create")
+        for k, v in self.state_dict().items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            t = v.detach().to("cpu", torch.float32).contiguous()
+            _lib.check(L.cetpick_unet_set_param(h, k.encode(), t.data_ptr(), t.numel()), f"set_param({k})")
+        _lib.check(L.cetpick_unet_finalize(h), "cetpick_unet_finalize")
+        self._plan, self._plan_key = h, key
+        return h
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x):
+        _lib.require_cuda(x, "TomoConvUNet.forward")
+        if x.dim() > 4:
+            x = x.squeeze()                                   # unet_small.py:64-65
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        b, d, h, w = x.shape
+        x = x.to(torch.float32).contiguous()
+        plan = self.plan()
+        L = _lib.lib()
+        oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        nbytes = C.c_size_t(0)
+        _lib.check(L.cetpick_unet_workspace_bytes(plan, d, h, w, 0, C.byref(nbytes)), "unet_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nbytes.value or self._ws.device != x.device:
+            self._ws = None
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        hm = torch.empty((b, 1, d, oh, ow), dtype=torch.float32, device=x.device)
+        pc = int(self.heads.get("proj", 0))
+        proj = torch.empty((b, pc, d, oh, ow), dtype=torch.float32, device=x.device) \
+            if (self.compute_proj and pc > 0) else None
+        self.last_launches = 0
+        for i in range(b):
+            _lib.check(L.cetpick_unet_forward(plan, x[i].data_ptr(), d, h, w, hm[i].data_ptr(),
+                                              1 if self.fuse_sigmoid else 0,
+                                              proj[i].data_ptr() if proj is not None else None,
+                                              self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                       "cetpick_unet_forward")
+            self.last_launches += L.cetpick_last_launch_count()
+        ret = {"hm": hm}
+        if proj is not None:
+            ret["proj"] = proj
+        return [ret]
+
+
+def get_tomo_unet_small(num_layers, heads, head_conv=32, last_k=3, local_path=None):
+    """unet_small.py:189-193."""
+    return TomoConvUNet(num_layers, heads, head_conv, last_k)

@@ -1,0 +1,145 @@
+/*
+ * cetpick.h -- C ABI of libcetpick_sm100a.so, the B200-native localisation hot path of
+ * MiLoPYP / cet_pick (refinement-step inference: detector forward + heat-map decode).
+ *
+ * This is the drop-in boundary.  The reference is pure Python/PyTorch and
+ * has no FFI of its own; each entry point below replaces the PyTorch operator sequence of the
+ * reference function it cites, and is what a ctypes binding inside the reference would call
+ * (see INTEGRATION.md).  Conventions:
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless named *_host;
+ *   - the caller owns every input / output / workspace buffer; the library owns only plan objects;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     the host except cetpick_unet_finalize (one-off weight upload) and cetpick_decode_status;
+ *   - return value 0 = CETPICK_OK, negative = error (cetpick_strerror).
+ *   - there is no CPU fallback: without a CUDA device every compute call returns
+ *     CETPICK_ERR_CUDA.
+ */
+#ifndef CETPICK_H
+#define CETPICK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CETPICK_ABI_VERSION 1
+
+enum {
+  CETPICK_OK = 0,
+  CETPICK_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, K > D*H*W, even NMS kernel ... */
+  CETPICK_ERR_UNSUPPORTED = -2,  /* valid in the reference but not built          */
+  CETPICK_ERR_WORKSPACE = -3,    /* workspace pointer null / too small / misaligned               */
+  CETPICK_ERR_CUDA = -4,         /* CUDA runtime / driver error (no device, launch failure)       */
+  CETPICK_ERR_STATE = -5,        /* plan not finalized / missing parameter                        */
+  CETPICK_ERR_SHAPE = -6         /* parameter tensor has the wrong number of elements             */
+};
+
+int cetpick_version(void);
+const char* cetpick_strerror(int code);
+/* last CUDA error string seen by the calling thread's most recent failing call ("" if none) */
+const char* cetpick_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Heat-map decode.  Replaces cet_pick/models/decode.py:
+ *   tomo_decode  (decode.py:123-155)  = _nms / (_nms_xy -> _nms_z) -> _topk -> _convert_1d_to_3d
+ *                                        -> (+0.25 | + reg gather) -> cat
+ *   _nms (:27-33), _nms_xy (:11-17), _nms_z (:19-25), _topk (:82-92), _convert_1d_to_3d (:35-41),
+ *   and models/utils.py:171-193 (_transpose_and_gather_feat) for `reg`.
+ * Tie order (unspecified by torch.topk) is fixed to (score descending, linear index ascending).
+ * ------------------------------------------------------------------------------------------ */
+
+/* nms_mode values */
+#define CETPICK_NMS_NONE  0   /* plain top-K of the map (decode.py:82-92 `_topk`)                  */
+#define CETPICK_NMS_3D    1   /* (3,k,k) max-pool NMS (decode.py:27-33 `_nms`)                      */
+#define CETPICK_NMS_FIBER 2   /* (1,k,k) then (k,1,1) on the suppressed map (decode.py:126-128)     */
+
+/* bytes of device workspace cetpick_decode_f32 needs for one (D,H,W) map and K picks */
+int cetpick_decode_workspace_bytes(int64_t D, int64_t H, int64_t W, int K, size_t* bytes);
+
+/*
+ * heat : (B,1,D,H,W) float32, contiguous.      reg : NULL or (B,2,D,H,W) float32.
+ * dets : (B,K,5) float32 out, rows [x+0.25 | x+reg0, y+0.25 | y+reg1, z, score, score] with the
+ *        reference's fp32 index arithmetic (wrong-by-design for linear indices >= 2^24).
+ * inds : NULL or (B,K) int64 out, linear indices (decode.py:87).
+ * kernel_xy : odd, 1..7 (opt.nms).  nms_mode : CETPICK_NMS_*.  FIBER needs kernel_xy == 3.
+ * ws   : >= cetpick_decode_workspace_bytes bytes, 256-byte aligned; reused across the batch.
+ */
+int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64_t H, int64_t W,
+                       int kernel_xy, int K, int nms_mode, const float* reg,
+                       float* dets, int64_t* inds, void* ws, size_t ws_bytes, void* stream);
+
+/* Status of the most recent decode that used `ws` (synchronises `stream`).
+ * flags bit0: heat contained NaN (reference raises ValueError later, tomo_det.py:64-65; picks are
+ *             unspecified); bit1: the sampled threshold overflowed the candidate buffer and the
+ *             exact full-volume select ran (slower, still exact).
+ * n_candidates: entries the final select saw. */
+int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_candidates);
+
+/* Full NMS map (decode.py:11-33): out = heat * (maxpool(heat) == heat).  mode: CETPICK_NMS_3D
+ * ((3,k,k)), 3 = xy only ((1,k,k), `_nms_xy`), 4 = z only ((k,1,1), `_nms_z`). */
+#define CETPICK_NMS_XY 3
+#define CETPICK_NMS_Z  4
+int cetpick_nms_f32(const float* heat, float* out, int64_t B, int64_t D, int64_t H, int64_t W,
+                    int kernel, int mode, void* stream);
+
+/* models/utils.py:167-169 `_sigmoid`: x <- clamp(sigmoid(x), 1e-4, 1-1e-4), in place. */
+int cetpick_sigmoid_clamp_f32(float* x, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Detector forward.  Replaces TomoConvUNet.forward (cet_pick/models/networks/unet_small.py:63-97)
+ * with its UNet trunk (models/networks/unet.py:198-249, 319-399, 861-886), as built by
+ * create_model('unet_N', heads, head_conv) (models/model.py:65-70).
+ * Arithmetic: BF16 operands on tcgen05 tensor cores, FP32 accumulation, BatchNorm (eval) folded
+ * into the convolution weights/bias, ReLU / bias / concat / pixel-shuffle fused in the epilogues.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cetpick_unet cetpick_unet;
+
+/* n_blocks: 4 for unet_4, 5 for unet_5 (2..6).  head_conv: channels of feature_head (32).
+ * proj_channels: classes of the 'proj' head (0 = head absent). */
+int cetpick_unet_create(cetpick_unet** plan, int n_blocks, int head_conv, int proj_channels);
+void cetpick_unet_destroy(cetpick_unet* plan);
+
+/* Hand over one tensor of the reference state_dict, by its key, as host
+ * float32 in PyTorch's native layout.  Keys ending in num_batches_tracked are ignored. */
+int cetpick_unet_set_param(cetpick_unet* plan, const char* key, const float* data_host,
+                           int64_t numel);
+
+/* Fold BatchNorm, repack to the tensor-core layouts and upload.  Synchronous. */
+int cetpick_unet_finalize(cetpick_unet* plan);
+
+int cetpick_unet_workspace_bytes(const cetpick_unet* plan, int64_t D, int64_t H, int64_t W,
+                                 int want_proj, size_t* bytes);
+
+/*
+ * tomo : (D,H,W) float32 device (the reference's (1,D,H,W) input with b == 1).
+ * hm   : (D,h,w) float32 out, h = floor((H-1)/2)+1, w likewise (the 'hm' head, (1,1,D,h,w)).
+ *        apply_sigmoid != 0 fuses models/utils.py:167-169 `_sigmoid` into the head epilogue.
+ * proj : NULL or (C,D,h,w) float32 out, the L2-normalised 'proj' head ((1,C,D,h,w)).
+ */
+int cetpick_unet_forward(cetpick_unet* plan, const float* tomo, int64_t D, int64_t H, int64_t W,
+                         float* hm, int apply_sigmoid, float* proj,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
+ * enqueued (bench.py's gpu_launches). */
+int64_t cetpick_last_launch_count(void);
+
+/* Self-test of the tcgen05 implicit-GEMM building block: C[M,N] = A[M,K] * B[N,K]^T (bf16 in,
+ * fp32 out) on device buffers; used by tests to validate descriptors in isolation. */
+int cetpick_selftest_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K,
+                               void* stream);
+
+/* Test hook: ONE convolution through the tcgen05 implicit-GEMM kernel with caller-packed bf16
+ * weights [k-block][Ntot][KC] (k-block = (source, tap, channel chunk)); taps = ntaps x (dz,dy,dx).
+ * epi: 0 bf16 NHWC, 1 ConvTranspose 2x2 scatter, 2 fp32 row-major, 3 fp32 L2-normalised NCDHW. */
+int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void* src1, int C1, int NIMG,
+                      int H, int W, const void* wpk, int KC, int ntaps, const int* taps, int Ntot,
+                      const float* bias, int relu, int epi, void* out, int out_cstride,
+                      int Ho, int Wo, int Cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CETPICK_H */

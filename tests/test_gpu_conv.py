@@ -1,0 +1,136 @@
+"""The tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) against torch fp32 convolutions on the
+same bf16-rounded operands (floating point => torch fp32 reference; tolerance stated per test)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from cet_pick_b200 import _lib
+    return _lib
+
+
+def pack(w, nsrc, csrc, kc):
+    """(Cout, nsrc*csrc, ntaps) -> [k-block][Cout][KC], k-block = (source, tap, chunk)."""
+    cout, cin, ntaps = w.shape
+    chunks = csrc // kc
+    out = torch.empty((nsrc * ntaps * chunks, cout, kc), dtype=w.dtype, device=w.device)
+    for s in range(nsrc):
+        for t in range(ntaps):
+            for ch in range(chunks):
+                lo = s * csrc + ch * kc
+                out[(s * ntaps + t) * chunks + ch] = w[:, lo:lo + kc, t]
+    return out.contiguous()
+
+
+def run_conv(L, srcs, wpk, kc, taps, ntot, bias, relu, epi, out, cstride=0, Ho=0, Wo=0, Cout=0):
+    n, h, w, _ = srcs[0].shape
+    tp = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
+    rc = L.lib().cetpick_conv_bf16(len(srcs), srcs[0].data_ptr(), srcs[0].shape[3],
+                                   srcs[1].data_ptr() if len(srcs) > 1 else None,
+                                   srcs[1].shape[3] if len(srcs) > 1 else 0, n, h, w, wpk.data_ptr(), kc,
+                                   len(taps), tp, ntot, bias.data_ptr() if bias is not None else None,
+                                   int(relu), epi, out.data_ptr(), cstride, Ho, Wo, Cout, L.stream_ptr())
+    L.check(rc, "cetpick_conv_bf16")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 16), (256, 32, 32), (384, 64, 64), (256, 128, 128),
+                                   (128, 256, 192), (640, 48, 96), (256, 32, 16)])
+def test_gemm_selftest(L, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    kc = 64 if K % 64 == 0 else 32 if K % 32 == 0 else 16
+    Bp = pack(B.view(N, K, 1), 1, K, kc)
+    Cm = torch.full((M, N), float("nan"), device="cuda")
+    L.check(L.lib().cetpick_selftest_gemm_bf16(A.data_ptr(), Bp.data_ptr(), Cm.data_ptr(), M, N, K,
+                                               L.stream_ptr()), "selftest")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (Cm - ref).abs().max().item()
+    assert err <= 1e-3 * K ** 0.5 + 1e-4, err      # fp32 accumulation-order noise only
+
+
+TAPS3 = [(0, ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 16, 16, 32), (3, 13, 21, 32, 32), (2, 19, 35, 64, 64),
+                                            (1, 9, 17, 128, 128), (1, 5, 7, 256, 256), (2, 24, 40, 32, 64)])
+def test_conv3x3_bias_relu(L, n, h, w, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    kc = min(64, cin)
+    wpk = pack(wt.reshape(cout, cin, 9), 1, cin, kc)
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run_conv(L, [x], wpk, kc, TAPS3, cout, b, True, L.EPI_BF16_NHWC, out, cstride=cout)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1)).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, err      # one bf16 rounding of O(1) outputs (2^-8 relative) + accumulation order
+
+
+def test_conv3x3_two_sources_is_concat(L):
+    n, h, w, c = 2, 11, 18, 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    s = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(c, 2 * c, 3, 3, device="cuda", generator=g) / (3 * (2 * c) ** 0.5)).bfloat16()
+    wpk = pack(wt.reshape(c, 2 * c, 9), 2, c, 32)
+    out = torch.full((n, h, w, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run_conv(L, [a, s], wpk, 32, TAPS3, c, None, False, L.EPI_BF16_NHWC, out, cstride=c)
+    xin = torch.cat((a, s), 3).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wt.float(), padding=1).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("cin,cout,h,w,Ho,Wo", [(64, 32, 6, 9, 12, 18), (256, 128, 5, 7, 9, 13), (128, 64, 4, 4, 7, 8)])
+def test_upconv_2x2_scatter_with_autocrop(L, cin, cout, h, w, Ho, Wo):
+    n = 2
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cin, cout, 2, 2, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    kc = min(64, cin)
+    # rows j = (dy*2+dx)*cout + co ; B[j][ci] = w[ci][co][dy][dx]
+    Bm = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1).contiguous()
+    wpk = pack(Bm, 1, cin, kc)
+    out = torch.full((n, Ho, Wo, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run_conv(L, [x], wpk, kc, [(0, 0, 0)], 4 * cout, b.repeat(4).contiguous(), True, L.EPI_UPCONV_2X2, out,
+             Ho=Ho, Wo=Wo, Cout=cout)
+    ref = F.relu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2))[:, :, :Ho, :Wo]
+    assert (out.float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 2e-2
+
+
+def test_conv3d_dilated_27_taps(L):
+    d, h, w, c = 5, 20, 27, 32
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(d, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(c, c, 3, 3, 3, device="cuda", generator=g) / (27 * c) ** 0.5).bfloat16()
+    taps = [(kz - 1, 4 * (ky - 1), 4 * (kx - 1)) for kz in range(3) for ky in range(3) for kx in range(3)]
+    wpk = pack(wt.reshape(c, c, 27), 1, c, 32)
+    out = torch.full((d, h, w, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+    run_conv(L, [x], wpk, 32, taps, c, None, True, L.EPI_BF16_NHWC, out, cstride=c)
+    xin = x.float().permute(3, 0, 1, 2)[None]
+    ref = F.relu(F.conv3d(xin, wt.float(), padding=(1, 4, 4), dilation=(1, 4, 4)))[0].permute(1, 2, 3, 0)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+def test_proj_head_l2norm_ncdhw(L):
+    d, h, w, c = 4, 9, 14, 32
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(d, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(32, c, 3, 1, 1, device="cuda", generator=g) / (3 * c) ** 0.5).bfloat16()
+    taps = [(kz - 1, 0, 0) for kz in range(3)]
+    wpk = pack(wt.reshape(32, c, 3), 1, c, 32)
+    out = torch.full((32, d, h, w), float("nan"), device="cuda")
+    run_conv(L, [x], wpk, 32, taps, 32, None, False, L.EPI_F32_L2NORM_NCDHW, out)
+    ref = F.normalize(F.conv3d(x.float().permute(3, 0, 1, 2)[None], wt.float(), padding=(1, 0, 0)), dim=1)[0]
+    assert (out - ref).abs().max().item() <= 1e-4
