@@ -24,6 +24,7 @@ SIGNATURES = {
     "cetpick_decode_workspace_bytes": (_int, [_i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "cetpick_decode_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cetpick_decode_status": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_i64)]),
+    "cetpick_decode_debug_state": (_int, [_vp, _vp, _vp]),
     "cetpick_nms_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "cetpick_sigmoid_clamp_f32": (_int, [_vp, _i64, _vp]),
     "cetpick_unet_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
@@ -33,6 +34,8 @@ SIGNATURES = {
     "cetpick_unet_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_last_launch_count": (_i64, []),
+    "cetpick_profile_enable": (_int, [_int]),
+    "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
     "cetpick_selftest_gemm_bf16": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
@@ -87,3 +90,21 @@ def require_cuda(t, what: str):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def profile_forward(fn):
+    """Run fn() (one or more cetpick_unet_forward calls) with per-launch CUDA-event timing and return
+    [(name, ms, flops)] of the LAST forward."""
+    L = lib()
+    L.cetpick_profile_enable(1)
+    try:
+        fn()
+        n = C.c_int(0)
+        ms = (C.c_float * 256)()
+        fl = (C.c_double * 256)()
+        names = C.create_string_buffer(256 * 32)
+        check(L.cetpick_profile_read(256, C.byref(n), ms, fl, names), "cetpick_profile_read")
+        return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i]), float(fl[i]))
+                for i in range(n.value)]
+    finally:
+        L.cetpick_profile_enable(0)

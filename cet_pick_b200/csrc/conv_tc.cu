@@ -344,7 +344,10 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    CETPICK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cudaFuncAttributes fa;
+    CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel));
+    CETPICK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)fa.sharedSizeBytes));
     attr_done = true;
   }
   const int grid = (int)std::min<long long>(p.total_tiles, num_sms());

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float c = cur.c[j][k];
-            const float m3 = fmaxf(fmaxf(prev.a[j][k], cur.a[j][k]), nxt.a[j][k]);
+            // NMS_NONE (plain top-K) has no z neighbourhood at all
+            const float m3 = znbr ? fmaxf(fmaxf(prev.a[j][k], cur.a[j][k]), nxt.a[j][k]) : cur.a[j][k];
             const bool valid = (y0 + ty * 4 + j < H) && (x0 + tx * 4 + k < W);
             uint32_t ok = (c == m3) ? f2key(c) : KEY_ZERO;
             saw_nan |= valid && (c != c);
@@ -833,6 +834,14 @@ extern "C" int cetpick_decode_status(const void* ws, void* stream, int* flags, i
   CETPICK_CUDA(cudaStreamSynchronize(s));
   if (flags) *flags = (int)h.flags;
   if (n_candidates) *n_candidates = (int64_t)h.n_final;
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out16) {
+  if (!ws || !out16) return CETPICK_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CETPICK_CUDA(cudaMemcpyAsync(out16, ws, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CETPICK_CUDA(cudaStreamSynchronize(s));
   return CETPICK_OK;
 }
 

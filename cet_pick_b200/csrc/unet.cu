@@ -166,6 +166,24 @@ struct PackedConv {
   double flops_per_pixel = 0;    // 2 * K * N
 };
 
+// Optional per-launch timing (CUDA events on the launching stream) for bench.py's roofline.
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> names;
+  std::vector<double> flops;
+  int n = 0;
+  void begin() { n = 0; names.clear(); flops.clear(); }
+  void mark(const char* name, double fl, cudaStream_t st) {
+    if (!on) return;
+    if ((int)ev.size() <= n) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    cudaEventRecord(ev[n], st);
+    names.push_back(name); flops.push_back(fl);
+    ++n;
+  }
+};
+Profiler g_prof;
+
 uint16_t f2bf(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -307,8 +325,9 @@ WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W) {
   return p;
 }
 
-int run_conv(const cetpick_unet* m, const PackedConv& pc, const void* s0, const void* s1, int NIMG, int H,
-             int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st) {
+int run_conv(const cetpick_unet* m, const char* name, const PackedConv& pc, const void* s0, const void* s1,
+             int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st) {
+  g_prof.mark(name, pc.flops_per_pixel * (double)NIMG * H * W, st);
   ConvLaunch L;
   L.nsrc = pc.nsrc; L.src[0] = s0; L.src[1] = s1; L.C[0] = pc.C[0]; L.C[1] = pc.C[1];
   L.NIMG = NIMG; L.H = H; L.W = W;
@@ -470,6 +489,8 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
 
   // stem -> X0 (16 channels)
   {
+    g_prof.begin();
+    g_prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
     const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
     const int grid = (int)std::min<long long>(tiles, (long long)sms * 8);
     stem_kernel<<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
@@ -480,10 +501,11 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   // encoder: level i: in Y0 -> conv1 -> Y1 -> conv2 -> Y2 (skip) -> pool -> next level's Y0
   for (int i = 0; i < nb; ++i) {
     const int h = dims[i].h, w = dims[i].w;
-    if ((rc = run_conv(m, m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
-    if ((rc = run_conv(m, m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc down.conv1", m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc down.conv2", m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st))) return rc;
     if (i < nb - 1) {
       const int C = 32 << i;
+      g_prof.mark("pool2x2", 0.0, st);
       const size_t total = (size_t)D * dims[i + 1].h * dims[i + 1].w * (C / 8);
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
       pool2x2_kernel<<<grid, 256, 0, st>>>(buf(i, 2), D, h, w, C, buf(i + 1, 0));
@@ -495,25 +517,49 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   for (int i = 0; i < nb - 1; ++i) {
     const int j = nb - 2 - i;
     const int h = dims[j].h, w = dims[j].w, Cout = 32 << j;
-    if ((rc = run_conv(m, m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
-    if ((rc = run_conv(m, m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
-    if ((rc = run_conv(m, m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc up.upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc up.conv1", m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc up.conv2", m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
     below = buf(j, 0);
   }
   const int h0 = dims[0].h, w0 = dims[0].w;
   // conv_final (1x1 + bias): X0 -> X1 ; feature_head: X1 -> X0 -> X1 (3-D, z = image axis)
-  if ((rc = run_conv(m, m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, m->fh2, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "conv_tc conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "conv_tc feature_head.0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "conv_tc feature_head.2", m->fh2, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
   {
     const size_t plane = (size_t)h0 * w0, total = plane * D;
+    g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
     const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
     hm_head_kernel<<<grid, 256, 0, st>>>(buf(0, 1), D, plane, reinterpret_cast<const float*>(blob + m->hm_w),
                                          apply_sigmoid, hm);
     CETPICK_LAUNCH_CHECK();
   }
   if (proj) {
-    if ((rc = run_conv(m, m->proj, buf(0, 1), nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "conv_tc proj", m->proj, buf(0, 1), nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
+  }
+  g_prof.mark("end", 0.0, st);
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_profile_enable(int on) {
+  g_prof.on = on != 0;
+  return CETPICK_OK;
+}
+
+// Per-launch device times of the most recent profiled cetpick_unet_forward (synchronises).
+extern "C" int cetpick_profile_read(int max_entries, int* n, float* ms, double* flops, char* names32) {
+  if (!n) return CETPICK_ERR_BAD_ARG;
+  const int cnt = std::max(0, g_prof.n - 1);
+  *n = cnt;
+  if (cnt == 0) return CETPICK_OK;
+  CETPICK_CUDA(cudaEventSynchronize(g_prof.ev[g_prof.n - 1]));
+  for (int i = 0; i < cnt && i < max_entries; ++i) {
+    float t = 0.f;
+    CETPICK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = g_prof.flops[i];
+    if (names32) { strncpy(names32 + (size_t)i * 32, g_prof.names[i].c_str(), 31); names32[(size_t)i * 32 + 31] = 0; }
   }
   return CETPICK_OK;
 }

@@ -105,3 +105,17 @@ def decode_status(device=None):
     _lib.check(_lib.lib().cetpick_decode_status(ws_ptr, _lib.stream_ptr(), C.byref(flags), C.byref(n)),
                "decode_status")
     return flags.value, n.value
+
+
+def decode_debug_state(device=None):
+    """First 16 words of the device-side decode state (diagnostics)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    ws = _ws_cache.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    if ws is None:
+        return None
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    out = (C.c_uint32 * 16)()
+    _lib.check(_lib.lib().cetpick_decode_debug_state(ws_ptr, _lib.stream_ptr(), out), "decode_debug_state")
+    names = ["t0key", "sel_prefix", "sel_kleft", "flags", "cand_count", "n_gt", "need_fallback", "eq_need",
+             "eq_zc", "done_ctr", "csel_kleft", "out_count"]
+    return {n: int(out[i]) for i, n in enumerate(names)}

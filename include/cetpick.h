@@ -77,6 +77,10 @@ int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64_t H, int64
  * n_candidates: entries the final select saw. */
 int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_candidates);
 
+/* Diagnostics: the first 16 words of the decode state block in `ws` (t0key, select prefix, rank
+ * left, flags, candidate count, n_gt, need_fallback, eq_need, eq_zc, ...).  Synchronises. */
+int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out16);
+
 /* Full NMS map (decode.py:11-33): out = heat * (maxpool(heat) == heat).  mode: CETPICK_NMS_3D
  * ((3,k,k)), 3 = xy only ((1,k,k), `_nms_xy`), 4 = z only ((k,1,1), `_nms_z`). */
 #define CETPICK_NMS_XY 3
@@ -125,6 +129,12 @@ int cetpick_unet_forward(cetpick_unet* plan, const float* tomo, int64_t D, int64
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);
+
+/* Per-launch timing of cetpick_unet_forward with CUDA events on the launching stream (bench.py's
+ * roofline).  enable(1), run a forward, then read(): n entries of (milliseconds, algorithmic FLOPs,
+ * 32-byte name) in launch order.  read() synchronises; profiling adds one event per launch. */
+int cetpick_profile_enable(int on);
+int cetpick_profile_read(int max_entries, int* n, float* ms, double* flops, char* names32);
 
 /* Self-test of the tcgen05 implicit-GEMM building block: C[M,N] = A[M,K] * B[N,K]^T (bf16 in,
  * fp32 out) on device buffers; used by tests to validate descriptors in isolation. */

@@ -148,6 +148,18 @@ def test_oracle_medium_plateau_eq_path(dec, do):
     assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, 2000)))
 
 
+def test_topk_plain_full_ranking(dec, do):
+    """_topk has no NMS: the full descending ranking (K == N) of a random map must match."""
+    D, H, W = 9, 24, 40
+    hm = synth.heatmap_tiefree_np(D, H, W, 44)[None, None]
+    K = D * H * W
+    ts, zs, ys, xs, ti = dec._topk(cu(hm), K=K)
+    rs, rz, ry, rx, ri = do.topk(hm, K)
+    assert np.array_equal(ti.cpu().numpy(), ri)
+    assert np.array_equal(bits(ts.cpu().numpy()[:, 0]), bits(rs))
+    assert np.array_equal(zs.cpu().numpy(), rz) and np.array_equal(xs.cpu().numpy(), rx)
+
+
 def test_fallback_exact_select(dec, do):
     """adversarial map for the sampled bound: plain top-K (every voxel is a candidate) with a
     low-valued sample region -> candidate overflow -> exact full-volume select (flag bit1)."""
@@ -159,7 +171,7 @@ def test_fallback_exact_select(dec, do):
     rs, rz, ry, rx, ri = do.topk(hm, 700)
     assert np.array_equal(ti.cpu().numpy(), ri) and np.array_equal(bits(ts.cpu().numpy()[:, 0]), bits(rs))
     flags, _ = dec.decode_status()
-    assert flags & 2
+    assert flags & 2, dec.decode_debug_state()
 
 
 def test_bad_arguments(dec):
