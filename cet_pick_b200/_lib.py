@@ -37,6 +37,7 @@ SIGNATURES = {
     "cetpick_profile_enable": (_int, [_int]),
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
     "cetpick_selftest_gemm_bf16": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
+    "cetpick_probe_umma": (_int, [_vp, _int, _vp, _int, _int, _int, _int, _vp, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
 }

@@ -1,0 +1,112 @@
+// Hardware probe (test hook, not on the product path): which shifted / strided shared-memory
+// descriptors does tcgen05.mma accept for a TMA-written, hardware-swizzled K-major tile?
+// One CTA: TMA-load A_big[R][KC] and B[32][KC], then D[128][32] = A_big[rows(m)] * B^T with the A
+// descriptor starting `r0` rows into the tile, 8-row groups `sbo_bytes` apart and the given
+// base_offset field.  The answers decide how conv_tc.cu may reuse one halo tile for several taps.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace cetpick {
+namespace {
+
+struct alignas(64) ProbeParams {
+  CUtensorMap tmA, tmB;
+  int R, KC, r0, sbo, base_offset, layout_type;
+  float* out;
+};
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ ProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full, bar_done;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.R * p.KC * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar_full, 1); ptx::mbar_init(&bar_done, 1); ptx::fence_barrier_init(); }
+  if (warp == 1) { ptx::tmem_alloc(&s_tmem, 32); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(&bar_full, (uint32_t)(p.R + 32) * p.KC * 2);
+    for (int r = 0; r < p.R; r += 128)   // TMA boxes are limited to 256 rows: load in 128-row boxes
+      ptx::tma_load_2d(sA + (size_t)r * p.KC * 2, &p.tmA, &bar_full, 0, r);
+    ptx::tma_load_2d(sB, &p.tmB, &bar_full, 0, 0);
+    ptx::mbar_wait(&bar_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 32);
+    for (int k = 0; k < p.KC / 16; ++k) {
+      uint64_t da = ptx::make_smem_desc(ptx::smem_u32(sA) + p.r0 * p.KC * 2 + k * 32, p.sbo, p.layout_type);
+      da |= (uint64_t)(p.base_offset & 7) << 49;
+      const uint64_t db = ptx::make_smem_desc(ptx::smem_u32(sB) + k * 32, 16u * p.KC, p.layout_type);
+      ptx::umma_bf16(tmem, da, db, idesc, k > 0);
+    }
+    ptx::umma_commit(&bar_done);
+  }
+  __syncwarp();
+  ptx::mbar_wait(&bar_done, 0);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t v[16];
+    __syncwarp();
+    ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    ptx::tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) p.out[(size_t)threadIdx.x * 32 + c0 + i] = __uint_as_float(v[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 32);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+}  // namespace
+}  // namespace cetpick
+
+using namespace cetpick;
+
+extern "C" int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,
+                                  int base_offset, float* out, void* stream) {
+  if (!A_big || !B || !out || R < 128 || (R % 128) || (KC != 16 && KC != 32 && KC != 64)) return CETPICK_ERR_BAD_ARG;
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess || !f)
+    return CETPICK_ERR_CUDA;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(f);
+  ProbeParams p;
+  memset(&p, 0, sizeof(p));
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
+  cuuint32_t es[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)R};
+    cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 128};
+    if (enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A_big), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return CETPICK_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)KC, 32};
+    cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 32};
+    if (enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(B), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return CETPICK_ERR_CUDA;
+  }
+  p.R = R; p.KC = KC; p.r0 = r0; p.sbo = sbo_bytes; p.base_offset = base_offset;
+  p.layout_type = KC == 64 ? 2 : KC == 32 ? 4 : 6;
+  p.out = out;
+  const size_t smem = (size_t)(R + 32) * KC * 2 + 2048;
+  CETPICK_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}

@@ -191,12 +191,15 @@ def tomogram_torch(D: int, H: int, W: int, seed: int = 0, device="cuda", out=Non
         out = torch.empty((D, H, W), dtype=torch.float32, device=device)
     s = (seed * 0xD1342543DE82EF95) & _M64
     s = s - (1 << 64) if s >= (1 << 63) else s
-    hw = H * W
-    base = torch.arange(hw, dtype=torch.int64, device=device)
-    for z in range(D):
-        bits = _mix64_t(base + (z * hw + s))
+    flat = out.view(-1)
+    n = D * H * W
+    step = 1 << 26
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        bits = _mix64_t(torch.arange(lo, hi, dtype=torch.int64, device=device) + s)
         k = ((bits >> 8) & 63) + ((bits >> 20) & 63) + ((bits >> 32) & 63) + ((bits >> 44) & 63)
-        out[z] = (k.to(torch.float32) / 255.0).view(H, W)
+        flat[lo:hi] = k.to(torch.float32) / 255.0
+        del bits, k
     return out
 
 

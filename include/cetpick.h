@@ -149,6 +149,11 @@ int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void* src1, int 
                       const float* bias, int relu, int epi, void* out, int out_cstride,
                       int Ho, int Wo, int Cout, void* stream);
 
+/* Hardware probe (test hook): D[128][32] = A_big[rows] * B^T where the A descriptor starts r0 rows
+ * into a TMA-written swizzled tile, with 8-row groups sbo_bytes apart and the given base_offset. */
+int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,
+                       int base_offset, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
