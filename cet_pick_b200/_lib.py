@@ -13,6 +13,7 @@ OK = 0
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_STATE, ERR_SHAPE = -1, -2, -3, -4, -5, -6
 NMS_NONE, NMS_3D, NMS_FIBER, NMS_XY, NMS_Z = 0, 1, 2, 3, 4
 EPI_BF16_NHWC, EPI_UPCONV_2X2, EPI_F32_ROWMAJOR, EPI_F32_L2NORM_NCDHW = 0, 1, 2, 3
+MARCH_2D_ROWS, MARCH_3D_PLANES = 0, 1
 
 _i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
 
@@ -38,6 +39,8 @@ SIGNATURES = {
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
     "cetpick_selftest_gemm_bf16": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
     "cetpick_probe_umma": (_int, [_vp, _int, _vp, _int, _int, _int, _int, _vp, _vp]),
+    "cetpick_conv_march_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
+                                       _vp, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
 }

@@ -1,0 +1,439 @@
+// "Marching" convolution on tcgen05 tensor cores (sm_100a) for the narrow layers of the detector
+// (Cout = 32 / 64; 2/3 of the network's FLOPs): cet_pick/models/networks/unet.py:127-145 (3x3
+// Conv2d of DownConv / UpConv) and unet_small.py:39-46 (feature_head Conv3d, dilation (1,4,4)).
+//
+// Why not a plain implicit GEMM: with N = Cout = 32 every UMMA re-reads its 4 KB A operand from
+// shared memory for 16 cycles of tensor work (the 128 B/clk shared-memory port allows ~40 % of
+// peak), and every tap re-fetches the activation tile from L2.  Here the kernel marches along one
+// axis (y for the 2-D convs, z for the 3-D ones).  The three taps along that axis are stacked on
+// the GEMM N dimension:
+//     input row i contributes to output rows i-1, i, i+1 with weights W[+1], W[0], W[-1]
+//  => ONE UMMA  D[128 px, 3*Cout] += A[128 px, 16 ch] * [W[+1]; W[0]; W[-1]]^T        (N = 96 / 192)
+// whose three column blocks are the accumulators of three different output rows, kept in a ring
+// of TMEM slots.  Each input row (2-D: 1 x (128+2) pixels; 3-D: a (16+2d) x (8*MT+2d) plane tile)
+// is loaded by TMA exactly once per strip, the in-step taps (dx, or (dy,dx)) are shifted UMMA
+// descriptors into that one tile, and all weights stay resident in shared memory.  An accumulator
+// slot is complete when the row after it has been consumed; the epilogue warps drain it
+// (bias, ReLU, bf16, NHWC store), write zeros back and hand the slot to the MMA thread again, so
+// every UMMA accumulates and no instruction needs a per-column-block "first touch" flag.
+//
+// Roles (384 threads, 1 CTA/SM, persistent over strips):
+//   warp 0: TMA producer   warp 1: UMMA issuer   warp 2: TMEM allocator   warps 4-11: epilogue
+#include "conv_march.cuh"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace cetpick {
+
+namespace {
+
+constexpr int MARCH_THREADS = 384;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_SLOTS = 16;
+constexpr int MAX_MT = 2;
+constexpr int TMEM_COLS = 512;
+
+struct alignas(64) MarchParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  int mode, dil, nsrc, chunks, KC, k16s, T, MT, S;
+  int NIMG, H, W;
+  int L, R, nchunk;        // march extent, rows per strip, strips along the march axis
+  int nxb;                 // tile columns (2-D: x blocks per row; 3-D: x tiles per plane)
+  long long total_strips;
+  int stages, stage_bytes, box_bytes;
+  int nblk, wblk_bytes;    // weight blocks (source, chunk, tap) and bytes of one
+  int sbo_a, sbo_b, layout_type;
+  int a_off[MAX_MT][9];    // byte offset of the A operand of (M-tile, in-step tap) inside a stage
+  int relu;
+  const float* bias;
+  __nv_bfloat16* out;
+};
+
+struct Strip { int ma, mb, x0, y0, img; };
+
+__device__ __forceinline__ void decode_strip(const MarchParams& p, long long k, Strip& s) {
+  const int ch = (int)(k % p.nchunk);
+  k /= p.nchunk;
+  s.ma = ch * p.R;
+  s.mb = min(s.ma + p.R, p.L);
+  const int bx = (int)(k % p.nxb);
+  k /= p.nxb;
+  if (p.mode == MARCH_2D_ROWS) { s.x0 = bx * 128 * p.MT; s.y0 = 0; s.img = (int)k; }
+  else { s.x0 = bx * 8 * p.MT; s.y0 = (int)k * 16; s.img = 0; }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ float s_bias[COUT];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + (((size_t)p.nblk * p.wblk_bytes + 1023) & ~(size_t)1023);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmA[0]);
+    if (p.nsrc > 1) ptx::prefetch_tensormap(&p.tmA[1]);
+    ptx::prefetch_tensormap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < p.S; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * p.MT); }
+    ptx::mbar_init(&bar_w, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&s_tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  if (warp == 3)
+    for (int c = lane; c < COUT; c += 32) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp >= 4) {   // all accumulator slots start at zero: every UMMA accumulates
+    const uint32_t row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp - 4) >> 2) * 256);
+    for (int c = 0; c < 256; c += 16) ptx::tmem_st16_fill(row + c, 0u);
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bar_w, (uint32_t)(p.nblk * p.wblk_bytes));
+      for (int b = 0; b < p.nblk; ++b)
+        ptx::tma_load_2d(sW + (size_t)b * p.wblk_bytes, &p.tmB, &bar_w, 0, b * 3 * COUT);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
+        Strip s;
+        decode_strip(p, k, s);
+        const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
+        for (int i = i_lo; i <= i_hi; ++i)
+          for (int src = 0; src < p.nsrc; ++src)
+            for (int c = 0; c < p.chunks; ++c) {
+              ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
+              ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)p.box_bytes);
+              uint8_t* dst = sA + (size_t)stage * p.stage_bytes;
+              if (p.mode == MARCH_2D_ROWS)
+                ptx::tma_load_4d(dst, &p.tmA[src], &bar_full[stage], c * p.KC, s.x0 - 1, i, s.img);
+              else
+                ptx::tma_load_4d(dst, &p.tmA[src], &bar_full[stage], c * p.KC, s.x0 - p.dil, s.y0 - p.dil, i);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ UMMA issuer =================================
+    if (lane == 0) {
+      uint32_t idesc[4];
+      for (int n = 1; n <= 3; ++n) idesc[n] = ptx::make_idesc_bf16(128, n * COUT);
+      const uint32_t sW_u32 = ptx::smem_u32(sW), sA_u32 = ptx::smem_u32(sA);
+      const uint32_t slot_bytes = (uint32_t)(COUT * p.KC * 2);   // one output row's block of B rows
+      const uint32_t smask = (uint32_t)p.S - 1u;
+      int sshift = 0;
+      while ((1 << sshift) < p.S) ++sshift;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t q0 = 0, q_touched = 0;
+      ptx::mbar_wait(&bar_w, 0);
+      for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
+        Strip s;
+        decode_strip(p, k, s);
+        const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
+        for (int i = i_lo; i <= i_hi; ++i) {
+          const int r_lo = max(s.ma, i - 1), r_hi = min(s.mb - 1, i + 1);
+          const uint32_t q_lo = q0 + (uint32_t)(r_lo - s.ma);
+          const int n = r_hi - r_lo + 1;
+          while (q_touched < q_lo + (uint32_t)n) {    // rows touched for the first time: slot must be drained
+            ptx::mbar_wait(&bar_aempty[q_touched & smask], ((q_touched >> sshift) & 1u) ^ 1u);
+            ++q_touched;
+          }
+          ptx::tc_fence_after();
+          const uint32_t s_lo = q_lo & smask;
+          const int n1 = min(n, p.S - (int)s_lo), n2 = n - n1;     // ring wrap splits the column range
+          const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * slot_bytes, boff2 = boff1 + (uint32_t)n1 * slot_bytes;
+          for (int src = 0; src < p.nsrc; ++src)
+            for (int c = 0; c < p.chunks; ++c) {
+              ptx::mbar_wait(&bar_full[stage], phase);
+              ptx::tc_fence_after();
+              const uint32_t a0 = sA_u32 + (uint32_t)(stage * p.stage_bytes);
+              const uint32_t w0 = sW_u32 + (uint32_t)((src * p.chunks + c) * p.T * p.wblk_bytes);
+              for (int t = 0; t < p.MT; ++t) {
+                const uint32_t d1 = tmem_base + (uint32_t)((t * p.S + (int)s_lo) * COUT);
+                const uint32_t d2 = tmem_base + (uint32_t)(t * p.S * COUT);
+                for (int j = 0; j < p.T; ++j) {
+                  const uint32_t aj = a0 + (uint32_t)p.a_off[t][j];
+                  const uint32_t wj = w0 + (uint32_t)(j * p.wblk_bytes);
+                  for (int kk = 0; kk < p.k16s; ++kk) {
+                    const uint64_t da = ptx::make_smem_desc(aj + kk * 32, (uint32_t)p.sbo_a, p.layout_type);
+                    ptx::umma_bf16(d1, da, ptx::make_smem_desc(wj + boff1 + kk * 32, (uint32_t)p.sbo_b, p.layout_type),
+                                   idesc[n1], 1u);
+                    if (n2)
+                      ptx::umma_bf16(d2, da, ptx::make_smem_desc(wj + boff2 + kk * 32, (uint32_t)p.sbo_b, p.layout_type),
+                                     idesc[n2], 1u);
+                  }
+                }
+              }
+              ptx::umma_commit(&bar_empty[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+          // rows that have now seen all three of their input rows
+          if (i - 1 >= s.ma) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - 1 - s.ma)) & smask]);
+          if (i == p.L - 1 && i < s.mb) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - s.ma)) & smask]);
+        }
+        q0 += (uint32_t)(s.mb - s.ma);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int quad = warp & 3, eg = (warp - 4) >> 2;
+    const int m = quad * 32 + lane;
+    const uint32_t smask = (uint32_t)p.S - 1u;
+    int sshift = 0;
+    while ((1 << sshift) < p.S) ++sshift;
+    uint32_t q0 = 0;
+    for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
+      Strip s;
+      decode_strip(p, k, s);
+      for (int r = s.ma; r < s.mb; ++r) {
+        const uint32_t q = q0 + (uint32_t)(r - s.ma);
+        const uint32_t slot = q & smask, par = (q >> sshift) & 1u;
+        for (int t = 0; t < p.MT; ++t) {
+          if ((int)((q * (uint32_t)p.MT + (uint32_t)t) & 1u) != eg) continue;
+          ptx::mbar_wait(&bar_afull[slot], par);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
+          uint32_t v[COUT];
+          __syncwarp();
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 16) ptx::tmem_ld16(taddr + c0, v + c0);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c0 = 0; c0 < COUT; c0 += 16) ptx::tmem_st16_fill(taddr + c0, 0u);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bar_aempty[slot]);
+
+          int x, y, z;
+          if (p.mode == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
+          else { x = s.x0 + t * 8 + (m & 7); y = s.y0 + (m >> 3); z = r; }
+          if (x < p.W && y < p.H) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 8) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[i] = __uint_as_float(v[c0 + i]) + s_bias[c0 + i];
+                if (p.relu) f[i] = fmaxf(f[i], 0.f);
+              }
+              uint4 w;
+              w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+              w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+              dst[c0 / 8] = w;
+            }
+          }
+        }
+      }
+      q0 += (uint32_t)(s.mb - s.ma);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int smem_limit() { return 227 * 1024; }
+
+}  // namespace
+
+bool march_supported(int mode, int C, int nsrc, int Cout) {
+  if (Cout != 32 && Cout != 64) return false;
+  if (C != 16 && C != 32 && C != 64) return false;
+  if (nsrc < 1 || nsrc > 2) return false;
+  if (mode == MARCH_3D_PLANES && (C != 32 || nsrc != 1 || Cout != 32)) return false;
+  const int T = mode == MARCH_2D_ROWS ? 3 : 9;
+  const size_t wbytes = align_up((size_t)nsrc * T * 3 * Cout * C * 2, 1024);
+  const size_t stage = mode == MARCH_2D_ROWS ? align_up((size_t)130 * std::min(C, 64) * 2, 1024) : (size_t)24 * 24 * 64;
+  return wbytes + 3 * stage + 4096 <= (size_t)smem_limit();   // weights + >= 3 activation stages
+}
+
+std::vector<uint16_t> march_pack_weights(int mode, const float* w, int Cout, int nsrc, int C, const double* scale) {
+  const int KC = std::min(C, 64), chunks = C / KC, T = mode == MARCH_2D_ROWS ? 3 : 9;
+  const int Cin = nsrc * C, ktot = 3 * T;     // kernel volume: 9 (ky,kx) or 27 (kz,ky,kx)
+  std::vector<uint16_t> out((size_t)nsrc * chunks * T * 3 * Cout * KC);
+  for (int s = 0; s < nsrc; ++s)
+    for (int c = 0; c < chunks; ++c)
+      for (int j = 0; j < T; ++j) {
+        const size_t b = ((size_t)s * chunks + c) * T + j;
+        for (int slot = 0; slot < 3; ++slot)
+          for (int co = 0; co < Cout; ++co)
+            for (int k = 0; k < KC; ++k) {
+              const int ci = s * C + c * KC + k;
+              const int km = 2 - slot;                // kernel index along the march axis
+              const int kidx = km * T + j;            // (ky, kx) or (kz, ky*3+kx): march axis is outermost
+              const double v = (double)w[((size_t)co * Cin + ci) * ktot + kidx] * (scale ? scale[co] : 1.0);
+              out[((b * 3 + slot) * Cout + co) * KC + k] = f2bf_host((float)v);
+            }
+      }
+  return out;
+}
+
+int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
+  if (!march_supported(L.mode, L.C, L.nsrc, L.Cout)) return CETPICK_ERR_UNSUPPORTED;
+  if (!L.src[0] || (L.nsrc > 1 && !L.src[1]) || !L.wpk || !L.out || L.NIMG <= 0 || L.H <= 0 || L.W <= 0)
+    return CETPICK_ERR_BAD_ARG;
+  if (L.mode == MARCH_3D_PLANES && (L.dil < 1 || L.dil > 4)) return CETPICK_ERR_UNSUPPORTED;
+
+  MarchParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = L.mode; p.dil = L.dil; p.nsrc = L.nsrc;
+  p.KC = std::min(L.C, 64);
+  p.chunks = L.C / p.KC;
+  p.k16s = p.KC / 16;
+  p.T = L.mode == MARCH_2D_ROWS ? 3 : 9;
+  p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
+  p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
+  p.layout_type = p.KC == 64 ? 2 : p.KC == 32 ? 4 : 6;
+  const int pix = p.KC * 2;                       // bytes of one pixel's channel chunk = swizzle span
+  p.sbo_b = 8 * pix;
+  p.nblk = L.nsrc * p.chunks * p.T;
+  p.wblk_bytes = 3 * L.Cout * pix;
+
+  int BX, BY;
+  long long base_strips;
+  if (L.mode == MARCH_2D_ROWS) {
+    p.MT = 1;
+    BX = 128 * p.MT + 2; BY = 1;
+    p.L = L.H;
+    p.nxb = ceil_div(L.W, 128 * p.MT);
+    base_strips = (long long)p.nxb * L.NIMG;
+    p.sbo_a = 8 * pix;
+    for (int t = 0; t < p.MT; ++t)
+      for (int j = 0; j < 3; ++j) p.a_off[t][j] = (t * 128 + j) * pix;
+  } else {
+    p.MT = (L.W > 8) ? 2 : 1;
+    BX = 8 * p.MT + 2 * L.dil; BY = 16 + 2 * L.dil;
+    p.L = L.NIMG;
+    p.nxb = ceil_div(L.W, 8 * p.MT);
+    base_strips = (long long)p.nxb * ceil_div(L.H, 16);
+    p.sbo_a = BX * pix;
+    for (int t = 0; t < p.MT; ++t)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) p.a_off[t][ky * 3 + kx] = ((ky * L.dil) * BX + kx * L.dil + t * 8) * pix;
+  }
+  p.S = std::min(MAX_SLOTS, TMEM_COLS / (p.MT * L.Cout));
+  p.box_bytes = BX * BY * pix;
+  p.stage_bytes = (int)align_up((size_t)p.box_bytes, 1024);
+  const size_t wtot = align_up((size_t)p.nblk * p.wblk_bytes, 1024);
+
+  // strips along the march axis: enough strips to balance the persistent grid, few enough that the
+  // two extra input rows per strip stay cheap
+  const int sms = num_sms();
+  int best_n = 1;
+  double best_eff = -1.0;
+  for (int n = 1; n <= std::max(1, p.L / 8); ++n) {
+    const int R = ceil_div(p.L, n);
+    if (ceil_div(p.L, R) != n) continue;
+    const long long strips = base_strips * n;
+    const double waves = (double)ceil_div<long long>(strips, sms);
+    const double eff = ((double)strips / (waves * sms)) * ((double)R / (R + 2));
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_n = n; }
+  }
+  p.nchunk = best_n;
+  p.R = ceil_div(p.L, best_n);
+  p.total_strips = base_strips * p.nchunk;
+
+  static int static_smem[2] = {-1, -1};
+  const int ti = L.Cout == 32 ? 0 : 1;
+  if (static_smem[ti] < 0) {
+    cudaFuncAttributes fa;
+    if (L.Cout == 32) {
+      CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_march_kernel<32>));
+      CETPICK_CUDA(cudaFuncSetAttribute(conv_march_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem_limit() - (int)fa.sharedSizeBytes));
+    } else {
+      CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_march_kernel<64>));
+      CETPICK_CUDA(cudaFuncSetAttribute(conv_march_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem_limit() - (int)fa.sharedSizeBytes));
+    }
+    static_smem[ti] = (int)fa.sharedSizeBytes;
+  }
+  const size_t avail = (size_t)smem_limit() - static_smem[ti] - 1024 - wtot;
+  p.stages = (int)std::min<size_t>(MAX_STAGES, avail / p.stage_bytes);
+  if (p.stages < 2) return CETPICK_ERR_UNSUPPORTED;
+  const size_t smem = 1024 + wtot + (size_t)p.stages * p.stage_bytes;
+
+  int rc;
+  for (int s = 0; s < L.nsrc; ++s) {
+    const uint64_t C = (uint64_t)L.C;
+    const uint64_t dims[4] = {C, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.NIMG};
+    const uint64_t strides[3] = {C * 2, C * 2 * L.W, C * 2 * (uint64_t)L.W * L.H};
+    const uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)BX, (uint32_t)BY, 1};
+    if ((rc = tmap_encode_bf16(&p.tmA[s], L.src[s], 4, dims, strides, box, p.KC))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)p.KC, (uint64_t)p.nblk * 3 * L.Cout};
+    const uint64_t strides[1] = {(uint64_t)pix};
+    const uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)(3 * L.Cout)};
+    if ((rc = tmap_encode_bf16(&p.tmB, L.wpk, 2, dims, strides, box, p.KC))) return rc;
+  }
+  const int grid = (int)std::min<long long>(p.total_strips, sms);
+  if (L.Cout == 32) conv_march_kernel<32><<<grid, MARCH_THREADS, smem, stream>>>(p);
+  else conv_march_kernel<64><<<grid, MARCH_THREADS, smem, stream>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+}  // namespace cetpick
+
+using namespace cetpick;
+
+// Test hook: one marching convolution from a PyTorch-layout fp32 host weight (packs, uploads,
+// launches, synchronises, frees) -- tests/test_gpu_conv.py.
+extern "C" int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
+                                       int NIMG, int H, int W, const float* w_host, int Cout,
+                                       const float* bias, int relu, void* out, void* stream) {
+  g_launches = 0;
+  if (!w_host) return CETPICK_ERR_BAD_ARG;
+  if (!march_supported(mode, C, nsrc, Cout)) return CETPICK_ERR_UNSUPPORTED;
+  std::vector<uint16_t> pk = march_pack_weights(mode, w_host, Cout, nsrc, C, nullptr);
+  void* d = nullptr;
+  CETPICK_CUDA(cudaMalloc(&d, pk.size() * 2));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = CETPICK_OK;
+  if (cudaMemcpyAsync(d, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = CETPICK_ERR_CUDA;
+  if (rc == CETPICK_OK) {
+    MarchLaunch L;
+    L.mode = mode; L.dil = dil; L.nsrc = nsrc; L.src[0] = src0; L.src[1] = src1; L.C = C;
+    L.NIMG = NIMG; L.H = H; L.W = W; L.wpk = d; L.Cout = Cout; L.bias = bias; L.relu = relu; L.out = out;
+    rc = conv_march_launch(L, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_march");
+  return rc;
+}

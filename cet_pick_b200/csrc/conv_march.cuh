@@ -1,0 +1,43 @@
+// Host-side description of one "marching" convolution launch (conv_march.cu): the kernel used for
+// the narrow layers (Cout 32 / 64) of the detector, 2-D 3x3 and 3-D 3x3x3 dilated (1,d,d).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace cetpick {
+
+enum MarchMode {
+  MARCH_2D_ROWS = 0,    // Conv2d 3x3 pad 1 per image: march along y, M-tile = 128 pixels of one row
+  MARCH_3D_PLANES = 1   // Conv3d 3x3x3 dilation (1,d,d) pad (1,d,d): march along z, M-tile = 8 x 16 (x,y)
+};
+
+struct MarchLaunch {
+  int mode = MARCH_2D_ROWS;
+  int dil = 1;              // in-plane dilation of the 3-D mode (4 for feature_head)
+  int nsrc = 1;             // two sources of equal C = torch.cat((up, skip), 1) (unet.py:390)
+  const void* src[2] = {nullptr, nullptr};   // bf16 [NIMG][H][W][C]
+  int C = 0;                // channels per source: 16 / 32 / 64
+  int NIMG = 0, H = 0, W = 0;
+  const void* wpk = nullptr;    // device, layout of march_pack_weights()
+  int Cout = 0;             // 32 or 64
+  const float* bias = nullptr;  // [Cout] fp32 or null
+  int relu = 0;
+  void* out = nullptr;      // bf16 [NIMG][H][W][Cout]
+};
+
+// True when conv_march_launch supports (mode, C per source, nsrc, Cout): weights must fit in shared
+// memory next to the activation ring.
+bool march_supported(int mode, int C, int nsrc, int Cout);
+
+// Pack a PyTorch-layout weight into the kernel's shared-memory image.
+//   2-D: w = (Cout, nsrc*C, 3, 3);  3-D: w = (Cout, nsrc*C, 3, 3, 3);  scale[Cout] (BN fold) or null.
+// Layout: [block b = (source, channel chunk, in-step tap j)][row n = slot*Cout + co][KC] bf16 where
+// slot 0/1/2 are the outputs one step behind / at / one step ahead of the input row (kernel index
+// 2 - slot along the march axis) and j is kx (2-D) or ky*3+kx (3-D).
+std::vector<uint16_t> march_pack_weights(int mode, const float* w, int Cout, int nsrc, int C,
+                                         const double* scale);
+
+int conv_march_launch(const MarchLaunch& L, cudaStream_t stream);
+
+}  // namespace cetpick

@@ -1,5 +1,6 @@
 // Host-side description of one implicit-GEMM convolution launch (conv_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -32,6 +33,11 @@ struct ConvLaunch {
   int out_cstride = 0;      // channels per output pixel (EPI_BF16_NHWC)
   int Ho = 0, Wo = 0, Cout = 0;  // EPI_UPCONV_2X2: output size (after autocrop) and channels
 };
+
+// bf16 tiled tensor map (rank <= 5) whose innermost box dimension is KC channels = the swizzle span
+// (KC 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B); out-of-bounds elements read as zero.
+int tmap_encode_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int KC);
 
 // Enqueue the convolution.  Returns a CETPICK_* code.
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);

@@ -122,6 +122,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// 32 lanes x 16 consecutive fp32 columns <- one value for every column (used to zero accumulators)
+__device__ __forceinline__ void tmem_st16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (K-major operand, swizzled; cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4

@@ -149,6 +149,15 @@ int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void* src1, int 
                       const float* bias, int relu, int epi, void* out, int out_cstride,
                       int Ho, int Wo, int Cout, void* stream);
 
+/* Test hook: ONE convolution through the marching tcgen05 kernel (csrc/conv_march.cu) used for the
+ * Cout 32/64 layers.  mode 0: Conv2d 3x3 pad 1 over NIMG images; mode 1: Conv3d 3x3x3 dilation
+ * (1,dil,dil) pad (1,dil,dil) with NIMG = depth.  src*: bf16 device [NIMG][H][W][C] (nsrc = 2 is the
+ * channel concat of two sources); w_host: fp32 HOST weight in PyTorch layout (Cout, nsrc*C, 3, 3[, 3]);
+ * out: bf16 device [NIMG][H][W][Cout].  Packs, uploads, launches and synchronises. */
+int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
+                            int NIMG, int H, int W, const float* w_host, int Cout,
+                            const float* bias, int relu, void* out, void* stream);
+
 /* Hardware probe (test hook): D[128][32] = A_big[rows] * B^T where the A descriptor starts r0 rows
  * into a TMA-written swizzled tile, with 8-row groups sbo_bytes apart and the given base_offset. */
 int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,

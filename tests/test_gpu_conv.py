@@ -134,3 +134,76 @@ def test_proj_head_l2norm_ncdhw(L):
     run_conv(L, [x], wpk, 32, taps, 32, None, False, L.EPI_F32_L2NORM_NCDHW, out)
     ref = F.normalize(F.conv3d(x.float().permute(3, 0, 1, 2)[None], wt.float(), padding=(1, 0, 0)), dim=1)[0]
     assert (out - ref).abs().max().item() <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# marching kernel (csrc/conv_march.cu): N-stacked taps along the march axis, resident weights
+# ------------------------------------------------------------------------------------------------
+def run_march(L, mode, dil, srcs, wt, cout, bias, relu):
+    n, h, w, c = srcs[0].shape
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wh = wt.float().cpu().contiguous()
+    rc = L.lib().cetpick_conv_march_bf16(mode, dil, len(srcs), srcs[0].data_ptr(),
+                                         srcs[1].data_ptr() if len(srcs) > 1 else None, c, n, h, w,
+                                         wh.data_ptr(), cout, bias.data_ptr() if bias is not None else None,
+                                         int(relu), out.data_ptr(), L.stream_ptr())
+    L.check(rc, "cetpick_conv_march_bf16")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (1, 1, 5, 32, 32),          # a single row: every output row is first and last
+    (2, 2, 16, 16, 32),
+    (3, 13, 21, 32, 32),
+    (2, 40, 130, 32, 32),       # two x blocks, ring of 16 slots wraps
+    (2, 19, 35, 64, 64),        # ring of 8 slots
+    (1, 37, 300, 32, 64),
+    (2, 24, 40, 16, 32),
+    (1, 70, 257, 64, 32),
+])
+def test_march2d_conv3x3_bias_relu(L, n, h, w, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(cin * 7 + cout + h)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = run_march(L, L.MARCH_2D_ROWS, 1, [x], wt, cout, b, True)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1)).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, err      # one bf16 rounding of O(1) outputs + accumulation order
+
+
+@pytest.mark.parametrize("c", [32, 64])
+def test_march2d_two_sources_is_concat(L, c):
+    n, h, w = 2, 27, 140
+    g = torch.Generator(device="cuda").manual_seed(5 + c)
+    a = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    s = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(c, 2 * c, 3, 3, device="cuda", generator=g) / (3 * (2 * c) ** 0.5)).bfloat16()
+    out = run_march(L, L.MARCH_2D_ROWS, 1, [a, s], wt, c, None, False)
+    xin = torch.cat((a, s), 3).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wt.float(), padding=1).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+def test_march2d_many_strips_persistent(L):
+    """more strips than SMs and several strips along y: ring state carries across strips"""
+    n, h, w, c = 40, 96, 520, 32
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(c, c, 3, 3, device="cuda", generator=g) / (3 * c ** 0.5)).bfloat16()
+    out = run_march(L, L.MARCH_2D_ROWS, 1, [x], wt, c, None, True)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("d,h,w", [(1, 9, 7), (5, 20, 27), (9, 33, 50), (40, 64, 64)])
+def test_march3d_dilated_27_taps(L, d, h, w):
+    c = 32
+    g = torch.Generator(device="cuda").manual_seed(11 + d)
+    x = torch.randn(d, h, w, c, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(c, c, 3, 3, 3, device="cuda", generator=g) / (27 * c) ** 0.5).bfloat16()
+    out = run_march(L, L.MARCH_3D_PLANES, 4, [x], wt, c, None, True)
+    xin = x.float().permute(3, 0, 1, 2)[None]
+    ref = F.relu(F.conv3d(xin, wt.float(), padding=(1, 4, 4), dilation=(1, 4, 4)))[0].permute(1, 2, 3, 0)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
