@@ -253,7 +253,7 @@ def run_b200(a, rank, world, local_rank):
 
     # roofline of the dominant kernel (conv_tc_kernel): per-launch CUDA events inside the library
     prof = _lib.profile_forward(lambda: model(pool[0][None])) if n_local else []
-    conv = [(n, ms, fl) for n, ms, fl in prof if n.startswith("conv_tc")]
+    conv = [(n, ms, fl) for n, ms, fl in prof if n.startswith("conv:")]
     conv_ms, conv_fl, tot_ms = sum(m for _, m, _ in conv), sum(f for _, _, f in conv), sum(m for _, m, _ in prof)
     pk = peaks()
     layers = {}
@@ -282,9 +282,10 @@ def run_b200(a, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
-                         "kernel": "conv_tc_kernel (all tcgen05 conv layers of one forward)",
+                         "kernel": "conv_march_kernel + conv_tc_kernel (all tcgen05 conv layers of one forward)",
                          "peak_source": pk["src"] + " sustained cuBLAS bf16", "share_of_forward": conv_ms / tot_ms if tot_ms else None,
-                         "layers_ms": {k: round(v[0], 3) for k, v in layers.items()}},
+                         "layers_ms": {k: round(v[0], 3) for k, v in layers.items()},
+                         "layers_tflops": {k: round(v[1] / v[0] / 1e9, 1) for k, v in layers.items() if v[0] > 0 and v[1] > 0}},
         }
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample((D, H, W), a.K, a.nms, a.cpu_sample_slices)

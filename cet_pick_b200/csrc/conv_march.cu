@@ -34,28 +34,53 @@ namespace {
 constexpr int MARCH_THREADS = 384;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_SLOTS = 16;
-constexpr int MAX_MT = 2;
 constexpr int TMEM_COLS = 512;
+constexpr int DIL3D = 4;         // feature_head dilation (unet_small.py:39-46)
 
 struct alignas(64) MarchParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
-  int mode, dil, nsrc, chunks, KC, k16s, T, MT, S;
+  int nsrc, chunks, S;
   int NIMG, H, W;
   int L, R, nchunk;        // march extent, rows per strip, strips along the march axis
   int nxb;                 // tile columns (2-D: x blocks per row; 3-D: x tiles per plane)
   long long total_strips;
-  int stages, stage_bytes, box_bytes;
-  int nblk, wblk_bytes;    // weight blocks (source, chunk, tap) and bytes of one
-  int sbo_a, sbo_b, layout_type;
-  int a_off[MAX_MT][9];    // byte offset of the A operand of (M-tile, in-step tap) inside a stage
+  int stages;
+  int nblk;                // weight blocks (source, chunk, tap)
   int relu;
   const float* bias;
   __nv_bfloat16* out;
 };
 
+// Compile-time geometry of one instantiation.
+template <int COUT, int KC, int MODE, int MT>
+struct Geo {
+  static constexpr int T = MODE == MARCH_2D_ROWS ? 3 : 9;            // in-step taps
+  static constexpr int K16 = KC / 16;
+  static constexpr int PIX = KC * 2;                                 // bytes of one pixel's chunk = swizzle span
+  // TMA boxes of one stage: 2-D = one (128+2)-pixel row piece per M-tile (box extents are capped at
+  // 256); 3-D = one (16+2d) x (8*MT+2d) plane tile shared by the M-tiles.
+  static constexpr int NBOX = MODE == MARCH_2D_ROWS ? MT : 1;
+  static constexpr int BX = MODE == MARCH_2D_ROWS ? 130 : 8 * MT + 2 * DIL3D;
+  static constexpr int BY = MODE == MARCH_2D_ROWS ? 1 : 16 + 2 * DIL3D;
+  static constexpr int BOX_BYTES = BX * BY * PIX;
+  static constexpr int BOX_STRIDE = (BOX_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = NBOX * BOX_STRIDE;
+  static constexpr int WBLK = 3 * COUT * PIX;                        // bytes of one weight block
+  static constexpr int SLOT_BYTES = COUT * PIX;                      // B rows of one output row
+  static constexpr int SBO_A = MODE == MARCH_2D_ROWS ? 8 * PIX : BX * PIX;
+  static constexpr int SBO_B = 8 * PIX;
+  static constexpr uint32_t LAYOUT = KC == 64 ? 2 : KC == 32 ? 4 : 6;
+  // byte offset of the A operand of (M-tile t, in-step tap j, k16 step kk) inside a stage
+  static __host__ __device__ constexpr int aoff(int t, int j, int kk) {
+    return (MODE == MARCH_2D_ROWS ? t * BOX_STRIDE + j * PIX
+                                  : (((j / 3) * DIL3D) * BX + (j % 3) * DIL3D + t * 8) * PIX) + kk * 32;
+  }
+};
+
 struct Strip { int ma, mb, x0, y0, img; };
 
+template <int MODE, int MT>
 __device__ __forceinline__ void decode_strip(const MarchParams& p, long long k, Strip& s) {
   const int ch = (int)(k % p.nchunk);
   k /= p.nchunk;
@@ -63,8 +88,8 @@ __device__ __forceinline__ void decode_strip(const MarchParams& p, long long k, 
   s.mb = min(s.ma + p.R, p.L);
   const int bx = (int)(k % p.nxb);
   k /= p.nxb;
-  if (p.mode == MARCH_2D_ROWS) { s.x0 = bx * 128 * p.MT; s.y0 = 0; s.img = (int)k; }
-  else { s.x0 = bx * 8 * p.MT; s.y0 = (int)k * 16; s.img = 0; }
+  if (MODE == MARCH_2D_ROWS) { s.x0 = bx * 128 * MT; s.y0 = 0; s.img = (int)k; }
+  else { s.x0 = bx * 8 * MT; s.y0 = (int)k * 16; s.img = 0; }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -72,8 +97,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int COUT>
+template <int COUT, int KC, int MODE, int MT>
 __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
+  using G = Geo<COUT, KC, MODE, MT>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
@@ -82,7 +108,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
-  uint8_t* sA = smem + (((size_t)p.nblk * p.wblk_bytes + 1023) & ~(size_t)1023);
+  uint8_t* sA = smem + (((size_t)p.nblk * G::WBLK + 1023) & ~(size_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -93,7 +119,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < p.S; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * p.MT); }
+    for (int s = 0; s < p.S; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * MT); }
     ptx::mbar_init(&bar_w, 1);
     ptx::fence_barrier_init();
   }
@@ -117,110 +143,123 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
 
+  const uint32_t smask = (uint32_t)p.S - 1u;
+  const int sshift = 31 - __clz(p.S);
+
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bar_w, (uint32_t)(p.nblk * p.wblk_bytes));
+      ptx::mbar_arrive_expect_tx(&bar_w, (uint32_t)(p.nblk * G::WBLK));
       for (int b = 0; b < p.nblk; ++b)
-        ptx::tma_load_2d(sW + (size_t)b * p.wblk_bytes, &p.tmB, &bar_w, 0, b * 3 * COUT);
+        ptx::tma_load_2d(sW + (size_t)b * G::WBLK, &p.tmB, &bar_w, 0, b * 3 * COUT);
       int stage = 0;
       uint32_t phase = 0;
       for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
         Strip s;
-        decode_strip(p, k, s);
+        decode_strip<MODE, MT>(p, k, s);
         const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
         for (int i = i_lo; i <= i_hi; ++i)
           for (int src = 0; src < p.nsrc; ++src)
             for (int c = 0; c < p.chunks; ++c) {
               ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
-              ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)p.box_bytes);
-              uint8_t* dst = sA + (size_t)stage * p.stage_bytes;
-              if (p.mode == MARCH_2D_ROWS)
-                ptx::tma_load_4d(dst, &p.tmA[src], &bar_full[stage], c * p.KC, s.x0 - 1, i, s.img);
+              ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(G::NBOX * G::BOX_BYTES));
+              uint8_t* dst = sA + (size_t)stage * G::STAGE_BYTES;
+              if (MODE == MARCH_2D_ROWS)
+                for (int t = 0; t < MT; ++t)
+                  ptx::tma_load_4d(dst + t * G::BOX_STRIDE, &p.tmA[src], &bar_full[stage], c * KC, s.x0 + t * 128 - 1, i, s.img);
               else
-                ptx::tma_load_4d(dst, &p.tmA[src], &bar_full[stage], c * p.KC, s.x0 - p.dil, s.y0 - p.dil, i);
+                ptx::tma_load_4d(dst, &p.tmA[src], &bar_full[stage], c * KC, s.x0 - DIL3D, s.y0 - DIL3D, i);
               if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
       }
     }
   } else if (warp == 1) {
     // ================================ UMMA issuer =================================
-    if (lane == 0) {
-      uint32_t idesc[4];
-      for (int n = 1; n <= 3; ++n) idesc[n] = ptx::make_idesc_bf16(128, n * COUT);
-      const uint32_t sW_u32 = ptx::smem_u32(sW), sA_u32 = ptx::smem_u32(sA);
-      const uint32_t slot_bytes = (uint32_t)(COUT * p.KC * 2);   // one output row's block of B rows
-      const uint32_t smask = (uint32_t)p.S - 1u;
-      int sshift = 0;
-      while ((1 << sshift) < p.S) ++sshift;
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t q0 = 0, q_touched = 0;
-      ptx::mbar_wait(&bar_w, 0);
-      for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
-        Strip s;
-        decode_strip(p, k, s);
-        const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
-        for (int i = i_lo; i <= i_hi; ++i) {
-          const int r_lo = max(s.ma, i - 1), r_hi = min(s.mb - 1, i + 1);
-          const uint32_t q_lo = q0 + (uint32_t)(r_lo - s.ma);
-          const int n = r_hi - r_lo + 1;
-          while (q_touched < q_lo + (uint32_t)n) {    // rows touched for the first time: slot must be drained
-            ptx::mbar_wait(&bar_aempty[q_touched & smask], ((q_touched >> sshift) & 1u) ^ 1u);
-            ++q_touched;
-          }
-          ptx::tc_fence_after();
-          const uint32_t s_lo = q_lo & smask;
-          const int n1 = min(n, p.S - (int)s_lo), n2 = n - n1;     // ring wrap splits the column range
-          const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * slot_bytes, boff2 = boff1 + (uint32_t)n1 * slot_bytes;
-          for (int src = 0; src < p.nsrc; ++src)
-            for (int c = 0; c < p.chunks; ++c) {
-              ptx::mbar_wait(&bar_full[stage], phase);
-              ptx::tc_fence_after();
-              const uint32_t a0 = sA_u32 + (uint32_t)(stage * p.stage_bytes);
-              const uint32_t w0 = sW_u32 + (uint32_t)((src * p.chunks + c) * p.T * p.wblk_bytes);
-              for (int t = 0; t < p.MT; ++t) {
-                const uint32_t d1 = tmem_base + (uint32_t)((t * p.S + (int)s_lo) * COUT);
-                const uint32_t d2 = tmem_base + (uint32_t)(t * p.S * COUT);
-                for (int j = 0; j < p.T; ++j) {
-                  const uint32_t aj = a0 + (uint32_t)p.a_off[t][j];
-                  const uint32_t wj = w0 + (uint32_t)(j * p.wblk_bytes);
-                  for (int kk = 0; kk < p.k16s; ++kk) {
-                    const uint64_t da = ptx::make_smem_desc(aj + kk * 32, (uint32_t)p.sbo_a, p.layout_type);
-                    ptx::umma_bf16(d1, da, ptx::make_smem_desc(wj + boff1 + kk * 32, (uint32_t)p.sbo_b, p.layout_type),
-                                   idesc[n1], 1u);
-                    if (n2)
-                      ptx::umma_bf16(d2, da, ptx::make_smem_desc(wj + boff2 + kk * 32, (uint32_t)p.sbo_b, p.layout_type),
-                                     idesc[n2], 1u);
-                  }
-                }
+    // The whole warp runs this loop on warp-uniform values (so descriptors live in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t A_HI = ptx::smem_desc_hi(G::SBO_A, G::LAYOUT), B_HI = ptx::smem_desc_hi(G::SBO_B, G::LAYOUT);
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const uint32_t sW_lo = ptx::smem_desc_lo(ptx::smem_u32(sW)), sA_lo = ptx::smem_desc_lo(ptx::smem_u32(sA));
+    const uint32_t tile_cols = (uint32_t)(p.S * COUT);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t q0 = 0, q_touched = 0;
+    ptx::mbar_wait(&bar_w, 0);
+    for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
+      Strip s;
+      decode_strip<MODE, MT>(p, k, s);
+      const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
+      for (int i = i_lo; i <= i_hi; ++i) {
+        const int r_lo = max(s.ma, i - 1), r_hi = min(s.mb - 1, i + 1);
+        const uint32_t q_lo = q0 + (uint32_t)(r_lo - s.ma);
+        const int n = r_hi - r_lo + 1;
+        while (q_touched < q_lo + (uint32_t)n) {    // rows touched for the first time: slot must be drained
+          ptx::mbar_wait(&bar_aempty[q_touched & smask], ((q_touched >> sshift) & 1u) ^ 1u);
+          ++q_touched;
+        }
+        const uint32_t s_lo = q_lo & smask;
+        const int n1 = min(n, p.S - (int)s_lo), n2 = n - n1;     // ring wrap splits the column range
+        const uint32_t id1 = IDESC0 | ((uint32_t)(n1 * COUT >> 3) << 17), id2 = IDESC0 | ((uint32_t)(n2 * COUT >> 3) << 17);
+        const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
+        const uint32_t boff2 = boff1 + (uint32_t)n1 * (G::SLOT_BYTES >> 4);
+        const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
+        for (int src = 0; src < p.nsrc; ++src)
+          for (int c = 0; c < p.chunks; ++c) {
+            ptx::mbar_wait(&bar_full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = sA_lo + (uint32_t)(stage * (G::STAGE_BYTES >> 4));
+            const uint32_t w_lo = sW_lo + (uint32_t)((src * p.chunks + c) * G::T * (G::WBLK >> 4));
+            if (ptx::elect_one()) {
+              if (n2 == 0) {
+#pragma unroll
+                for (int t = 0; t < MT; ++t)
+#pragma unroll
+                  for (int j = 0; j < G::T; ++j)
+#pragma unroll
+                    for (int kk = 0; kk < G::K16; ++kk)
+                      ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
+                                          w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
+              } else {
+#pragma unroll 1
+                for (int t = 0; t < MT; ++t)
+#pragma unroll
+                  for (int j = 0; j < G::T; ++j)
+#pragma unroll
+                    for (int kk = 0; kk < G::K16; ++kk) {
+                      ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
+                                          w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
+                      ptx::umma_bf16_lohi(d2 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
+                                          w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
+                    }
               }
               ptx::umma_commit(&bar_empty[stage]);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
-          // rows that have now seen all three of their input rows
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        // rows that have now seen all three of their input rows
+        if (ptx::elect_one()) {
           if (i - 1 >= s.ma) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - 1 - s.ma)) & smask]);
           if (i == p.L - 1 && i < s.mb) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - s.ma)) & smask]);
         }
-        q0 += (uint32_t)(s.mb - s.ma);
+        __syncwarp();
       }
+      q0 += (uint32_t)(s.mb - s.ma);
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     const int quad = warp & 3, eg = (warp - 4) >> 2;
     const int m = quad * 32 + lane;
-    const uint32_t smask = (uint32_t)p.S - 1u;
-    int sshift = 0;
-    while ((1 << sshift) < p.S) ++sshift;
     uint32_t q0 = 0;
     for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
       Strip s;
-      decode_strip(p, k, s);
+      decode_strip<MODE, MT>(p, k, s);
       for (int r = s.ma; r < s.mb; ++r) {
         const uint32_t q = q0 + (uint32_t)(r - s.ma);
         const uint32_t slot = q & smask, par = (q >> sshift) & 1u;
-        for (int t = 0; t < p.MT; ++t) {
-          if ((int)((q * (uint32_t)p.MT + (uint32_t)t) & 1u) != eg) continue;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+          if ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg) continue;
           ptx::mbar_wait(&bar_afull[slot], par);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
@@ -237,7 +276,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           if (lane == 0) ptx::mbar_arrive(&bar_aempty[slot]);
 
           int x, y, z;
-          if (p.mode == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
+          if (MODE == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
           else { x = s.x0 + t * 8 + (m & 7); y = s.y0 + (m >> 3); z = r; }
           if (x < p.W && y < p.H) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
@@ -273,11 +312,13 @@ int smem_limit() { return 227 * 1024; }
 bool march_supported(int mode, int C, int nsrc, int Cout) {
   if (Cout != 32 && Cout != 64) return false;
   if (C != 16 && C != 32 && C != 64) return false;
+  if (Cout == 64 && C == 16) return false;
   if (nsrc < 1 || nsrc > 2) return false;
   if (mode == MARCH_3D_PLANES && (C != 32 || nsrc != 1 || Cout != 32)) return false;
   const int T = mode == MARCH_2D_ROWS ? 3 : 9;
   const size_t wbytes = align_up((size_t)nsrc * T * 3 * Cout * C * 2, 1024);
-  const size_t stage = mode == MARCH_2D_ROWS ? align_up((size_t)130 * std::min(C, 64) * 2, 1024) : (size_t)24 * 24 * 64;
+  const size_t stage = mode == MARCH_2D_ROWS ? (Cout == 32 ? 2 : 1) * align_up((size_t)130 * std::min(C, 64) * 2, 1024)
+                                             : (size_t)24 * 24 * 64;
   return wbytes + 3 * stage + 4096 <= (size_t)smem_limit();   // weights + >= 3 activation stages
 }
 
@@ -302,54 +343,38 @@ std::vector<uint16_t> march_pack_weights(int mode, const float* w, int Cout, int
   return out;
 }
 
-int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
-  if (!march_supported(L.mode, L.C, L.nsrc, L.Cout)) return CETPICK_ERR_UNSUPPORTED;
-  if (!L.src[0] || (L.nsrc > 1 && !L.src[1]) || !L.wpk || !L.out || L.NIMG <= 0 || L.H <= 0 || L.W <= 0)
-    return CETPICK_ERR_BAD_ARG;
-  if (L.mode == MARCH_3D_PLANES && (L.dil < 1 || L.dil > 4)) return CETPICK_ERR_UNSUPPORTED;
+namespace {
 
-  MarchParams p;
-  memset(&p, 0, sizeof(p));
-  p.mode = L.mode; p.dil = L.dil; p.nsrc = L.nsrc;
-  p.KC = std::min(L.C, 64);
-  p.chunks = L.C / p.KC;
-  p.k16s = p.KC / 16;
-  p.T = L.mode == MARCH_2D_ROWS ? 3 : 9;
-  p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
-  p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
-  p.layout_type = p.KC == 64 ? 2 : p.KC == 32 ? 4 : 6;
-  const int pix = p.KC * 2;                       // bytes of one pixel's channel chunk = swizzle span
-  p.sbo_b = 8 * pix;
-  p.nblk = L.nsrc * p.chunks * p.T;
-  p.wblk_bytes = 3 * L.Cout * pix;
-
-  int BX, BY;
-  long long base_strips;
-  if (L.mode == MARCH_2D_ROWS) {
-    p.MT = 1;
-    BX = 128 * p.MT + 2; BY = 1;
-    p.L = L.H;
-    p.nxb = ceil_div(L.W, 128 * p.MT);
-    base_strips = (long long)p.nxb * L.NIMG;
-    p.sbo_a = 8 * pix;
-    for (int t = 0; t < p.MT; ++t)
-      for (int j = 0; j < 3; ++j) p.a_off[t][j] = (t * 128 + j) * pix;
-  } else {
-    p.MT = (L.W > 8) ? 2 : 1;
-    BX = 8 * p.MT + 2 * L.dil; BY = 16 + 2 * L.dil;
-    p.L = L.NIMG;
-    p.nxb = ceil_div(L.W, 8 * p.MT);
-    base_strips = (long long)p.nxb * ceil_div(L.H, 16);
-    p.sbo_a = BX * pix;
-    for (int t = 0; t < p.MT; ++t)
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) p.a_off[t][ky * 3 + kx] = ((ky * L.dil) * BX + kx * L.dil + t * 8) * pix;
+template <int COUT, int KC, int MODE, int MT>
+int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
+  using G = Geo<COUT, KC, MODE, MT>;
+  auto kern = conv_march_kernel<COUT, KC, MODE, MT>;
+  static int static_smem = -1;
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    CETPICK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_limit() - (int)fa.sharedSizeBytes));
+    static_smem = (int)fa.sharedSizeBytes;
   }
-  p.S = std::min(MAX_SLOTS, TMEM_COLS / (p.MT * L.Cout));
-  p.box_bytes = BX * BY * pix;
-  p.stage_bytes = (int)align_up((size_t)p.box_bytes, 1024);
-  const size_t wtot = align_up((size_t)p.nblk * p.wblk_bytes, 1024);
+  p.nblk = L.nsrc * p.chunks * G::T;
+  p.S = std::min(MAX_SLOTS, TMEM_COLS / (MT * COUT));
+  const size_t wtot = align_up((size_t)p.nblk * G::WBLK, 1024);
+  const size_t avail = (size_t)smem_limit() - static_smem - 1024 - wtot;
+  p.stages = (int)std::min<size_t>(MAX_STAGES, avail / G::STAGE_BYTES);
+  if (p.stages < 2) return CETPICK_ERR_UNSUPPORTED;
+  const size_t smem = 1024 + wtot + (size_t)p.stages * G::STAGE_BYTES;
 
+  long long base_strips;
+  if (MODE == MARCH_2D_ROWS) {
+    p.L = L.H;
+    p.nxb = ceil_div(L.W, 128 * MT);
+    base_strips = (long long)p.nxb * L.NIMG;
+  } else {
+    p.L = L.NIMG;
+    p.nxb = ceil_div(L.W, 8 * MT);
+    base_strips = (long long)p.nxb * ceil_div(L.H, 16);
+  }
   // strips along the march axis: enough strips to balance the persistent grid, few enough that the
   // two extra input rows per strip stay cheap
   const int sms = num_sms();
@@ -367,45 +392,52 @@ int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
   p.R = ceil_div(p.L, best_n);
   p.total_strips = base_strips * p.nchunk;
 
-  static int static_smem[2] = {-1, -1};
-  const int ti = L.Cout == 32 ? 0 : 1;
-  if (static_smem[ti] < 0) {
-    cudaFuncAttributes fa;
-    if (L.Cout == 32) {
-      CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_march_kernel<32>));
-      CETPICK_CUDA(cudaFuncSetAttribute(conv_march_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem_limit() - (int)fa.sharedSizeBytes));
-    } else {
-      CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_march_kernel<64>));
-      CETPICK_CUDA(cudaFuncSetAttribute(conv_march_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem_limit() - (int)fa.sharedSizeBytes));
-    }
-    static_smem[ti] = (int)fa.sharedSizeBytes;
-  }
-  const size_t avail = (size_t)smem_limit() - static_smem[ti] - 1024 - wtot;
-  p.stages = (int)std::min<size_t>(MAX_STAGES, avail / p.stage_bytes);
-  if (p.stages < 2) return CETPICK_ERR_UNSUPPORTED;
-  const size_t smem = 1024 + wtot + (size_t)p.stages * p.stage_bytes;
-
   int rc;
   for (int s = 0; s < L.nsrc; ++s) {
     const uint64_t C = (uint64_t)L.C;
     const uint64_t dims[4] = {C, (uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.NIMG};
     const uint64_t strides[3] = {C * 2, C * 2 * L.W, C * 2 * (uint64_t)L.W * L.H};
-    const uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)BX, (uint32_t)BY, 1};
-    if ((rc = tmap_encode_bf16(&p.tmA[s], L.src[s], 4, dims, strides, box, p.KC))) return rc;
+    const uint32_t box[4] = {(uint32_t)KC, (uint32_t)G::BX, (uint32_t)G::BY, 1};
+    if ((rc = tmap_encode_bf16(&p.tmA[s], L.src[s], 4, dims, strides, box, KC))) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)p.KC, (uint64_t)p.nblk * 3 * L.Cout};
-    const uint64_t strides[1] = {(uint64_t)pix};
-    const uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)(3 * L.Cout)};
-    if ((rc = tmap_encode_bf16(&p.tmB, L.wpk, 2, dims, strides, box, p.KC))) return rc;
+    const uint64_t dims[2] = {(uint64_t)KC, (uint64_t)p.nblk * 3 * COUT};
+    const uint64_t strides[1] = {(uint64_t)G::PIX};
+    const uint32_t box[2] = {(uint32_t)KC, (uint32_t)(3 * COUT)};
+    if ((rc = tmap_encode_bf16(&p.tmB, L.wpk, 2, dims, strides, box, KC))) return rc;
   }
   const int grid = (int)std::min<long long>(p.total_strips, sms);
-  if (L.Cout == 32) conv_march_kernel<32><<<grid, MARCH_THREADS, smem, stream>>>(p);
-  else conv_march_kernel<64><<<grid, MARCH_THREADS, smem, stream>>>(p);
+  kern<<<grid, MARCH_THREADS, smem, stream>>>(p);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
+}
+
+}  // namespace
+
+int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
+  if (!march_supported(L.mode, L.C, L.nsrc, L.Cout)) return CETPICK_ERR_UNSUPPORTED;
+  if (!L.src[0] || (L.nsrc > 1 && !L.src[1]) || !L.wpk || !L.out || L.NIMG <= 0 || L.H <= 0 || L.W <= 0)
+    return CETPICK_ERR_BAD_ARG;
+  if (L.mode == MARCH_3D_PLANES && L.dil != DIL3D) return CETPICK_ERR_UNSUPPORTED;
+
+  MarchParams p;
+  memset(&p, 0, sizeof(p));
+  p.nsrc = L.nsrc;
+  const int KC = std::min(L.C, 64);
+  p.chunks = L.C / KC;
+  p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
+  p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
+
+  if (L.mode == MARCH_3D_PLANES) return launch_inst<32, 32, MARCH_3D_PLANES, 2>(p, L, stream);
+  const bool wide = L.W > 128;   // two M-tiles per step amortise the per-step barrier traffic
+  if (L.Cout == 32) {
+    if (KC == 16) return wide ? launch_inst<32, 16, MARCH_2D_ROWS, 2>(p, L, stream) : launch_inst<32, 16, MARCH_2D_ROWS, 1>(p, L, stream);
+    if (KC == 32) return wide ? launch_inst<32, 32, MARCH_2D_ROWS, 2>(p, L, stream) : launch_inst<32, 32, MARCH_2D_ROWS, 1>(p, L, stream);
+    return wide ? launch_inst<32, 64, MARCH_2D_ROWS, 2>(p, L, stream) : launch_inst<32, 64, MARCH_2D_ROWS, 1>(p, L, stream);
+  }
+  if (KC == 16) return CETPICK_ERR_UNSUPPORTED;
+  if (KC == 32) return launch_inst<64, 32, MARCH_2D_ROWS, 1>(p, L, stream);
+  return launch_inst<64, 64, MARCH_2D_ROWS, 1>(p, L, stream);
 }
 
 }  // namespace cetpick

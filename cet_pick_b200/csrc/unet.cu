@@ -9,6 +9,7 @@
 //   Layer by layer over the whole volume; torch.cat is never materialised (two TMA sources).
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_march.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -164,6 +165,7 @@ struct PackedConv {
   size_t w_off = 0, b_off = 0;   // byte offsets into the device weight blob
   bool has_bias = false;
   double flops_per_pixel = 0;    // 2 * K * N
+  int march = -1;                // >= 0: MarchMode of conv_march.cu (w_off then holds ITS weight image)
 };
 
 // Optional per-launch timing (CUDA events on the launching stream) for bench.py's roofline.
@@ -183,14 +185,6 @@ struct Profiler {
   }
 };
 Profiler g_prof;
-
-uint16_t f2bf(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
 
 }  // namespace
 }  // namespace cetpick
@@ -252,6 +246,14 @@ bool pack_conv(cetpick_unet* m, const std::string& wkey, int Cout, int nsrc, int
   pc.relu = relu;
   const int chunks = Csrc / pc.KC;
   const size_t nkb = (size_t)nsrc * ntaps * chunks;
+  const int mmode = ntaps == 9 ? MARCH_2D_ROWS : ntaps == 27 ? MARCH_3D_PLANES : -1;
+  if (mmode >= 0 && march_supported(mmode, Csrc, nsrc, Cout)) {
+    // narrow layer: weight image of the marching kernel (conv_march.cu)
+    const std::vector<uint16_t> pk = march_pack_weights(mmode, w->data(), Cout, nsrc, Csrc, fold ? fold->scale.data() : nullptr);
+    pc.march = mmode;
+    pc.w_off = blob_alloc(m, pk.size() * 2);
+    memcpy(m->blob.data() + pc.w_off, pk.data(), pk.size() * 2);
+  } else {
   pc.w_off = blob_alloc(m, nkb * Cout * pc.KC * 2);
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->blob.data() + pc.w_off);
   for (int s = 0; s < nsrc; ++s)
@@ -262,9 +264,10 @@ bool pack_conv(cetpick_unet* m, const std::string& wkey, int Cout, int nsrc, int
           for (int k = 0; k < pc.KC; ++k) {
             const int ci = s * Csrc + ch * pc.KC + k;
             const double v = (double)(*w)[((size_t)n * Cin + ci) * ntaps + t] * (fold ? fold->scale[n] : 1.0);
-            dst[(kb * Cout + n) * pc.KC + k] = f2bf((float)v);
+            dst[(kb * Cout + n) * pc.KC + k] = f2bf_host((float)v);
           }
       }
+  }
   pc.has_bias = fold || conv_bias;
   if (pc.has_bias) {
     pc.b_off = blob_alloc(m, (size_t)Cout * 4);
@@ -325,9 +328,20 @@ WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W) {
   return p;
 }
 
-int run_conv(const cetpick_unet* m, const char* name, const PackedConv& pc, const void* s0, const void* s1,
+int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
              int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st) {
-  g_prof.mark(name, pc.flops_per_pixel * (double)NIMG * H * W, st);
+  g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : ":tc")).c_str(),
+              pc.flops_per_pixel * (double)NIMG * H * W, st);
+  const float* bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
+  if (pc.march >= 0) {
+    if (epi != EPI_BF16_NHWC) return CETPICK_ERR_STATE;
+    MarchLaunch M;
+    M.mode = pc.march; M.dil = 4; M.nsrc = pc.nsrc; M.src[0] = s0; M.src[1] = s1; M.C = pc.C[0];
+    M.NIMG = NIMG; M.H = H; M.W = W;
+    M.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off;
+    M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out;
+    return conv_march_launch(M, st);
+  }
   ConvLaunch L;
   L.nsrc = pc.nsrc; L.src[0] = s0; L.src[1] = s1; L.C[0] = pc.C[0]; L.C[1] = pc.C[1];
   L.NIMG = NIMG; L.H = H; L.W = W;
@@ -335,7 +349,7 @@ int run_conv(const cetpick_unet* m, const char* name, const PackedConv& pc, cons
   L.KC = pc.KC; L.ntaps = pc.ntaps;
   memcpy(L.tap, pc.tap, sizeof(L.tap));
   L.Ntot = pc.Ntot;
-  L.bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
+  L.bias = bias;
   L.relu = pc.relu; L.epi = epi; L.out = out; L.out_cstride = pc.Ntot;
   L.Ho = Ho; L.Wo = Wo; L.Cout = Cout;
   return conv_tc_launch(L, st);
@@ -418,7 +432,7 @@ extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
             for (int k = 0; k < u.KC; ++k) {
               const int ci = ch * u.KC + k;
               const double v = (double)(*w)[((size_t)ci * outs + co) * 4 + q] * f.scale[co];
-              dst[((size_t)ch * u.Ntot + q * outs + co) * u.KC + k] = f2bf((float)v);
+              dst[((size_t)ch * u.Ntot + q * outs + co) * u.KC + k] = f2bf_host((float)v);
             }
       u.has_bias = true;
       u.b_off = blob_alloc(m, (size_t)u.Ntot * 4);
@@ -501,8 +515,8 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   // encoder: level i: in Y0 -> conv1 -> Y1 -> conv2 -> Y2 (skip) -> pool -> next level's Y0
   for (int i = 0; i < nb; ++i) {
     const int h = dims[i].h, w = dims[i].w;
-    if ((rc = run_conv(m, "conv_tc down.conv1", m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
-    if ((rc = run_conv(m, "conv_tc down.conv2", m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "down" + std::to_string(i) + ".c1", m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "down" + std::to_string(i) + ".c2", m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st))) return rc;
     if (i < nb - 1) {
       const int C = 32 << i;
       g_prof.mark("pool2x2", 0.0, st);
@@ -517,16 +531,16 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   for (int i = 0; i < nb - 1; ++i) {
     const int j = nb - 2 - i;
     const int h = dims[j].h, w = dims[j].w, Cout = 32 << j;
-    if ((rc = run_conv(m, "conv_tc up.upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
-    if ((rc = run_conv(m, "conv_tc up.conv1", m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
-    if ((rc = run_conv(m, "conv_tc up.conv2", m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "up" + std::to_string(i) + ".upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
+    if ((rc = run_conv(m, "up" + std::to_string(i) + ".c1", m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "up" + std::to_string(i) + ".c2", m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
     below = buf(j, 0);
   }
   const int h0 = dims[0].h, w0 = dims[0].w;
   // conv_final (1x1 + bias): X0 -> X1 ; feature_head: X1 -> X0 -> X1 (3-D, z = image axis)
-  if ((rc = run_conv(m, "conv_tc conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, "conv_tc feature_head.0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, "conv_tc feature_head.2", m->fh2, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "fhead0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
+  if ((rc = run_conv(m, "fhead2", m->fh2, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
   {
     const size_t plane = (size_t)h0 * w0, total = plane * D;
     g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
@@ -536,7 +550,7 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
     CETPICK_LAUNCH_CHECK();
   }
   if (proj) {
-    if ((rc = run_conv(m, "conv_tc proj", m->proj, buf(0, 1), nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
+    if ((rc = run_conv(m, "proj", m->proj, buf(0, 1), nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
   }
   g_prof.mark("end", 0.0, st);
   return CETPICK_OK;
