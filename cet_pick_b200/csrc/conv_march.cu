@@ -50,6 +50,10 @@ struct alignas(64) MarchParams {
   int relu;
   const float* bias;
   __nv_bfloat16* out;
+  const float* bias_tab;   // 3-D: [64][COUT] tap-validity dependent bias (or null)
+  const float* hm_w;       // 3-D: fused hm head weights [3][COUT] (or null)
+  float* hm_out;
+  int hm_sigmoid;
 };
 
 // Compile-time geometry of one instantiation.
@@ -78,7 +82,7 @@ struct Geo {
   }
 };
 
-struct Strip { int ma, mb, x0, y0, img; };
+struct Strip { int ma, mb, ha, hb, x0, y0, img; };   // rows computed [ma,mb); hm rows written [ha,hb)
 
 template <int MODE, int MT>
 __device__ __forceinline__ void decode_strip(const MarchParams& p, long long k, Strip& s) {
@@ -86,6 +90,11 @@ __device__ __forceinline__ void decode_strip(const MarchParams& p, long long k, 
   k /= p.nchunk;
   s.ma = ch * p.R;
   s.mb = min(s.ma + p.R, p.L);
+  s.ha = s.ma; s.hb = s.mb;
+  if (MODE == MARCH_3D_PLANES && p.hm_out) {   // fused hm head needs the feature rows around its own
+    s.ma = max(s.ma - 1, 0);
+    s.mb = min(s.mb + 1, p.L);
+  }
   const int bx = (int)(k % p.nxb);
   k /= p.nxb;
   if (MODE == MARCH_2D_ROWS) { s.x0 = bx * 128 * MT; s.y0 = 0; s.img = (int)k; }
@@ -105,6 +114,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
   __shared__ uint32_t s_tmem_base;
   __shared__ float s_bias[COUT];
+  __shared__ __align__(16) float s_btab[MODE == MARCH_3D_PLANES ? 64 * COUT : 4];
+  __shared__ float s_hmw[MODE == MARCH_3D_PLANES ? 3 * COUT : 4];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
@@ -127,8 +138,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     ptx::tmem_alloc(&s_tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (warp == 3)
+  if (warp == 3) {
     for (int c = lane; c < COUT; c += 32) s_bias[c] = p.bias ? p.bias[c] : 0.f;
+    if (MODE == MARCH_3D_PLANES) {
+      for (int c = lane; c < 64 * COUT; c += 32) s_btab[c] = p.bias_tab ? p.bias_tab[c] : 0.f;
+      for (int c = lane; c < 3 * COUT; c += 32) s_hmw[c] = p.hm_w ? p.hm_w[c] : 0.f;
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -250,10 +266,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     // ================================ epilogue ====================================
     const int quad = warp & 3, eg = (warp - 4) >> 2;
     const int m = quad * 32 + lane;
+    const bool fuse_hm = MODE == MARCH_3D_PLANES && p.hm_out != nullptr;
     uint32_t q0 = 0;
     for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
       Strip s;
       decode_strip<MODE, MT>(p, k, s);
+      float hmA = 0.f, hmB = 0.f;     // fused hm head: partial sums of hm[r-1] and hm[r] (this thread's pixel)
       for (int r = s.ma; r < s.mb; ++r) {
         const uint32_t q = q0 + (uint32_t)(r - s.ma);
         const uint32_t slot = q & smask, par = (q >> sshift) & 1u;
@@ -278,21 +296,51 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           int x, y, z;
           if (MODE == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
           else { x = s.x0 + t * 8 + (m & 7); y = s.y0 + (m >> 3); z = r; }
-          if (x < p.W && y < p.H) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
+          const bool valid = x < p.W && y < p.H;
+          const float* brow = s_bias;
+          if (MODE == MARCH_3D_PLANES) {
+            const int cz = (z >= 1) + 2 * (z + 1 < p.NIMG);
+            const int cy = (y >= DIL3D) + 2 * (y + DIL3D < p.H);
+            const int cx = (x >= DIL3D) + 2 * (x + DIL3D < p.W);
+            brow = s_btab + ((cz * 4 + cy) * 4 + cx) * COUT;
+          }
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 8) {
-              float f[8];
+          for (int c0 = 0; c0 < COUT; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[i] = __uint_as_float(v[c0 + i]) + brow[c0 + i];
+              if (p.relu) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (fuse_hm) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                f[i] = __uint_as_float(v[c0 + i]) + s_bias[c0 + i];
-                if (p.relu) f[i] = fmaxf(f[i], 0.f);
+                d0 = fmaf(f[i], s_hmw[c0 + i], d0);
+                d1 = fmaf(f[i], s_hmw[COUT + c0 + i], d1);
+                d2 = fmaf(f[i], s_hmw[2 * COUT + c0 + i], d2);
               }
+            }
+            if (valid && p.out) {
               uint4 w;
               w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
               w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
               dst[c0 / 8] = w;
             }
+          }
+          if (fuse_hm) {
+            // hm[z] = w0.f[z-1] + w1.f[z] + w2.f[z+1]; rows outside the volume contribute zero
+            auto emit = [&](int zz, float val) {
+              if (valid && zz >= s.ha && zz < s.hb) {
+                if (p.hm_sigmoid) val = fminf(fmaxf(1.0f / (1.0f + expf(-val)), 1e-4f), 1.0f - 1e-4f);
+                p.hm_out[((size_t)zz * p.H + y) * p.W + x] = val;
+              }
+            };
+            emit(r - 1, hmA + d2);
+            hmA = hmB + d1;
+            hmB = d0;
+            if (r == p.L - 1) emit(r, hmA);
           }
         }
       }
@@ -416,7 +464,7 @@ int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
 
 int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
   if (!march_supported(L.mode, L.C, L.nsrc, L.Cout)) return CETPICK_ERR_UNSUPPORTED;
-  if (!L.src[0] || (L.nsrc > 1 && !L.src[1]) || !L.wpk || !L.out || L.NIMG <= 0 || L.H <= 0 || L.W <= 0)
+  if (!L.src[0] || (L.nsrc > 1 && !L.src[1]) || !L.wpk || (!L.out && !(L.mode == MARCH_3D_PLANES && L.hm_out)) || L.NIMG <= 0 || L.H <= 0 || L.W <= 0)
     return CETPICK_ERR_BAD_ARG;
   if (L.mode == MARCH_3D_PLANES && L.dil != DIL3D) return CETPICK_ERR_UNSUPPORTED;
 
@@ -427,6 +475,10 @@ int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
   p.chunks = L.C / KC;
   p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
+  if (L.mode == MARCH_3D_PLANES) {
+    p.bias_tab = L.bias_tab; p.hm_w = L.hm_w; p.hm_out = L.hm_out; p.hm_sigmoid = L.hm_sigmoid;
+    if ((L.hm_out != nullptr) != (L.hm_w != nullptr)) return CETPICK_ERR_BAD_ARG;
+  }
 
   if (L.mode == MARCH_3D_PLANES) return launch_inst<32, 32, MARCH_3D_PLANES, 2>(p, L, stream);
   const bool wide = L.W > 128;   // two M-tiles per step amortise the per-step barrier traffic

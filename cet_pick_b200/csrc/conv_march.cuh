@@ -23,7 +23,18 @@ struct MarchLaunch {
   int Cout = 0;             // 32 or 64
   const float* bias = nullptr;  // [Cout] fp32 or null
   int relu = 0;
-  void* out = nullptr;      // bf16 [NIMG][H][W][Cout]
+  void* out = nullptr;      // bf16 [NIMG][H][W][Cout] (may be null when hm_out is set)
+  // 3-D mode extras -------------------------------------------------------------------------
+  // bias_tab: [64][Cout] fp32 or null: a bias that depends on which taps fall inside the volume,
+  // row = (cz*4 + cy)*4 + cx with c = (lower neighbour inside) + 2*(upper neighbour inside) per axis.
+  // This is how a 1x1 conv with bias in FRONT of a zero-padded conv is folded into it exactly
+  // (conv_final -> feature_head.0, unet.py:882 -> unet_small.py:85).
+  const float* bias_tab = nullptr;
+  // fused `hm` head (unet_small.py:53-61,89): Conv3d(Cout,1,(3,1,1),pad (1,0,0)) on the ReLU output,
+  // kept in fp32 registers across the march; hm_w = [3][Cout] fp32 (kz major), hm_out = (D,H,W) fp32.
+  const float* hm_w = nullptr;
+  float* hm_out = nullptr;
+  int hm_sigmoid = 0;       // models/utils.py:167-169 _sigmoid fused
 };
 
 // True when conv_march_launch supports (mode, C per source, nsrc, Cout): weights must fit in shared

@@ -30,22 +30,26 @@ constexpr double BN_EPS = 1e-5;
 // ------------------------------------------------------------------------------------------
 
 // Stem: Conv2d(1,16,7,stride 2,pad 3,bias=False) + BN + ReLU (unet_small.py:35-37,72-74).
-// fp32 (D,H,W) in, bf16 NHWC16 (D,h,w,16) out.  CTA = 32 x 8 output pixels; the (69 x 21) input
-// patch and the 49x16 folded weights sit in shared memory.
-constexpr int ST_TW = 32, ST_TH = 8, ST_IW = 2 * ST_TW + 5, ST_IH = 2 * ST_TH + 5;
+// fp32 (D,H,W) in, bf16 NHWC16 (D,h,w,16) out.  One input channel: not GEMM-shaped enough for a
+// TMA-fed UMMA (K = 49), so this is an FFMA kernel sized to be issue-bound on FMAs: CTA = 64 x 16
+// output pixels, thread = 2 x 2 pixels x 16 channels (64 accumulators; one weight row of 16 floats is
+// reused by 4 pixels).  The (133 x 37) input patch is split into even / odd columns in shared memory
+// so that the stride-2 window reads of a warp hit consecutive banks.
+constexpr int ST_TW = 64, ST_TH = 16, ST_IW = 2 * ST_TW + 5, ST_IH = 2 * ST_TH + 5, ST_HP = 68;
 
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, int D, int H, int W,
-                                                   int h, int w, const float* __restrict__ wgt /*[49][16]*/,
-                                                   const float* __restrict__ bias /*[16]*/,
-                                                   __nv_bfloat16* __restrict__ out) {
-  __shared__ float s_in[ST_IH][ST_IW + 1];
-  __shared__ float s_w[49 * 16];
+__global__ void __launch_bounds__(256, 2) stem_kernel(const float* __restrict__ in, int D, int H, int W,
+                                                      int h, int w, const float* __restrict__ wgt /*[49][16]*/,
+                                                      const float* __restrict__ bias /*[16]*/,
+                                                      __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_par[2][ST_IH][ST_HP];       // [column parity][patch row][patch column / 2]
+  __shared__ __align__(16) float s_w[49 * 16];
   __shared__ float s_b[16];
   const int tid = threadIdx.x;
   for (int i = tid; i < 49 * 16; i += 256) s_w[i] = wgt[i];
   if (tid < 16) s_b[tid] = bias[tid];
   const int tiles_x = ceil_div(w, ST_TW), tiles_y = ceil_div(h, ST_TH);
   const long long total = (long long)tiles_x * tiles_y * D;
+  const int lx = tid & 31, ty = tid >> 5;
   for (long long t = blockIdx.x; t < total; t += gridDim.x) {
     const int tx0 = (int)(t % tiles_x) * ST_TW;
     const int ty0 = (int)((t / tiles_x) % tiles_y) * ST_TH;
@@ -56,34 +60,54 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
     for (int i = tid; i < ST_IH * ST_IW; i += 256) {
       const int r = i / ST_IW, c = i - r * ST_IW;
       const int gy = iy0 + r, gx = ix0 + c;
-      s_in[r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? plane[(size_t)gy * W + gx] : 0.f;
+      s_par[c & 1][r][c >> 1] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + (size_t)gy * W + gx) : 0.f;
     }
     __syncthreads();
-    const int lx = tid & 31, ly = tid >> 5;
-    const int ox = tx0 + lx, oy = ty0 + ly;
-    float acc[16];
+    float acc[2][2][16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = s_b[c];
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[a][b][c] = s_b[c];
 #pragma unroll
     for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float v = s_in[2 * ly + ky][2 * lx + kx];
-        const float* wr = &s_w[(ky * 7 + kx) * 16];
+        float wv[16];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[(ky * 7 + kx) * 16]);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
-      }
-    if (ox < w && oy < h) {
-      uint32_t pk[8];
+        for (int q = 0; q < 4; ++q) {
+          const float4 f = wr[q];
+          wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w;
+        }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        __nv_bfloat162 v2 = __floats2bfloat162_rn(fmaxf(acc[2 * c], 0.f), fmaxf(acc[2 * c + 1], 0.f));
-        pk[c] = *reinterpret_cast<uint32_t*>(&v2);
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            // output pixel (yy, xx) = (2*ty + a, lx + 32*b): patch row 2*yy + ky, patch column 2*xx + kx
+            const float v = s_par[kx & 1][2 * (2 * ty + a) + ky][lx + 32 * b + (kx >> 1)];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[a][b][c] = fmaf(v, wv[c], acc[a][b][c]);
+          }
       }
-      uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)z * h + oy) * w + ox) * 16);
-      dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ox = tx0 + lx + 32 * b, oy = ty0 + 2 * ty + a;
+        if (ox < w && oy < h) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(fmaxf(acc[a][b][2 * c], 0.f), fmaxf(acc[a][b][2 * c + 1], 0.f));
+            pk[c] = *reinterpret_cast<uint32_t*>(&v2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)z * h + oy) * w + ox) * 16);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
   }
 }
 
@@ -199,6 +223,8 @@ struct cetpick_unet {
   void* d_blob = nullptr;
   // packed layers
   size_t stem_w = 0, stem_b = 0, hm_w = 0;
+  bool fold_cf = false;          // conv_final folded into feature_head.0 (weights + tap-validity bias table)
+  size_t fh0_btab = 0;
   std::vector<PackedConv> down1, down2, upc, up1, up2;
   PackedConv conv_final, fh0, fh2, proj;
 
@@ -236,10 +262,11 @@ size_t blob_alloc(cetpick_unet* m, size_t bytes) {
 // Pack a PyTorch conv weight (Cout, Cin_total, *kernel) into [k-block][Cout][KC] bf16 with the
 // per-output-channel scale folded in.  The K loop is (source, tap, channel chunk).
 bool pack_conv(cetpick_unet* m, const std::string& wkey, int Cout, int nsrc, int Csrc, int ntaps,
-               const Fold* fold, const std::vector<float>* conv_bias, int relu, PackedConv& pc) {
+               const Fold* fold, const std::vector<float>* conv_bias, int relu, PackedConv& pc,
+               const std::vector<float>* w_override = nullptr) {
   const int Cin = nsrc * Csrc;
-  auto w = m->get(wkey, (size_t)Cout * Cin * ntaps);
-  if (!w) return false;
+  auto w = w_override ? w_override : m->get(wkey, (size_t)Cout * Cin * ntaps);
+  if (!w || w->size() != (size_t)Cout * Cin * ntaps) return false;
   pc.KC = std::min(64, Csrc);
   if (Csrc % pc.KC) return false;
   pc.ntaps = ntaps; pc.Ntot = Cout; pc.nsrc = nsrc; pc.C[0] = Csrc; pc.C[1] = nsrc > 1 ? Csrc : 0;
@@ -328,8 +355,16 @@ WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W) {
   return p;
 }
 
+struct HeadExtras {
+  const float* bias_tab = nullptr;
+  const float* hm_w = nullptr;
+  float* hm_out = nullptr;
+  int hm_sigmoid = 0;
+};
+
 int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
-             int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st) {
+             int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st,
+             const HeadExtras* ex = nullptr) {
   g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : ":tc")).c_str(),
               pc.flops_per_pixel * (double)NIMG * H * W, st);
   const float* bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
@@ -340,6 +375,7 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
     M.NIMG = NIMG; M.H = H; M.W = W;
     M.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off;
     M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out;
+    if (ex) { M.bias_tab = ex->bias_tab; M.hm_w = ex->hm_w; M.hm_out = ex->hm_out; M.hm_sigmoid = ex->hm_sigmoid; }
     return conv_march_launch(M, st);
   }
   ConvLaunch L;
@@ -452,6 +488,43 @@ extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
     auto b = m->get("unet.conv_final.bias", 32);
     if (!b || !pack_conv(m, "unet.conv_final.weight", 32, 1, 32, 1, nullptr, b, 0, m->conv_final)) return CETPICK_ERR_STATE;
     if (!pack_conv(m, "feature_head.0.weight", 32, 1, 32, 27, nullptr, nullptr, 1, m->fh0)) return CETPICK_ERR_STATE;
+    m->fold_cf = false;
+    if (m->fh0.march >= 0) {
+      // conv_final is a bias-carrying 1x1 conv with no activation between it and feature_head.0
+      // (unet.py:882 -> unet_small.py:85): fh0(Wc u + bc) = (W_t Wc) * u + sum over in-volume taps of
+      // W_t bc.  The second term depends only on which taps are inside the volume: a 64-row table.
+      auto wf = m->get("feature_head.0.weight", (size_t)32 * 32 * 27);
+      auto wc = m->get("unet.conv_final.weight", (size_t)32 * 32);
+      std::vector<float> wfold((size_t)32 * 32 * 27);
+      for (int co = 0; co < 32; ++co)
+        for (int ci = 0; ci < 32; ++ci)
+          for (int t = 0; t < 27; ++t) {
+            double a = 0.0;
+            for (int mid = 0; mid < 32; ++mid) a += (double)(*wf)[((size_t)co * 32 + mid) * 27 + t] * (double)(*wc)[mid * 32 + ci];
+            wfold[((size_t)co * 32 + ci) * 27 + t] = (float)a;
+          }
+      PackedConv folded;
+      if (!pack_conv(m, "", 32, 1, 32, 27, nullptr, nullptr, 1, folded, &wfold)) return CETPICK_ERR_STATE;
+      m->fh0 = folded;
+      m->fh0_btab = blob_alloc(m, (size_t)64 * 32 * 4);
+      float* tab = reinterpret_cast<float*>(m->blob.data() + m->fh0_btab);
+      for (int cz = 0; cz < 4; ++cz)
+        for (int cy = 0; cy < 4; ++cy)
+          for (int cx = 0; cx < 4; ++cx)
+            for (int co = 0; co < 32; ++co) {
+              double a = 0.0;
+              for (int kz = 0; kz < 3; ++kz)
+                for (int ky = 0; ky < 3; ++ky)
+                  for (int kx = 0; kx < 3; ++kx) {
+                    auto ok = [](int k, int c) { return k == 1 || (k == 0 && (c & 1)) || (k == 2 && (c & 2)); };
+                    if (!ok(kz, cz) || !ok(ky, cy) || !ok(kx, cx)) continue;
+                    for (int mid = 0; mid < 32; ++mid)
+                      a += (double)(*wf)[((size_t)co * 32 + mid) * 27 + (kz * 3 + ky) * 3 + kx] * (double)(*b)[mid];
+                  }
+              tab[((cz * 4 + cy) * 4 + cx) * 32 + co] = (float)a;
+            }
+      m->fold_cf = true;
+    }
     if (!pack_conv(m, "feature_head.2.weight", 32, 1, 32, 27, nullptr, nullptr, 1, m->fh2)) return CETPICK_ERR_STATE;
     taps_3x3x3_dil(m->fh0, 4, 4); taps_3x3x3_dil(m->fh2, 4, 4);
     auto hw = m->get("hm.weight", 32 * 3);
@@ -506,7 +579,7 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
     g_prof.begin();
     g_prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
     const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
-    const int grid = (int)std::min<long long>(tiles, (long long)sms * 8);
+    const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
     stem_kernel<<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
                                       reinterpret_cast<const float*>(blob + m->stem_w),
                                       reinterpret_cast<const float*>(blob + m->stem_b), buf(0, 0));
@@ -537,20 +610,38 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
     below = buf(j, 0);
   }
   const int h0 = dims[0].h, w0 = dims[0].w;
-  // conv_final (1x1 + bias): X0 -> X1 ; feature_head: X1 -> X0 -> X1 (3-D, z = image axis)
-  if ((rc = run_conv(m, "conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, "fhead0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
-  if ((rc = run_conv(m, "fhead2", m->fh2, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+  // conv_final (1x1 + bias) is folded into feature_head.0; feature_head: X0 -> X1 -> (X0 | hm).
+  // Without a `proj` request the hm head (+ _sigmoid) is fused into feature_head.2's epilogue and the
+  // 32-channel feature map is never written.
   {
-    const size_t plane = (size_t)h0 * w0, total = plane * D;
-    g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
-    const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
-    hm_head_kernel<<<grid, 256, 0, st>>>(buf(0, 1), D, plane, reinterpret_cast<const float*>(blob + m->hm_w),
-                                         apply_sigmoid, hm);
-    CETPICK_LAUNCH_CHECK();
-  }
-  if (proj) {
-    if ((rc = run_conv(m, "proj", m->proj, buf(0, 1), nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
+    const float* hmw = reinterpret_cast<const float*>(blob + m->hm_w);
+    const __nv_bfloat16* f_in = buf(0, 0);
+    if (!m->fold_cf) {
+      if ((rc = run_conv(m, "conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
+      if ((rc = run_conv(m, "fhead0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
+      f_in = buf(0, 0);
+    } else {
+      HeadExtras ex;
+      ex.bias_tab = reinterpret_cast<const float*>(blob + m->fh0_btab);
+      if ((rc = run_conv(m, "fhead0+conv_final", m->fh0, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st, &ex))) return rc;
+      f_in = buf(0, 1);
+    }
+    __nv_bfloat16* f_out = (f_in == buf(0, 1)) ? buf(0, 0) : buf(0, 1);
+    if (!proj && m->fh2.march >= 0) {
+      HeadExtras ex;
+      ex.hm_w = hmw; ex.hm_out = hm; ex.hm_sigmoid = apply_sigmoid;
+      if ((rc = run_conv(m, "fhead2+hm", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, nullptr, 0, 0, 0, st, &ex))) return rc;
+    } else {
+      if ((rc = run_conv(m, "fhead2", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, f_out, 0, 0, 0, st))) return rc;
+      const size_t plane = (size_t)h0 * w0, total = plane * D;
+      g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
+      const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
+      hm_head_kernel<<<grid, 256, 0, st>>>(f_out, D, plane, hmw, apply_sigmoid, hm);
+      CETPICK_LAUNCH_CHECK();
+      if (proj) {
+        if ((rc = run_conv(m, "proj", m->proj, f_out, nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;
+      }
+    }
   }
   g_prof.mark("end", 0.0, st);
   return CETPICK_OK;
