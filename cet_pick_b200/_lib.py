@@ -41,6 +41,7 @@ SIGNATURES = {
     "cetpick_probe_umma": (_int, [_vp, _int, _vp, _int, _int, _int, _int, _vp, _vp]),
     "cetpick_conv_march_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
                                        _vp, _vp]),
+    "cetpick_upconv_bf16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _vp, _int, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
 }

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_march.cuh"
+#include "conv_up.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -189,6 +190,7 @@ struct PackedConv {
   size_t w_off = 0, b_off = 0;   // byte offsets into the device weight blob
   bool has_bias = false;
   double flops_per_pixel = 0;    // 2 * K * N
+  bool upk = false;              // ConvTranspose weights packed for conv_up.cu
   int march = -1;                // >= 0: MarchMode of conv_march.cu (w_off then holds ITS weight image)
 };
 
@@ -459,17 +461,24 @@ extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
       auto b = m->get(p + ".upconv.bias", outs);
       if (!w || !b || !bn_fold(m, p + ".norm0", outs, f)) return CETPICK_ERR_STATE;
       u.KC = std::min(64, ins); u.ntaps = 1; u.Ntot = 4 * outs; u.nsrc = 1; u.C[0] = ins; u.relu = 1;
-      const int chunks = ins / u.KC;
-      u.w_off = blob_alloc(m, (size_t)chunks * u.Ntot * u.KC * 2);
-      uint16_t* dst = reinterpret_cast<uint16_t*>(m->blob.data() + u.w_off);
-      for (int ch = 0; ch < chunks; ++ch)
-        for (int q = 0; q < 4; ++q)
-          for (int co = 0; co < outs; ++co)
-            for (int k = 0; k < u.KC; ++k) {
-              const int ci = ch * u.KC + k;
-              const double v = (double)(*w)[((size_t)ci * outs + co) * 4 + q] * f.scale[co];
-              dst[((size_t)ch * u.Ntot + q * outs + co) * u.KC + k] = f2bf_host((float)v);
-            }
+      if (upconv_supported(ins, outs)) {
+        const std::vector<uint16_t> pk = upconv_pack_weights(w->data(), ins, outs, f.scale.data());
+        u.upk = true;
+        u.w_off = blob_alloc(m, pk.size() * 2);
+        memcpy(m->blob.data() + u.w_off, pk.data(), pk.size() * 2);
+      } else {
+        const int chunks = ins / u.KC;
+        u.w_off = blob_alloc(m, (size_t)chunks * u.Ntot * u.KC * 2);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(m->blob.data() + u.w_off);
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < outs; ++co)
+              for (int k = 0; k < u.KC; ++k) {
+                const int ci = ch * u.KC + k;
+                const double v = (double)(*w)[((size_t)ci * outs + co) * 4 + q] * f.scale[co];
+                dst[((size_t)ch * u.Ntot + q * outs + co) * u.KC + k] = f2bf_host((float)v);
+              }
+      }
       u.has_bias = true;
       u.b_off = blob_alloc(m, (size_t)u.Ntot * 4);
       float* bb = reinterpret_cast<float*>(m->blob.data() + u.b_off);
@@ -604,7 +613,15 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   for (int i = 0; i < nb - 1; ++i) {
     const int j = nb - 2 - i;
     const int h = dims[j].h, w = dims[j].w, Cout = 32 << j;
-    if ((rc = run_conv(m, "up" + std::to_string(i) + ".upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
+    if (m->upc[i].upk) {
+      const PackedConv& u = m->upc[i];
+      g_prof.mark(("conv:up" + std::to_string(i) + ".upconv:up").c_str(), u.flops_per_pixel * (double)D * dims[j + 1].h * dims[j + 1].w, st);
+      UpLaunch U;
+      U.src = below; U.Cin = u.C[0]; U.NIMG = D; U.h = dims[j + 1].h; U.w = dims[j + 1].w;
+      U.wpk = blob + u.w_off; U.bias = reinterpret_cast<const float*>(blob + u.b_off);
+      U.Cout = Cout; U.out = buf(j, 0); U.Ho = h; U.Wo = w;
+      if ((rc = conv_up_launch(U, st))) return rc;
+    } else if ((rc = run_conv(m, "up" + std::to_string(i) + ".upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
     if ((rc = run_conv(m, "up" + std::to_string(i) + ".c1", m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
     if ((rc = run_conv(m, "up" + std::to_string(i) + ".c2", m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
     below = buf(j, 0);

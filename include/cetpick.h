@@ -158,6 +158,12 @@ int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const
                             int NIMG, int H, int W, const float* w_host, int Cout,
                             const float* bias, int relu, void* out, void* stream);
 
+/* Test hook: ConvTranspose2d(Cin,Cout,2,stride 2)+bias+ReLU through csrc/conv_up.cu.  src: bf16 device
+ * [NIMG][h][w][Cin]; w_host: fp32 HOST weight in PyTorch layout (Cin,Cout,2,2); bias_host: fp32 HOST
+ * [Cout]; out: bf16 device [NIMG][Ho][Wo][Cout] with Ho <= 2h, Wo <= 2w (autocrop).  Synchronises. */
+int cetpick_upconv_bf16(const void* src, int Cin, int NIMG, int h, int w, const float* w_host,
+                        const float* bias_host, int Cout, void* out, int Ho, int Wo, void* stream);
+
 /* Hardware probe (test hook): D[128][32] = A_big[rows] * B^T where the A descriptor starts r0 rows
  * into a TMA-written swizzled tile, with 8-row groups sbo_bytes apart and the given base_offset. */
 int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,

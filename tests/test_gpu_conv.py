@@ -207,3 +207,21 @@ def test_march3d_dilated_27_taps(L, d, h, w):
     xin = x.float().permute(3, 0, 1, 2)[None]
     ref = F.relu(F.conv3d(xin, wt.float(), padding=(1, 4, 4), dilation=(1, 4, 4)))[0].permute(1, 2, 3, 0)
     assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("cin,cout,n,h,w,Ho,Wo", [(64, 32, 2, 6, 9, 12, 18), (256, 128, 2, 5, 7, 9, 13),
+                                                  (128, 64, 3, 4, 4, 7, 8), (64, 32, 5, 33, 47, 66, 93),
+                                                  (128, 64, 2, 40, 40, 80, 80), (256, 128, 1, 16, 24, 32, 48)])
+def test_conv_up_kernel(L, cin, cout, n, h, w, Ho, Wo):
+    """csrc/conv_up.cu: resident weights, flat pixel tiles, pixel-shuffle epilogue with autocrop"""
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + h)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cin, cout, 2, 2, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = torch.full((n, Ho, Wo, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wh, bh = wt.float().cpu().contiguous(), b.cpu().contiguous()
+    L.check(L.lib().cetpick_upconv_bf16(x.data_ptr(), cin, n, h, w, wh.data_ptr(), bh.data_ptr(), cout,
+                                        out.data_ptr(), Ho, Wo, L.stream_ptr()), "cetpick_upconv_bf16")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2))[:, :, :Ho, :Wo]
+    assert (out.float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 2e-2
