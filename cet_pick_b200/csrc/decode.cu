@@ -17,6 +17,8 @@
 // volume (exact, 3 extra reads) -- every kernel is always enqueued and exits early on device-side
 // state, so the call never synchronises the host.
 #include "common.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
 #include <algorithm>
 
 namespace cetpick {
@@ -52,7 +54,8 @@ struct DecodeState {
   uint32_t pad[3];
 };
 
-struct ScanParams {
+struct alignas(64) ScanParams {
+  CUtensorMap tm;      // TMA path: (W,H,D) fp32 map, box (PITCH, TY+2P, 1), out-of-bounds = NaN (ignored by fmaxf)
   const float* heat;
   int D, H, W;
   int zlo, zhi;        // planes whose voxels are emitted
@@ -65,6 +68,7 @@ struct ScanParams {
   int phase;           // 0 = first COLLECT (may request fallback), 1 = fallback COLLECT
   int collect_all;     // COLLECT: append every voxel (small volumes)
   int vec_ok;          // rows are 16-byte aligned: use 16-byte cp.async
+  int use_tma;         // rows are 16-byte aligned: TMA ring (host-side choice)
   int K;
   uint32_t k_select;   // HIST pass 0: rank to select
   uint32_t cap_gt;     // capacity reserved for COLLECT entries
@@ -176,11 +180,17 @@ __device__ __forceinline__ void load_plane(float* buf, const float* plane, int y
   }
 }
 
+// max of three floats in one instruction (PTX ISA 8.6, sm_100+); NaN operands are ignored like fmaxf
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 template <int P>
 __device__ __forceinline__ void compute_plane(const float* buf, int fiber, PlaneRegs<P>& out) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float hm[4 + 2 * P][4];
-  float ctr[4][4];
 #pragma unroll
   for (int rr = 0; rr < 4 + 2 * P; ++rr) {
     const float* row = buf + (ty * 4 + rr) * PITCH + XH + 4 * tx;
@@ -191,50 +201,80 @@ __device__ __forceinline__ void compute_plane(const float* buf, int fiber, Plane
       // halo columns come from the neighbouring lanes; the warp's two edge lanes read smem
       float l = __shfl_up_sync(0xffffffffu, q.w, 1);
       float r = __shfl_down_sync(0xffffffffu, q.x, 1);
-      if (tx == 0) l = row[-1];
-      if (tx == 31) r = row[4];
+      {
+        const uint32_t ra = (uint32_t)__cvta_generic_to_shared(row);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1;\n\t"
+            "setp.eq.s32 p0, %2, 0;\n\t"
+            "setp.eq.s32 p1, %2, 31;\n\t"
+            "@p0 ld.shared.f32 %0, [%3+-4];\n\t"
+            "@p1 ld.shared.f32 %1, [%3+16];\n\t"
+            "}\n"
+            : "+f"(l), "+f"(r)
+            : "r"(tx), "r"(ra));
+      }
       w[0] = l; w[5] = r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hm[rr][i] = fmax3(w[i], w[i + 1], w[i + 2]);
     } else {
 #pragma unroll
       for (int k = 0; k < P; ++k) { w[k] = row[k - P]; w[P + 4 + k] = row[4 + k]; }
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float m = w[i];
+      for (int i = 0; i < 4; ++i) {
+        float m = w[i];
 #pragma unroll
-      for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, w[i + k]);
-      hm[rr][i] = m;
+        for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, w[i + k]);
+        hm[rr][i] = m;
+      }
     }
     if (rr >= P && rr < P + 4) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ctr[rr - P][i] = w[P + i];
+      for (int i = 0; i < 4; ++i) out.c[rr - P][i] = w[P + i];
     }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float m = hm[j][i];
+      float m;
+      if (P == 1) {
+        m = fmax3(hm[j][i], hm[j + 1][i], hm[j + 2][i]);
+      } else {
+        m = hm[j][i];
 #pragma unroll
-      for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, hm[j + k][i]);
-      const float v = ctr[j][i];
+        for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, hm[j + k][i]);
+      }
       if (fiber) {  // decode.py:11-17 on this plane: o1 = v * (m == v)
+        const float v = out.c[j][i];
         const float o1 = (v == m) ? v : v * 0.0f;
         out.a[j][i] = o1;
         out.c[j][i] = o1;
       } else {
         out.a[j][i] = m;
-        out.c[j][i] = v;
       }
     }
 }
 
+// TMA = true: the planes arrive through a ring of NBUF TMA boxes (one elected thread issues, an
+// mbarrier per slot signals arrival), so several planes per CTA are in flight and no thread spends
+// issue slots on address arithmetic; needs 16-byte aligned rows.  TMA = false: cp.async double
+// buffer for unaligned maps.
+constexpr int NBUF = 4;
 template <int P>
-__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams p) {
+constexpr int plane_buf_floats() { return ((TY + 2 * P) * PITCH * 4 + 127) / 128 * 32; }
+
+// MODE_T / FIBER_T >= 0 fix the pass and the fiber flag at compile time (the TMA instantiations, so
+// each carries only its own emit code); -1 = take them from the parameters.
+template <int P, bool TMA, int MODE_T, int FIBER_T>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_constant__ ScanParams p) {
   constexpr int ROWS = TY + 2 * P;
-  extern __shared__ __align__(16) float smem[];
-  float* bufs[2] = {smem, smem + ROWS * PITCH};
-  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + 2 * ROWS * PITCH);
+  constexpr int BUF = plane_buf_floats<P>();
+  constexpr int NB = TMA ? NBUF : 2;
+  extern __shared__ __align__(128) float smem[];
+  auto bufs = [&](int b) { return smem + b * BUF; };
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + NB * BUF);
+  __shared__ __align__(8) uint64_t s_full[NBUF];
   __shared__ uint32_t s_eq[MAX_ZC];
   __shared__ uint32_t s_sel[2];
   __shared__ uint32_t s_ticket;
@@ -242,14 +282,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
   DecodeState* st = p.st;
   if (p.gate && st->need_fallback == 0) return;
   int zlo = p.zlo, zhi = p.zhi;
-  if (p.mode == MODE_EQ) {
+  if (((MODE_T >= 0) ? MODE_T : p.mode) == MODE_EQ) {
     if (st->eq_need == 0) return;
     zhi = min(zhi, st->eq_zc + 1);
   }
-  const int mode = p.mode;
+  const int mode = (MODE_T >= 0) ? MODE_T : p.mode;
   const int H = p.H, W = p.W, D = p.D;
-  const bool znbr = p.nms_mode != CETPICK_NMS_NONE;
-  const int fiber = p.nms_mode == CETPICK_NMS_FIBER;
+  const bool znbr = (P > 0) ? true : (p.nms_mode != CETPICK_NMS_NONE);   // P > 0 implies an NMS mode
+  const int fiber = (FIBER_T >= 0) ? FIBER_T : (p.nms_mode == CETPICK_NMS_FIBER);
   const uint32_t t0key = st->t0key;
   // HIST filter: keys whose bits above (shift+bits) equal the prefix chosen so far
   const int hs = p.shift + p.bits;
@@ -259,6 +299,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
   if (mode == MODE_HIST) {
     for (int i = threadIdx.x; i < HIST_BINS; i += SCAN_THREADS) s_hist[i] = 0;
   }
+  if (TMA && threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&p.tm);
+    for (int b = 0; b < NBUF; ++b) ptx::mbar_init(&s_full[b], 1);
+    ptx::fence_barrier_init();
+  }
+  uint32_t n_iss = 0, n_cons = 0;   // TMA ring: planes issued / consumed so far (uniform across the CTA)
   __syncthreads();
 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, lane = tx;
@@ -266,6 +312,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
   const int nzc = (zhi > zlo) ? ceil_div(zhi - zlo, p.ZC) : 0;
   const long long items = (long long)ntx * nty * nzc;
   const size_t plane_sz = (size_t)H * W;
+  const float t0f = key2f(t0key);
+  // non-survivors carry KEY_ZERO: do they matter to this pass? (collect-all, a threshold <= 0, ...)
+  const bool zgen = (mode == MODE_COLLECT) ? (p.collect_all || KEY_ZERO >= t0key)
+                                            : (mode == MODE_EQ) ? (t0key == KEY_ZERO) : false;
   uint32_t zero_cnt = 0;   // HIST: voxels with okey == KEY_ZERO seen by this thread
   bool saw_nan = false;
 
@@ -279,84 +329,172 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
     if (mode == MODE_COLLECT) {
       for (int i = threadIdx.x; i < MAX_ZC; i += SCAN_THREADS) s_eq[i] = 0;
     }
-    PlaneRegs<P> prev, cur, nxt;
+    // Three register sets rotate through the roles (plane below, centre plane, incoming plane): the
+    // plane loop is unrolled by three, so nothing is copied per plane and max over z is one max3.
+    PlaneRegs<P> R0, R1, R2;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { prev.a[j][i] = cur.a[j][i] = -INFINITY; prev.c[j][i] = cur.c[j][i] = 0.f; }
+      for (int i = 0; i < 4; ++i) {
+        R0.a[j][i] = R1.a[j][i] = R2.a[j][i] = -INFINITY;
+        R0.c[j][i] = R1.c[j][i] = R2.c[j][i] = 0.f;
+      }
+    const bool tile_full = (x0 + TX <= W) && (y0 + TY <= H);
 
-    {
+    // plane i of the item is pz = z0-1+i; it is fetched when it exists and is either emitted or a z neighbour
+    auto fetched = [&](int i) {
+      const int pz = z0 - 1 + i;
+      return (pz >= 0) && (pz < D) && (((i >= 1) && (i <= nplanes - 2)) || znbr);
+    };
+    int iss = 0;                       // TMA: next plane of this item to issue
+    auto issue_more = [&]() {
+      while (iss < nplanes && n_iss - n_cons < (uint32_t)NBUF) {
+        if (fetched(iss)) {
+          if (threadIdx.x == 0) {
+            const uint32_t b = n_iss % NBUF;
+            ptx::mbar_arrive_expect_tx(&s_full[b], (uint32_t)(ROWS * PITCH * 4));
+            ptx::tma_load_3d(bufs(b), &p.tm, &s_full[b], x0 - XH, y0 - P, z0 - 1 + iss);
+          }
+          ++n_iss;
+        }
+        ++iss;
+      }
+    };
+    if (TMA) {
+      issue_more();
+    } else {
       const int pz = z0 - 1;
-      if (znbr && pz >= 0) load_plane<P>(bufs[0], p.heat + (size_t)pz * plane_sz, y0, x0, H, W, p.vec_ok);
+      if (znbr && pz >= 0) load_plane<P>(bufs(0), p.heat + (size_t)pz * plane_sz, y0, x0, H, W, p.vec_ok);
       cp_async_commit();
     }
-    for (int i = 0; i < nplanes; ++i) {
+
+    // one plane: bring plane i into `nx`, then emit plane i-1 (centre `cu`, plane below `pv`)
+    auto step = [&](int i, const PlaneRegs<P>& pv, const PlaneRegs<P>& cu, PlaneRegs<P>& nx) {
       const int pz = z0 - 1 + i;
       const bool interior = (i >= 1) && (i <= nplanes - 2);   // an emitted plane
-      if (i + 1 < nplanes) {
-        const int qz = pz + 1;
-        const bool qint = (i + 1 <= nplanes - 2);
-        if (qz < D && (qint || znbr))
-          load_plane<P>(bufs[(i + 1) & 1], p.heat + (size_t)qz * plane_sz, y0, x0, H, W, p.vec_ok);
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
       const bool have = (pz >= 0) && (pz < D) && (interior || znbr);
+      const float* cbuf = bufs(i & 1);
+      if (TMA) {
+        if (have) {
+          const uint32_t b = n_cons % NBUF;
+          ptx::mbar_wait(&s_full[b], (n_cons / NBUF) & 1u);
+          cbuf = bufs(b);
+        }
+      } else {
+        if (i + 1 < nplanes) {
+          const int qz = pz + 1;
+          const bool qint = (i + 1 <= nplanes - 2);
+          if (qz < D && (qint || znbr))
+            load_plane<P>(bufs((i + 1) & 1), p.heat + (size_t)qz * plane_sz, y0, x0, H, W, p.vec_ok);
+          cp_async_commit();
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        __syncthreads();
+      }
       if (have) {
-        compute_plane<P>(bufs[i & 1], fiber, nxt);
+        compute_plane<P>(cbuf, fiber, nx);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { nxt.a[j][k] = -INFINITY; nxt.c[j][k] = 0.f; }
+          for (int k = 0; k < 4; ++k) { nx.a[j][k] = -INFINITY; nx.c[j][k] = 0.f; }
+      }
+      if (TMA) {
+        if (have) ++n_cons;
+        __syncthreads();               // every thread has copied what it needs out of the slot
+        issue_more();                  // refill the ring while this plane is emitted
       }
       if (i >= 2) {
-        // ---- emit plane ez = pz - 1 from (prev, cur, nxt) ----
+        // ---- emit plane ez = pz - 1: centre = cu, z neighbours = pm (two planes back, centre) and nx ----
         const int ez = pz - 1;
-        uint32_t okey[4][4];
-        uint32_t n_gt = 0, n_eq = 0;
+        // bit j*4+k.  HIST / generic: voxel is an NMS survivor (c == max of its window).  COLLECT / EQ
+        // fast path: survivor AND c >= threshold -- the only voxels that can matter, and they are rare
+        // whatever the map looks like (plateaus survive NMS everywhere but sit below the threshold).
+        const bool need_all = zgen || (mode == MODE_HIST);
+        uint32_t mask = 0;
+        float nansum = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float c = cur.c[j][k];
+            const float c = cu.c[j][k];
             // NMS_NONE (plain top-K) has no z neighbourhood at all
-            const float m3 = znbr ? fmaxf(fmaxf(prev.a[j][k], cur.a[j][k]), nxt.a[j][k]) : cur.a[j][k];
-            const bool valid = (y0 + ty * 4 + j < H) && (x0 + tx * 4 + k < W);
-            uint32_t ok = (c == m3) ? f2key(c) : KEY_ZERO;
-            saw_nan |= valid && (c != c);
-            if (!valid) ok = 0;  // key 0 never matches anything below
-            okey[j][k] = ok;
-            if (mode == MODE_COLLECT) {
-              n_gt += (valid && (p.collect_all || ok > t0key)) ? 1u : 0u;
-              n_eq += (valid && ok == t0key) ? 1u : 0u;
-            } else if (mode == MODE_EQ) {
-              n_gt += (valid && ok == t0key) ? 1u : 0u;
-            }
+            const float m3 = znbr ? fmax3(pv.a[j][k], cu.a[j][k], nx.a[j][k]) : cu.a[j][k];
+            const bool s = need_all ? (c == m3) : ((c == m3) && (c >= t0f));
+            mask |= s ? (1u << (j * 4 + k)) : 0u;
+            nansum += c;
           }
-        if (mode == MODE_HIST) {
-          uint32_t run_key = 0, run_cnt = 0;
+        uint32_t vmask = 0xFFFFu;
+        if (!tile_full) {
+          vmask = 0;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t ok = okey[j][k];
-              if (ok == 0) continue;
-              if (hs < 32 && (ok >> hs) != prefix) continue;
-              if (ok == KEY_ZERO) { ++zero_cnt; continue; }
-              if (ok == run_key) { ++run_cnt; continue; }
-              if (run_cnt) atomicAdd(&s_hist[(run_key >> p.shift) & dmask], run_cnt);
-              run_key = ok; run_cnt = 1;
+            for (int k = 0; k < 4; ++k)
+              vmask |= ((y0 + ty * 4 + j < H) && (x0 + tx * 4 + k < W)) ? (1u << (j * 4 + k)) : 0u;
+          mask &= vmask;
+        }
+        if (nansum != nansum) {        // a NaN (or +inf with -inf) among the 16 centres: look exactly
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) saw_nan |= ((vmask >> (j * 4 + k)) & 1u) && (cu.c[j][k] != cu.c[j][k]);
+        }
+        // every voxel that is not a survivor has key KEY_ZERO; zgen = those zeros matter to this pass
+        uint32_t take = 0;             // COLLECT / EQ: voxels to append
+        uint32_t n_eq = 0;
+        if (!zgen) {
+          if (mode == MODE_HIST) {
+            zero_cnt += __popc(vmask) - __popc(mask);
+            if (mask) {
+#pragma unroll
+              for (int b = 0; b < 16; ++b)
+                if ((mask >> b) & 1u) {
+                  const uint32_t ok = f2key(cu.c[b >> 2][b & 3]);
+                  if (hs < 32 && (ok >> hs) != prefix) continue;
+                  if (ok == KEY_ZERO) ++zero_cnt;
+                  else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
+                }
             }
-          if (run_cnt) atomicAdd(&s_hist[(run_key >> p.shift) & dmask], run_cnt);
+          } else if (mask) {
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+              const float c = cu.c[b >> 2][b & 3];
+              const bool on = (mask >> b) & 1u;
+              if (mode == MODE_COLLECT) {
+                take |= (on && c > t0f) ? (1u << b) : 0u;       // key order == float order (c is not NaN)
+                n_eq += (on && !(c > t0f)) ? 1u : 0u;
+              } else {
+                take |= (on && !(c > t0f)) ? (1u << b) : 0u;
+              }
+            }
+          }
         } else {
+          // generic path: zeros are candidates / equal to the threshold (tiny or degenerate maps)
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            if (!((vmask >> b) & 1u)) continue;
+            const uint32_t ok = ((mask >> b) & 1u) ? f2key(cu.c[b >> 2][b & 3]) : KEY_ZERO;
+            if (mode == MODE_HIST) {
+              if (hs < 32 && (ok >> hs) != prefix) continue;
+              if (ok == KEY_ZERO) ++zero_cnt;
+              else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
+            } else if (mode == MODE_COLLECT) {
+              take |= (p.collect_all || ok > t0key) ? (1u << b) : 0u;
+              n_eq += (ok == t0key) ? 1u : 0u;
+            } else {
+              take |= (ok == t0key) ? (1u << b) : 0u;
+            }
+          }
+        }
+        if (mode != MODE_HIST) {
           if (mode == MODE_COLLECT) {
             const uint32_t weq = __reduce_add_sync(0xffffffffu, n_eq);
             if (lane == 0 && weq) atomicAdd(&s_eq[ez - z0], weq);
           }
+          const uint32_t n_gt = __popc(take);
           if (__any_sync(0xffffffffu, n_gt != 0)) {
             uint32_t incl = n_gt;
 #pragma unroll
@@ -368,32 +506,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
             if (lane == 31) base = atomicAdd(&st->cand_count, incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             uint32_t off = base + incl - n_gt;
-            const uint32_t cap = p.cap_total;
-            const uint32_t lim = (mode == MODE_COLLECT) ? p.cap_gt : cap;
+            const uint32_t lim = (mode == MODE_COLLECT) ? p.cap_gt : p.cap_total;
+            if (take) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t ok = okey[j][k];
-                const bool take = (ok != 0) && ((mode == MODE_COLLECT) ? (p.collect_all || ok > t0key)
-                                                                        : (ok == t0key));
-                if (take) {
+              for (int b = 0; b < 16; ++b)
+                if ((take >> b) & 1u) {
                   if (off < lim) {
+                    const uint32_t ok = ((mask >> b) & 1u) ? f2key(cu.c[b >> 2][b & 3]) : KEY_ZERO;
                     const uint32_t idx = (uint32_t)((size_t)ez * plane_sz +
-                                                    (size_t)(y0 + ty * 4 + j) * W + (x0 + tx * 4 + k));
+                                                    (size_t)(y0 + ty * 4 + (b >> 2)) * W + (x0 + tx * 4 + (b & 3)));
                     p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
                   }
                   ++off;
                 }
-              }
+            }
           }
         }
       }
-      prev = cur;
-      cur = nxt;
-      __syncthreads();
+      if (!TMA) __syncthreads();
+    };
+    for (int i = 0; i < nplanes; i += 3) {
+      step(i, R1, R2, R0);
+      if (i + 1 < nplanes) step(i + 1, R2, R0, R1);
+      if (i + 2 < nplanes) step(i + 2, R0, R1, R2);
     }
     if (mode == MODE_COLLECT) {
+      if (TMA) __syncthreads();
       for (int i = threadIdx.x; i < z1 - z0; i += SCAN_THREADS)
         if (s_eq[i]) atomicAdd(&p.eqcnt[z0 + i], s_eq[i]);
       __syncthreads();
@@ -658,19 +796,36 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   return L;
 }
 
-template <int P>
-int launch_scan(const ScanParams& p, int grid, cudaStream_t s) {
-  constexpr int ROWS = TY + 2 * P;
-  const size_t smem = (size_t)2 * ROWS * PITCH * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+template <int P, bool TMA, int MODE_T, int FIBER_T>
+int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
+  const size_t smem = (size_t)(TMA ? NBUF : 2) * plane_buf_floats<P>() * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+  auto kern = scan_kernel<P, TMA, MODE_T, FIBER_T>;
   static bool attr_done = false;
   if (!attr_done) {
-    CETPICK_CUDA(cudaFuncSetAttribute(scan_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+    CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  scan_kernel<P><<<grid, SCAN_THREADS, smem, s>>>(p);
+  kern<<<grid, SCAN_THREADS, smem, s>>>(p);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
+}
+
+template <int P, int FIBER_T>
+int launch_scan_m(const ScanParams& p, int grid, cudaStream_t s) {
+  switch (p.mode) {
+    case MODE_HIST: return launch_scan_t<P, true, MODE_HIST, FIBER_T>(p, grid, s);
+    case MODE_COLLECT: return launch_scan_t<P, true, MODE_COLLECT, FIBER_T>(p, grid, s);
+    default: return launch_scan_t<P, true, MODE_EQ, FIBER_T>(p, grid, s);
+  }
+}
+
+template <int P>
+int launch_scan(const ScanParams& p, int grid, cudaStream_t s) {
+  if (!p.use_tma) return launch_scan_t<P, false, -1, -1>(p, grid, s);   // unaligned rows: generic cp.async kernel
+  if constexpr (P == 1) {
+    if (p.nms_mode == CETPICK_NMS_FIBER) return launch_scan_m<P, 1>(p, grid, s);
+  }
+  return launch_scan_m<P, 0>(p, grid, s);
 }
 
 int launch_scan_p(int P, const ScanParams& p, int grid, cudaStream_t s) {
@@ -721,6 +876,15 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   p.nms_mode = nms_mode; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand;
   p.cap_gt = L.cap_gt; p.cap_total = L.cap_total;
   p.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
+  p.use_tma = 0;
+  if (p.vec_ok) {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)D};
+    const uint64_t strides[2] = {(uint64_t)W * 4, (uint64_t)W * H * 4};
+    const uint32_t box[3] = {(uint32_t)PITCH, (uint32_t)(TY + 2 * P), 1};
+    int trc = tmap_encode_f32_nanfill(&p.tm, heat, 3, dims, strides, box);
+    if (trc) return trc;
+    p.use_tma = 1;
+  }
   const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
 
   auto run_select = [&](int zlo, int zhi, int gate) -> int {
