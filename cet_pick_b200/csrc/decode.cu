@@ -51,7 +51,8 @@ struct DecodeState {
   unsigned long long csel_prefix;  // candidate radix select prefix (right aligned)
   unsigned long long kth_comp;     // exact K-th largest composite
   uint32_t n_final;        // number of candidates the final select saw
-  uint32_t pad[3];
+  uint32_t csel_done;     // candidate select resolved after the key digits (no ties at the K-th key)
+  uint32_t pad[2];
 };
 
 struct alignas(64) ScanParams {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // the cumulative count reaches kleft.  Runs in ONE CTA (the last one to finish a HIST pass).
 // Returns the chosen digit and the rank left inside it through shared memory.
 __device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* s_hist,
-                             uint32_t* s_out /*[2]*/) {
+                             uint32_t* s_out /*[3]: digit, rank left, bin count*/) {
   for (int i = threadIdx.x; i < nb; i += blockDim.x) {
     s_hist[i] = ghist[i];
     ghist[i] = 0;  // ready for the next pass
@@ -126,7 +127,7 @@ __device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* 
     bool mine = (excl < kleft) && (incl >= kleft);
     unsigned who = __ballot_sync(0xffffffffu, mine);
     if (who == 0) {  // fewer than kleft elements in total: take the lowest non-empty bin
-      if (lane == 0) { s_out[0] = 0; s_out[1] = 0xffffffffu; }
+      if (lane == 0) { s_out[0] = 0; s_out[1] = 0xffffffffu; s_out[2] = 0; }
     } else if (lane == __ffs(who) - 1) {
       uint32_t cum = excl;
       int d = nb - 1 - lane * per;
@@ -137,6 +138,7 @@ __device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* 
       }
       s_out[0] = (uint32_t)d;
       s_out[1] = kleft - cum;
+      s_out[2] = s_hist[d];
     }
   }
   __syncthreads();
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + NB * BUF);
   __shared__ __align__(8) uint64_t s_full[NBUF];
   __shared__ uint32_t s_eq[MAX_ZC];
-  __shared__ uint32_t s_sel[2];
+  __shared__ uint32_t s_sel[3];
   __shared__ uint32_t s_ticket;
 
   DecodeState* st = p.st;
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       st->sel_kleft = s_sel[1];
       if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
       if (p.last_pass) {
-        st->t0key = np;
+        st->t0key = np << p.shift;   // all 32 bits after three digits; the bin's lower edge after two
         if (p.gate) {  // fallback select finished: restart the candidate list for COLLECT phase 1
           st->cand_count = 0;
         }
@@ -616,8 +618,9 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
     const unsigned long long* __restrict__ cand, DecodeState* st, uint32_t* ghist, int shift,
     int bits, int first, int last, uint32_t cap_total, int K) {
   __shared__ uint32_t s_hist[HIST_BINS];
-  __shared__ uint32_t s_sel[2];
+  __shared__ uint32_t s_sel[3];
   __shared__ uint32_t s_ticket;
+  if (!first && st->csel_done) return;     // the key digits already fixed the K-th composite
   const uint32_t n = min(st->cand_count, cap_total);
   const int hs = shift + bits;
   const unsigned long long prefix = first ? 0ull : st->csel_prefix;
@@ -646,6 +649,12 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
     if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
     if (first) st->n_final = n;
     if (last) { st->kth_comp = np; st->out_count = 0; }
+    if (shift == 32 && s_sel[1] == s_sel[2]) {
+      // every candidate with the K-th key is needed (the usual case: no ties): skip the index digits
+      st->kth_comp = np << 32;
+      st->out_count = 0;
+      st->csel_done = 1;
+    }
     st->done_ctr = 0;
   }
 }
@@ -662,6 +671,67 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_compact_kernel(
       if (o < (uint32_t)K) out[o] = c;
     }
   }
+}
+
+// K <= RANK_MAX_K: the K composites are distinct, so rank = #{composites greater than mine} is the
+// output row.  rank_kernel counts against one slice of the list per blockIdx.y (slice in shared
+// memory, broadcast reads); rank_write_kernel writes the picks.  O(K^2 / PARTS) per thread, all SMs
+// busy: ~20 us at K = 10 000 where a one-CTA bitonic sort needs ~260 us.
+constexpr int RANK_MAX_K = 16384, RANK_PARTS = 16, RANK_THREADS = 128;
+
+__global__ void __launch_bounds__(RANK_THREADS) rank_kernel(const unsigned long long* __restrict__ keys, int K,
+                                                            uint32_t* __restrict__ ranks) {
+  __shared__ unsigned long long s_k[RANK_MAX_K / RANK_PARTS];
+  const int per = ceil_div(K, RANK_PARTS);
+  const int j0 = blockIdx.y * per, j1 = min(K, j0 + per);
+  for (int j = j0 + threadIdx.x; j < j1; j += RANK_THREADS) s_k[j - j0] = keys[j];
+  __syncthreads();
+  const int r = blockIdx.x * RANK_THREADS + threadIdx.x;
+  if (r >= K) return;
+  const unsigned long long c = keys[r];
+  uint32_t cnt = 0;
+  const int n = j1 - j0;
+  int j = 0;
+  for (; j + 4 <= n; j += 4) {
+    cnt += (s_k[j] > c) + (s_k[j + 1] > c) + (s_k[j + 2] > c) + (s_k[j + 3] > c);
+  }
+  for (; j < n; ++j) cnt += (s_k[j] > c);
+  if (cnt) atomicAdd(&ranks[r], cnt);
+}
+
+__device__ __forceinline__ void write_pick(unsigned long long c, int r, const float* __restrict__ heat,
+                                           const float* __restrict__ reg, size_t n_vox, int hw, int W,
+                                           float* __restrict__ dets, long long* __restrict__ inds) {
+  const float fhw = (float)hw, fw = (float)W;
+  const uint32_t key = (uint32_t)(c >> 32);
+  const uint32_t idx = ~(uint32_t)c;
+  float score;
+  if (key == KEY_ZERO) score = copysignf(0.0f, heat[idx]);   // heat*0 keeps the sign of heat
+  else score = key2f(key);
+  const float zf = floorf((float)idx / fhw);                  // decode.py:36 (fp32 division)
+  const int z = (int)zf;
+  const int t = (int)idx - z * hw;                            // decode.py:37 (int32)
+  const float yf = floorf((float)t / fw);                     // decode.py:38 (stays fp32)
+  int x = t % W;                                              // decode.py:39 (sign of divisor)
+  if (x < 0) x += W;
+  float xo, yo;
+  if (reg) { xo = (float)x + reg[idx]; yo = yf + reg[n_vox + idx]; }
+  else { xo = (float)x + 0.25f; yo = yf + 0.25f; }
+  float* d = dets + (size_t)r * 5;
+  d[0] = xo; d[1] = yo; d[2] = (float)z; d[3] = score; d[4] = score;
+  if (inds) inds[r] = (long long)idx;
+}
+
+__global__ void __launch_bounds__(256) rank_write_kernel(const unsigned long long* __restrict__ keys, int K,
+                                                         uint32_t* __restrict__ ranks,
+                                                         const float* __restrict__ heat,
+                                                         const float* __restrict__ reg, int D, int H, int W,
+                                                         float* __restrict__ dets, long long* __restrict__ inds) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= K) return;
+  const uint32_t r = ranks[i];
+  ranks[i] = 0;                                               // ready for the next decode
+  write_pick(keys[i], (int)r, heat, reg, (size_t)D * H * W, H * W, W, dets, inds);
 }
 
 // One CTA: bitonic sort (descending) of K composites, then the pick writer
@@ -691,33 +761,12 @@ __global__ void __launch_bounds__(1024) sort_write_kernel(
       __syncthreads();
     }
   }
-  const size_t n_vox = (size_t)D * H * W;
-  const int hw = H * W;
-  const float fhw = (float)hw, fw = (float)W;
-  for (int r = threadIdx.x; r < K; r += blockDim.x) {
-    const unsigned long long c = a[r];
-    const uint32_t key = (uint32_t)(c >> 32);
-    const uint32_t idx = ~(uint32_t)c;
-    float score;
-    if (key == KEY_ZERO) score = copysignf(0.0f, heat[idx]);   // heat*0 keeps the sign of heat
-    else score = key2f(key);
-    const float zf = floorf((float)idx / fhw);                  // decode.py:36 (fp32 division)
-    const int z = (int)zf;
-    const int t = (int)idx - z * hw;                            // decode.py:37 (int32)
-    const float yf = floorf((float)t / fw);                     // decode.py:38 (stays fp32)
-    int x = t % W;                                              // decode.py:39 (sign of divisor)
-    if (x < 0) x += W;
-    float xo, yo;
-    if (reg) { xo = (float)x + reg[idx]; yo = yf + reg[n_vox + idx]; }
-    else { xo = (float)x + 0.25f; yo = yf + 0.25f; }
-    float* d = dets + (size_t)r * 5;
-    d[0] = xo; d[1] = yo; d[2] = (float)z; d[3] = score; d[4] = score;
-    if (inds) inds[r] = (long long)idx;
-  }
+  for (int r = threadIdx.x; r < K; r += blockDim.x)
+    write_pick(a[r], r, heat, reg, (size_t)D * H * W, H * W, W, dets, inds);
 }
 
 __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqcnt, int D,
-                                  uint32_t t0key) {
+                                  uint32_t t0key, uint32_t* ranks, int n_ranks) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     DecodeState z = {};
@@ -727,6 +776,7 @@ __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqc
   }
   if (i < HIST_BINS) hist[i] = 0;
   for (int k = i; k < D; k += gridDim.x * blockDim.x) eqcnt[k] = 0;
+  for (int k = i; k < n_ranks; k += gridDim.x * blockDim.x) ranks[k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -771,7 +821,7 @@ __global__ void sigmoid_clamp_kernel(float* __restrict__ x, size_t n) {
 }
 
 struct WsLayout {
-  size_t off_state, off_hist, off_eq, off_cand, off_out, total;
+  size_t off_state, off_hist, off_eq, off_cand, off_out, off_rank, total;
   uint32_t cap_gt, cap_total;
   int npad;
 };
@@ -792,6 +842,7 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   L.off_eq = o;    o = align_up(o + (size_t)D * sizeof(uint32_t), 256);
   L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
   L.off_out = o;   o = align_up(o + (size_t)npad * 8, 256);
+  L.off_rank = o;  o = align_up(o + (size_t)std::min<int64_t>(K, RANK_MAX_K) * 4, 256);
   L.total = o;
   return L;
 }
@@ -868,7 +919,9 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   const int P = (nms_mode == CETPICK_NMS_NONE) ? 0 : (kernel_xy - 1) / 2;
   const bool collect_all = (n <= L.cap_gt);
 
-  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u);
+  uint32_t* ranks = reinterpret_cast<uint32_t*>(base + L.off_rank);
+  const int n_ranks = std::min(K, RANK_MAX_K);
+  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, ranks, n_ranks);
   CETPICK_LAUNCH_CHECK();
 
   ScanParams p = {};
@@ -887,11 +940,12 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   }
   const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
 
-  auto run_select = [&](int zlo, int zhi, int gate) -> int {
-    for (int pass = 0; pass < 3; ++pass) {
+  // npass = 2 stops after 22 key bits: t0 = lower edge of the K-th key's bin, still a valid lower bound
+  auto run_select = [&](int zlo, int zhi, int gate, int npass) -> int {
+    for (int pass = 0; pass < npass; ++pass) {
       ScanParams q = p;
       q.mode = MODE_HIST; q.zlo = zlo; q.zhi = zhi; q.gate = gate;
-      q.shift = shifts[pass]; q.bits = nbits[pass]; q.last_pass = (pass == 2);
+      q.shift = shifts[pass]; q.bits = nbits[pass]; q.last_pass = (pass == npass - 1);
       q.k_select = (uint32_t)K;
       const int grid = scan_grid(D, H, W, zlo, zhi, &q.ZC);
       int rc = launch_scan_p(P, q, grid, s);
@@ -916,10 +970,10 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     int sp = (int)std::min<uint64_t>((uint64_t)D, ceil_div<uint64_t>(want, hw));
     sp = std::max(sp, 1);
     const int zlo = (D - sp) / 2, zhi = zlo + sp;
-    if ((rc = run_select(zlo, zhi, 0))) return rc;
+    if ((rc = run_select(zlo, zhi, 0, 2))) return rc;
     if ((rc = run_collect(0, 0, 0))) return rc;
     // exact fallback (device-gated): full-volume select, then COLLECT again
-    if ((rc = run_select(0, D, 1))) return rc;
+    if ((rc = run_select(0, D, 1, 3))) return rc;
     if ((rc = run_collect(1, 1, 0))) return rc;
   }
   {  // EQ pass (device-gated on eq_need)
@@ -939,7 +993,12 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     cand_compact_kernel<<<grid, CAND_THREADS, 0, s>>>(cand, st, outb, L.cap_total, K);
     CETPICK_LAUNCH_CHECK();
   }
-  {
+  if (K <= RANK_MAX_K) {
+    rank_kernel<<<dim3(ceil_div(K, RANK_THREADS), RANK_PARTS), RANK_THREADS, 0, s>>>(outb, K, ranks);
+    CETPICK_LAUNCH_CHECK();
+    rank_write_kernel<<<ceil_div(K, 256), 256, 0, s>>>(outb, K, ranks, heat, reg, D, H, W, dets, inds);
+    CETPICK_LAUNCH_CHECK();
+  } else {
     const int use_smem = L.npad <= SORT_SMEM_MAX;
     const size_t smem = use_smem ? (size_t)L.npad * 8 : 0;
     static bool attr_done = false;
