@@ -52,7 +52,8 @@ struct DecodeState {
   unsigned long long kth_comp;     // exact K-th largest composite
   uint32_t n_final;        // number of candidates the final select saw
   uint32_t csel_done;     // candidate select resolved after the key digits (no ties at the K-th key)
-  uint32_t pad[2];
+  uint32_t n_real;        // COLLECT: voxels above the threshold (cand_count also counts chunk padding)
+  uint32_t pad[1];
 };
 
 struct alignas(64) ScanParams {
@@ -152,7 +153,6 @@ __device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* 
 template <int P>
 struct PlaneRegs {
   float a[4][4];  // in-plane (2P+1)^2 max (or, fiber, the xy-suppressed value)
-  float c[4][4];  // centre value compared in z
 };
 
 template <int P>
@@ -189,6 +189,8 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+// The centre values are not kept in registers: the caller re-reads them from shared memory when the
+// plane is emitted (fiber: the value compared in z IS `a`, the xy-suppressed value).
 template <int P>
 __device__ __forceinline__ void compute_plane(const float* buf, int fiber, PlaneRegs<P>& out) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -231,8 +233,10 @@ __device__ __forceinline__ void compute_plane(const float* buf, int fiber, Plane
       }
     }
     if (rr >= P && rr < P + 4) {
+      if (fiber) {                   // stash the centre in `a` until the xy maximum is known
 #pragma unroll
-      for (int i = 0; i < 4; ++i) out.c[rr - P][i] = w[P + i];
+        for (int i = 0; i < 4; ++i) out.a[rr - P][i] = w[P + i];
+      }
     }
   }
 #pragma unroll
@@ -248,10 +252,9 @@ __device__ __forceinline__ void compute_plane(const float* buf, int fiber, Plane
         for (int k = 1; k <= 2 * P; ++k) m = fmaxf(m, hm[j + k][i]);
       }
       if (fiber) {  // decode.py:11-17 on this plane: o1 = v * (m == v)
-        const float v = out.c[j][i];
+        const float v = out.a[j][i];
         const float o1 = (v == m) ? v : v * 0.0f;
         out.a[j][i] = o1;
-        out.c[j][i] = o1;
       } else {
         out.a[j][i] = m;
       }
@@ -262,21 +265,27 @@ __device__ __forceinline__ void compute_plane(const float* buf, int fiber, Plane
 // mbarrier per slot signals arrival), so several planes per CTA are in flight and no thread spends
 // issue slots on address arithmetic; needs 16-byte aligned rows.  TMA = false: cp.async double
 // buffer for unaligned maps.
-constexpr int NBUF = 4;
+constexpr int NBUF = 5;
+constexpr uint32_t CAND_CHUNK = 64;
 template <int P>
 constexpr int plane_buf_floats() { return ((TY + 2 * P) * PITCH * 4 + 127) / 128 * 32; }
 
 // MODE_T / FIBER_T >= 0 fix the pass and the fiber flag at compile time (the TMA instantiations, so
 // each carries only its own emit code); -1 = take them from the parameters.
+// TMA kernels have NO CTA-wide barrier in the plane loop: every warp counts its release of a ring slot
+// in shared memory and the LAST warp to release a slot re-arms it with the TMA load of the plane
+// NBUF positions further down the CTA's plane sequence, so the warps drift apart by up to NBUF planes.
 template <int P, bool TMA, int MODE_T, int FIBER_T>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_constant__ ScanParams p) {
   constexpr int ROWS = TY + 2 * P;
   constexpr int BUF = plane_buf_floats<P>();
-  constexpr int NB = TMA ? NBUF : 2;
+  constexpr int NB = TMA ? NBUF : 3;   // cp.async: plane i-1 must survive the load of plane i+1
   extern __shared__ __align__(128) float smem[];
   auto bufs = [&](int b) { return smem + b * BUF; };
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + NB * BUF);
   __shared__ __align__(8) uint64_t s_full[NBUF];
+  __shared__ uint32_t s_rel[NBUF];      // warps that have released the slot's current plane
+  const int NT = SCAN_THREADS;
   __shared__ uint32_t s_eq[MAX_ZC];
   __shared__ uint32_t s_sel[3];
   __shared__ uint32_t s_ticket;
@@ -299,14 +308,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
   const uint32_t dmask = (1u << p.bits) - 1u;
 
   if (mode == MODE_HIST) {
-    for (int i = threadIdx.x; i < HIST_BINS; i += SCAN_THREADS) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < HIST_BINS; i += NT) s_hist[i] = 0;
   }
   if (TMA && threadIdx.x == 0) {
     ptx::prefetch_tensormap(&p.tm);
-    for (int b = 0; b < NBUF; ++b) ptx::mbar_init(&s_full[b], 1);
+    for (int b = 0; b < NBUF; ++b) { ptx::mbar_init(&s_full[b], 1); s_rel[b] = 0; }
     ptx::fence_barrier_init();
   }
-  uint32_t n_iss = 0, n_cons = 0;   // TMA ring: planes issued / consumed so far (uniform across the CTA)
+  uint32_t n_cons = 0;              // TMA ring: planes this warp has consumed so far
   __syncthreads();
 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, lane = tx;
@@ -314,11 +323,47 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
   const int nzc = (zhi > zlo) ? ceil_div(zhi - zlo, p.ZC) : 0;
   const long long items = (long long)ntx * nty * nzc;
   const size_t plane_sz = (size_t)H * W;
+  // TMA: arm ring slot `slot` with the `ahead`-th fetched plane after position (item it, plane ii) of
+  // this CTA's sequence (items blockIdx.x, +gridDim.x, ...; planes 0..nplanes-1, fetched ones only)
+  auto issue_ahead = [&](long long it, int ii, int ahead, uint32_t slot) {
+    while (it < items) {
+      const int iz_ = (int)(it / ((long long)ntx * nty));
+      const int z0_ = zlo + iz_ * p.ZC, z1_ = min(z0_ + p.ZC, zhi);
+      const int np_ = z1_ - z0_ + 2;
+      for (++ii; ii < np_; ++ii) {
+        const int pz = z0_ - 1 + ii;
+        if (!((pz >= 0) && (pz < D) && (((ii >= 1) && (ii <= np_ - 2)) || znbr))) continue;
+        if (--ahead == 0) {
+          const int x0_ = (int)(it % ntx) * TX, y0_ = (int)((it / ntx) % nty) * TY;
+          ptx::mbar_arrive_expect_tx(&s_full[slot], (uint32_t)(ROWS * PITCH * 4));
+          ptx::tma_load_3d(bufs((int)slot), &p.tm, &s_full[slot], x0_ - XH, y0_ - P, pz);
+          return;
+        }
+      }
+      it += gridDim.x;
+      ii = -1;
+    }
+  };
+  // a warp is done with the plane at (it, ii) held in `slot`; the last of the 8 warps refills the slot
+  auto release_slot = [&](long long it, int ii, uint32_t slot) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&s_rel[slot], 1u) == SCAN_THREADS / 32 - 1) {
+        s_rel[slot] = 0;
+        __threadfence_block();
+        issue_ahead(it, ii, NBUF, slot);
+      }
+    }
+  };
+  if (TMA && threadIdx.x == 0)
+    for (int b = 0; b < NBUF; ++b) issue_ahead(blockIdx.x, -1, b + 1, (uint32_t)b);
   const float t0f = key2f(t0key);
   // non-survivors carry KEY_ZERO: do they matter to this pass? (collect-all, a threshold <= 0, ...)
   const bool zgen = (mode == MODE_COLLECT) ? (p.collect_all || KEY_ZERO >= t0key)
                                             : (mode == MODE_EQ) ? (t0key == KEY_ZERO) : false;
   uint32_t zero_cnt = 0;   // HIST: voxels with okey == KEY_ZERO seen by this thread
+  uint32_t w_base = 0, w_used = CAND_CHUNK;   // COLLECT: this warp's chunk of the candidate list (warp-uniform)
   bool saw_nan = false;
 
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -328,66 +373,46 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
     const int x0 = ix * TX, y0 = iy * TY;
     const int z0 = zlo + iz * p.ZC, z1 = min(z0 + p.ZC, zhi);
     const int nplanes = z1 - z0 + 2;
-    if (mode == MODE_COLLECT) {
+    if (!TMA && mode == MODE_COLLECT) {
       for (int i = threadIdx.x; i < MAX_ZC; i += SCAN_THREADS) s_eq[i] = 0;
     }
-    // Three register sets rotate through the roles (plane below, centre plane, incoming plane): the
-    // plane loop is unrolled by three, so nothing is copied per plane and max over z is one max3.
-    PlaneRegs<P> R0, R1, R2;
+    // Register sets: in-plane maxima of the plane below (pv), the centre plane (cu) and the incoming
+    // plane (nx).  The plane loop is a real loop (small code: the warps of a CTA run different planes,
+    // so the hot loop has to fit the instruction cache); the roles rotate by register moves.
+    PlaneRegs<P> pv, cu, nx;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        R0.a[j][i] = R1.a[j][i] = R2.a[j][i] = -INFINITY;
-        R0.c[j][i] = R1.c[j][i] = R2.c[j][i] = 0.f;
-      }
+      for (int i = 0; i < 4; ++i) pv.a[j][i] = cu.a[j][i] = nx.a[j][i] = -INFINITY;
     const bool tile_full = (x0 + TX <= W) && (y0 + TY <= H);
-
-    // plane i of the item is pz = z0-1+i; it is fetched when it exists and is either emitted or a z neighbour
-    auto fetched = [&](int i) {
-      const int pz = z0 - 1 + i;
-      return (pz >= 0) && (pz < D) && (((i >= 1) && (i <= nplanes - 2)) || znbr);
-    };
-    int iss = 0;                       // TMA: next plane of this item to issue
-    auto issue_more = [&]() {
-      while (iss < nplanes && n_iss - n_cons < (uint32_t)NBUF) {
-        if (fetched(iss)) {
-          if (threadIdx.x == 0) {
-            const uint32_t b = n_iss % NBUF;
-            ptx::mbar_arrive_expect_tx(&s_full[b], (uint32_t)(ROWS * PITCH * 4));
-            ptx::tma_load_3d(bufs(b), &p.tm, &s_full[b], x0 - XH, y0 - P, z0 - 1 + iss);
-          }
-          ++n_iss;
-        }
-        ++iss;
-      }
-    };
-    if (TMA) {
-      issue_more();
-    } else {
+    bool prev_valid = false;           // TMA: plane i-1 sits in ring slot prev_slot (not yet released)
+    uint32_t prev_slot = 0;
+    if (!TMA) {
       const int pz = z0 - 1;
       if (znbr && pz >= 0) load_plane<P>(bufs(0), p.heat + (size_t)pz * plane_sz, y0, x0, H, W, p.vec_ok);
       cp_async_commit();
     }
 
-    // one plane: bring plane i into `nx`, then emit plane i-1 (centre `cu`, plane below `pv`)
-    auto step = [&](int i, const PlaneRegs<P>& pv, const PlaneRegs<P>& cu, PlaneRegs<P>& nx) {
+    for (int i = 0; i < nplanes; ++i) {
+      // ---- bring plane i (pz) in: its in-plane maxima go to nx ----
       const int pz = z0 - 1 + i;
       const bool interior = (i >= 1) && (i <= nplanes - 2);   // an emitted plane
       const bool have = (pz >= 0) && (pz < D) && (interior || znbr);
-      const float* cbuf = bufs(i & 1);
+      const float* cbuf = bufs(i % 3);
+      uint32_t cur_slot = 0;
       if (TMA) {
         if (have) {
-          const uint32_t b = n_cons % NBUF;
-          ptx::mbar_wait(&s_full[b], (n_cons / NBUF) & 1u);
-          cbuf = bufs(b);
+          cur_slot = n_cons % NBUF;
+          ptx::mbar_wait(&s_full[cur_slot], (n_cons / NBUF) & 1u);
+          cbuf = bufs((int)cur_slot);
+          ++n_cons;
         }
       } else {
         if (i + 1 < nplanes) {
           const int qz = pz + 1;
           const bool qint = (i + 1 <= nplanes - 2);
           if (qz < D && (qint || znbr))
-            load_plane<P>(bufs((i + 1) & 1), p.heat + (size_t)qz * plane_sz, y0, x0, H, W, p.vec_ok);
+            load_plane<P>(bufs((i + 1) % 3), p.heat + (size_t)qz * plane_sz, y0, x0, H, W, p.vec_ok);
           cp_async_commit();
           cp_async_wait<1>();
         } else {
@@ -401,16 +426,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { nx.a[j][k] = -INFINITY; nx.c[j][k] = 0.f; }
-      }
-      if (TMA) {
-        if (have) ++n_cons;
-        __syncthreads();               // every thread has copied what it needs out of the slot
-        issue_more();                  // refill the ring while this plane is emitted
+          for (int k = 0; k < 4; ++k) nx.a[j][k] = -INFINITY;
       }
       if (i >= 2) {
-        // ---- emit plane ez = pz - 1: centre = cu, z neighbours = pm (two planes back, centre) and nx ----
+        // ---- emit plane ez = pz - 1 (centre cu, z neighbours pv and nx).  Its raw values are still in
+        // shared memory: ring slot prev_slot (TMA) / buffer (i-1) % 3 (cp.async).
         const int ez = pz - 1;
+        const float* pb = (TMA ? bufs((int)prev_slot) : bufs((i - 1) % 3)) + (ty * 4 + P) * PITCH + XH + 4 * tx;
+        // centre value of voxel b = j*4+k: fiber compares the xy-suppressed value (== cu.a), else the raw one
+        auto centre = [&](int b) -> float {
+          if (fiber) {
+            const int j = b >> 2, k = b & 3;
+            const float r0 = (k & 2) ? ((k & 1) ? cu.a[0][3] : cu.a[0][2]) : ((k & 1) ? cu.a[0][1] : cu.a[0][0]);
+            const float r1 = (k & 2) ? ((k & 1) ? cu.a[1][3] : cu.a[1][2]) : ((k & 1) ? cu.a[1][1] : cu.a[1][0]);
+            const float r2 = (k & 2) ? ((k & 1) ? cu.a[2][3] : cu.a[2][2]) : ((k & 1) ? cu.a[2][1] : cu.a[2][0]);
+            const float r3 = (k & 2) ? ((k & 1) ? cu.a[3][3] : cu.a[3][2]) : ((k & 1) ? cu.a[3][1] : cu.a[3][0]);
+            return (j & 2) ? ((j & 1) ? r3 : r2) : ((j & 1) ? r1 : r0);
+          }
+          return pb[(b >> 2) * PITCH + (b & 3)];
+        };
         // bit j*4+k.  HIST / generic: voxel is an NMS survivor (c == max of its window).  COLLECT / EQ
         // fast path: survivor AND c >= threshold -- the only voxels that can matter, and they are rare
         // whatever the map looks like (plateaus survive NMS everywhere but sit below the threshold).
@@ -418,16 +452,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         uint32_t mask = 0;
         float nansum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
+          float c4[4];
+          if (fiber) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c4[k] = cu.a[j][k];
+          } else {
+            const float4 q = *reinterpret_cast<const float4*>(pb + j * PITCH);
+            c4[0] = q.x; c4[1] = q.y; c4[2] = q.z; c4[3] = q.w;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float c = cu.c[j][k];
+            const float c = c4[k];
             // NMS_NONE (plain top-K) has no z neighbourhood at all
             const float m3 = znbr ? fmax3(pv.a[j][k], cu.a[j][k], nx.a[j][k]) : cu.a[j][k];
-            const bool s = need_all ? (c == m3) : ((c == m3) && (c >= t0f));
-            mask |= s ? (1u << (j * 4 + k)) : 0u;
+            const bool sv = need_all ? (c == m3) : ((c == m3) && (c >= t0f));
+            mask |= sv ? (1u << (j * 4 + k)) : 0u;
             nansum += c;
           }
+        }
         uint32_t vmask = 0xFFFFu;
         if (!tile_full) {
           vmask = 0;
@@ -439,10 +482,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
           mask &= vmask;
         }
         if (nansum != nansum) {        // a NaN (or +inf with -inf) among the 16 centres: look exactly
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) saw_nan |= ((vmask >> (j * 4 + k)) & 1u) && (cu.c[j][k] != cu.c[j][k]);
+          for (uint32_t m = vmask; m; m &= m - 1) {
+            const float c = centre(__ffs(m) - 1);
+            saw_nan |= (c != c);
+          }
         }
         // every voxel that is not a survivor has key KEY_ZERO; zgen = those zeros matter to this pass
         uint32_t take = 0;             // COLLECT / EQ: voxels to append
@@ -450,51 +493,44 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         if (!zgen) {
           if (mode == MODE_HIST) {
             zero_cnt += __popc(vmask) - __popc(mask);
-            if (mask) {
-#pragma unroll
-              for (int b = 0; b < 16; ++b)
-                if ((mask >> b) & 1u) {
-                  const uint32_t ok = f2key(cu.c[b >> 2][b & 3]);
-                  if (hs < 32 && (ok >> hs) != prefix) continue;
-                  if (ok == KEY_ZERO) ++zero_cnt;
-                  else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
-                }
+            for (uint32_t m = mask; m; m &= m - 1) {
+              const uint32_t ok = f2key(centre(__ffs(m) - 1));
+              if (hs < 32 && (ok >> hs) != prefix) continue;
+              if (ok == KEY_ZERO) ++zero_cnt;
+              else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
             }
-          } else if (mask) {
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-              const float c = cu.c[b >> 2][b & 3];
-              const bool on = (mask >> b) & 1u;
-              if (mode == MODE_COLLECT) {
-                take |= (on && c > t0f) ? (1u << b) : 0u;       // key order == float order (c is not NaN)
-                n_eq += (on && !(c > t0f)) ? 1u : 0u;
-              } else {
-                take |= (on && !(c > t0f)) ? (1u << b) : 0u;
-              }
+          } else {
+            for (uint32_t m = mask; m; m &= m - 1) {
+              const int b = __ffs(m) - 1;
+              const bool gt = centre(b) > t0f;                    // key order == float order (c is not NaN)
+              if (mode == MODE_COLLECT) { if (gt) take |= 1u << b; else ++n_eq; }
+              else if (!gt) take |= 1u << b;
             }
           }
         } else {
           // generic path: zeros are candidates / equal to the threshold (tiny or degenerate maps)
-#pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            if (!((vmask >> b) & 1u)) continue;
-            const uint32_t ok = ((mask >> b) & 1u) ? f2key(cu.c[b >> 2][b & 3]) : KEY_ZERO;
+          for (uint32_t m = vmask; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const uint32_t ok = ((mask >> b) & 1u) ? f2key(centre(b)) : KEY_ZERO;
             if (mode == MODE_HIST) {
               if (hs < 32 && (ok >> hs) != prefix) continue;
               if (ok == KEY_ZERO) ++zero_cnt;
               else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
             } else if (mode == MODE_COLLECT) {
-              take |= (p.collect_all || ok > t0key) ? (1u << b) : 0u;
+              if (p.collect_all || ok > t0key) take |= 1u << b;
               n_eq += (ok == t0key) ? 1u : 0u;
             } else {
-              take |= (ok == t0key) ? (1u << b) : 0u;
+              if (ok == t0key) take |= 1u << b;
             }
           }
         }
         if (mode != MODE_HIST) {
           if (mode == MODE_COLLECT) {
             const uint32_t weq = __reduce_add_sync(0xffffffffu, n_eq);
-            if (lane == 0 && weq) atomicAdd(&s_eq[ez - z0], weq);
+            if (lane == 0 && weq) {
+              if (TMA) atomicAdd(&p.eqcnt[ez], weq);
+              else atomicAdd(&s_eq[ez - z0], weq);
+            }
           }
           const uint32_t n_gt = __popc(take);
           if (__any_sync(0xffffffffu, n_gt != 0)) {
@@ -504,42 +540,64 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
               uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
               if (lane >= o) incl += t;
             }
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(&st->cand_count, incl);
-            base = __shfl_sync(0xffffffffu, base, 31);
-            uint32_t off = base + incl - n_gt;
             const uint32_t lim = (mode == MODE_COLLECT) ? p.cap_gt : p.cap_total;
-            if (take) {
-#pragma unroll
-              for (int b = 0; b < 16; ++b)
-                if ((take >> b) & 1u) {
-                  if (off < lim) {
-                    const uint32_t ok = ((mask >> b) & 1u) ? f2key(cu.c[b >> 2][b & 3]) : KEY_ZERO;
-                    const uint32_t idx = (uint32_t)((size_t)ez * plane_sz +
-                                                    (size_t)(y0 + ty * 4 + (b >> 2)) * W + (x0 + tx * 4 + (b & 3)));
-                    p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
-                  }
-                  ++off;
-                }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t off;
+            if (mode == MODE_COLLECT && !zgen && tot <= CAND_CHUNK) {
+              // space comes from a per-warp chunk: one returning atomic per CAND_CHUNK candidates instead
+              // of one global round trip per plane; the unused tail of a chunk is padded with composite 0
+              if (w_used + tot > CAND_CHUNK) {
+                for (uint32_t q = w_used + lane; q < CAND_CHUNK; q += 32)
+                  if (w_base + q < lim) p.cand[w_base + q] = 0ull;
+                uint32_t nb = 0;
+                if (lane == 0) nb = atomicAdd(&st->cand_count, (uint32_t)CAND_CHUNK);
+                w_base = __shfl_sync(0xffffffffu, nb, 0);
+                w_used = 0;
+              }
+              off = w_base + w_used + incl - n_gt;
+              w_used += tot;
+            } else {
+              uint32_t base = 0;
+              if (lane == 31) base = atomicAdd(&st->cand_count, incl);
+              base = __shfl_sync(0xffffffffu, base, 31);
+              off = base + incl - n_gt;
+            }
+            if (mode == MODE_COLLECT && lane == 0) atomicAdd(&st->n_real, tot);   // no return value: fire and forget
+            for (uint32_t m = take; m; m &= m - 1, ++off) {
+              if (off >= lim) continue;
+              const int b = __ffs(m) - 1;
+              const uint32_t ok = ((mask >> b) & 1u) ? f2key(centre(b)) : KEY_ZERO;
+              const uint32_t idx = (uint32_t)((size_t)ez * plane_sz + (size_t)(y0 + ty * 4 + (b >> 2)) * W +
+                                              (x0 + tx * 4 + (b & 3)));
+              p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
             }
           }
         }
       }
-      if (!TMA) __syncthreads();
-    };
-    for (int i = 0; i < nplanes; i += 3) {
-      step(i, R1, R2, R0);
-      if (i + 1 < nplanes) step(i + 1, R2, R0, R1);
-      if (i + 2 < nplanes) step(i + 2, R0, R1, R2);
+      if (TMA) {                       // plane i-1 is no longer needed in shared memory; plane i stays one step
+        if (prev_valid) release_slot(item, i - 1, prev_slot);
+        prev_valid = have;
+        prev_slot = cur_slot;
+      } else {
+        __syncthreads();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { pv.a[j][k] = cu.a[j][k]; cu.a[j][k] = nx.a[j][k]; }
     }
-    if (mode == MODE_COLLECT) {
-      if (TMA) __syncthreads();
+    if (TMA && prev_valid) release_slot(item, nplanes - 1, prev_slot);
+    if (!TMA && mode == MODE_COLLECT) {
       for (int i = threadIdx.x; i < z1 - z0; i += SCAN_THREADS)
         if (s_eq[i]) atomicAdd(&p.eqcnt[z0 + i], s_eq[i]);
       __syncthreads();
     }
   }
 
+  if (mode == MODE_COLLECT) {   // pad the unused tail of the warp's last chunk
+    for (uint32_t q = w_used + (threadIdx.x & 31); q < CAND_CHUNK; q += 32)
+      if (w_base + q < p.cap_gt) p.cand[w_base + q] = 0ull;
+  }
   if (saw_nan) atomicOr(&st->flags, (uint32_t)FLAG_NAN);
 
   if (mode == MODE_EQ) return;
@@ -549,7 +607,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
     if (zero_cnt && (hs >= 32 || (KEY_ZERO >> hs) == prefix))
       atomicAdd(&s_hist[(KEY_ZERO >> p.shift) & dmask], zero_cnt);
     __syncthreads();
-    for (int i = threadIdx.x; i < HIST_BINS; i += SCAN_THREADS)
+    for (int i = threadIdx.x; i < HIST_BINS; i += NT)
       if (s_hist[i]) atomicAdd(&p.hist[i], s_hist[i]);
   }
   __threadfence();
@@ -576,12 +634,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       st->done_ctr = 0;
     }
     if (p.last_pass && p.gate) {
-      for (int i = threadIdx.x; i < D; i += SCAN_THREADS) p.eqcnt[i] = 0;
+      for (int i = threadIdx.x; i < D; i += NT) p.eqcnt[i] = 0;
     }
   } else {  // MODE_COLLECT: plan the EQ pass
     if (threadIdx.x == 0) {
-      const uint32_t n = st->cand_count;
-      st->n_gt = n;
+      const uint32_t n = st->cand_count;      // list entries incl. chunk padding (space check)
+      const uint32_t nr = st->n_real;         // voxels above the threshold
+      st->n_gt = nr;
+      st->n_real = 0;
       st->eq_need = 0;
       st->eq_zc = -1;
       st->done_ctr = 0;
@@ -589,8 +649,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; }
         else st->flags |= FLAG_INTERNAL;
         st->cand_count = 0;
-      } else if (n < (uint32_t)p.K) {
-        const uint32_t need = (uint32_t)p.K - n;
+      } else if (nr < (uint32_t)p.K) {
+        const uint32_t need = (uint32_t)p.K - nr;
         uint32_t cum = 0;
         int zc = -1;
         for (int z = p.zlo; z < p.zhi; ++z) {
@@ -849,7 +909,7 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
 
 template <int P, bool TMA, int MODE_T, int FIBER_T>
 int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
-  const size_t smem = (size_t)(TMA ? NBUF : 2) * plane_buf_floats<P>() * sizeof(float) + HIST_BINS * sizeof(uint32_t);
+  const size_t smem = (size_t)(TMA ? NBUF : 3) * plane_buf_floats<P>() * sizeof(float) + HIST_BINS * sizeof(uint32_t);
   auto kern = scan_kernel<P, TMA, MODE_T, FIBER_T>;
   static bool attr_done = false;
   if (!attr_done) {
