@@ -348,10 +348,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
   auto release_slot = [&](long long it, int ii, uint32_t slot) {
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();
-      if (atomicAdd(&s_rel[slot], 1u) == SCAN_THREADS / 32 - 1) {
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;"
+                   : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(&s_rel[slot])) : "memory");
+      if (old == SCAN_THREADS / 32 - 1) {
         s_rel[slot] = 0;
-        __threadfence_block();
         issue_ahead(it, ii, NBUF, slot);
       }
     }
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       if (TMA) {
         if (have) {
           cur_slot = n_cons % NBUF;
-          ptx::mbar_wait(&s_full[cur_slot], (n_cons / NBUF) & 1u);
+          ptx::mbar_wait_parked(&s_full[cur_slot], (n_cons / NBUF) & 1u, 4000u);
           cbuf = bufs((int)cur_slot);
           ++n_cons;
         }
@@ -450,26 +451,47 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         // whatever the map looks like (plateaus survive NMS everywhere but sit below the threshold).
         const bool need_all = zgen || (mode == MODE_HIST);
         uint32_t mask = 0;
-        float nansum = 0.f;
+        float c16[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float c4[4];
           if (fiber) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) c4[k] = cu.a[j][k];
+            for (int k = 0; k < 4; ++k) c16[j][k] = cu.a[j][k];
           } else {
             const float4 q = *reinterpret_cast<const float4*>(pb + j * PITCH);
-            c4[0] = q.x; c4[1] = q.y; c4[2] = q.z; c4[3] = q.w;
+            c16[j][0] = q.x; c16[j][1] = q.y; c16[j][2] = q.z; c16[j][3] = q.w;
           }
+        }
+        // sum: NaN detector (exact check below when it trips); max: can ANY of the 16 reach the threshold?
+        float nansum = 0.f;
+        float r4[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float c = c4[k];
-            // NMS_NONE (plain top-K) has no z neighbourhood at all
-            const float m3 = znbr ? fmax3(pv.a[j][k], cu.a[j][k], nx.a[j][k]) : cu.a[j][k];
-            const bool sv = need_all ? (c == m3) : ((c == m3) && (c >= t0f));
-            mask |= sv ? (1u << (j * 4 + k)) : 0u;
-            nansum += c;
-          }
+        for (int j = 0; j < 4; ++j) {
+          nansum += (c16[j][0] + c16[j][1]) + (c16[j][2] + c16[j][3]);
+          r4[j] = fmax3(fmaxf(c16[j][0], c16[j][1]), c16[j][2], c16[j][3]);
+        }
+        const float cmax = fmax3(fmaxf(r4[0], r4[1]), r4[2], r4[3]);
+        // fast path skip (warp-uniform): no voxel of the warp's 512 reaches the threshold
+        if (need_all || __any_sync(0xffffffffu, cmax >= t0f)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float c = c16[j][k];
+              // NMS_NONE (plain top-K) has no z neighbourhood at all
+              const float m3 = znbr ? fmax3(pv.a[j][k], cu.a[j][k], nx.a[j][k]) : cu.a[j][k];
+              if (need_all) {
+                mask |= (c == m3) ? (1u << (j * 4 + k)) : 0u;
+              } else {   // (c >= t0f) && (c == m3): two compares and one predicated OR
+                asm("{\n\t"
+                    ".reg .pred q;\n\t"
+                    "setp.ge.f32 q, %1, %3;\n\t"
+                    "setp.eq.and.f32 q, %1, %2, q;\n\t"
+                    "@q or.b32 %0, %0, %4;\n\t"
+                    "}\n"
+                    : "+r"(mask) : "f"(c), "f"(m3), "f"(t0f), "r"(1u << (j * 4 + k)));
+              }
+            }
         }
         uint32_t vmask = 0xFFFFu;
         if (!tile_full) {
