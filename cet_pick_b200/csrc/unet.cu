@@ -11,6 +11,7 @@
 #include "conv_tc.cuh"
 #include "conv_march.cuh"
 #include "conv_up.cuh"
+#include "conv_halo.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -191,6 +192,7 @@ struct PackedConv {
   bool has_bias = false;
   double flops_per_pixel = 0;    // 2 * K * N
   bool upk = false;              // ConvTranspose weights packed for conv_up.cu
+  bool halo = false;             // 3x3 weights packed for conv_halo.cu
   int march = -1;                // >= 0: MarchMode of conv_march.cu (w_off then holds ITS weight image)
 };
 
@@ -282,6 +284,12 @@ bool pack_conv(cetpick_unet* m, const std::string& wkey, int Cout, int nsrc, int
     pc.march = mmode;
     pc.w_off = blob_alloc(m, pk.size() * 2);
     memcpy(m->blob.data() + pc.w_off, pk.data(), pk.size() * 2);
+  } else if (ntaps == 9 && halo_supported(Csrc, nsrc, Cout) && (fold || conv_bias)) {
+    // wide level: weight image of the halo-tile kernel (conv_halo.cu)
+    const std::vector<uint16_t> pk = halo_pack_weights(w->data(), Cout, nsrc, Csrc, fold ? fold->scale.data() : nullptr);
+    pc.halo = true;
+    pc.w_off = blob_alloc(m, pk.size() * 2);
+    memcpy(m->blob.data() + pc.w_off, pk.data(), pk.size() * 2);
   } else {
   pc.w_off = blob_alloc(m, nkb * Cout * pc.KC * 2);
   uint16_t* dst = reinterpret_cast<uint16_t*>(m->blob.data() + pc.w_off);
@@ -367,7 +375,7 @@ struct HeadExtras {
 int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
              int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st,
              const HeadExtras* ex = nullptr) {
-  g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : ":tc")).c_str(),
+  g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : pc.halo ? ":halo" : ":tc")).c_str(),
               pc.flops_per_pixel * (double)NIMG * H * W, st);
   const float* bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
   if (pc.march >= 0) {
@@ -379,6 +387,14 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
     M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out;
     if (ex) { M.bias_tab = ex->bias_tab; M.hm_w = ex->hm_w; M.hm_out = ex->hm_out; M.hm_sigmoid = ex->hm_sigmoid; }
     return conv_march_launch(M, st);
+  }
+  if (pc.halo) {
+    if (epi != EPI_BF16_NHWC || !bias) return CETPICK_ERR_STATE;
+    HaloLaunch Hh;
+    Hh.nsrc = pc.nsrc; Hh.src[0] = s0; Hh.src[1] = s1; Hh.C = pc.C[0]; Hh.NIMG = NIMG; Hh.H = H; Hh.W = W;
+    Hh.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off; Hh.bias = bias; Hh.Cout = pc.Ntot;
+    Hh.relu = pc.relu; Hh.out = out;
+    return conv_halo_launch(Hh, st);
   }
   ConvLaunch L;
   L.nsrc = pc.nsrc; L.src[0] = s0; L.src[1] = s1; L.C[0] = pc.C[0]; L.C[1] = pc.C[1];

@@ -164,6 +164,14 @@ int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const
 int cetpick_upconv_bf16(const void* src, int Cin, int NIMG, int h, int w, const float* w_host,
                         const float* bias_host, int Cout, void* out, int Ho, int Wo, void* stream);
 
+/* Test hook: ONE 3x3 Conv2d (pad 1) + bias (+ReLU) through the halo-tile tcgen05 kernel (csrc/conv_halo.cu)
+ * used for the wide trunk levels (C per source a multiple of 64, Cout a multiple of 128).  src*: bf16 device
+ * [NIMG][H][W][C]; w_host: fp32 HOST weight (Cout, nsrc*C, 3, 3); bias_host: fp32 HOST [Cout];
+ * out: bf16 device [NIMG][H][W][Cout].  Packs, uploads, launches and synchronises. */
+int cetpick_conv_halo_bf16(int nsrc, const void* src0, const void* src1, int C, int NIMG, int H, int W,
+                           const float* w_host, const float* bias_host, int Cout, int relu, void* out,
+                           void* stream);
+
 /* Hardware probe (test hook): D[128][32] = A_big[rows] * B^T where the A descriptor starts r0 rows
  * into a TMA-written swizzled tile, with 8-row groups sbo_bytes apart and the given base_offset. */
 int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,

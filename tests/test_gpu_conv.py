@@ -225,3 +225,23 @@ def test_conv_up_kernel(L, cin, cout, n, h, w, Ho, Wo):
     torch.cuda.synchronize()
     ref = F.relu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2))[:, :, :Ho, :Wo]
     assert (out.float() - ref.permute(0, 2, 3, 1)).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("nsrc,c,cout,n,h,w", [(1, 64, 128, 2, 16, 16), (1, 128, 128, 2, 19, 35), (1, 128, 256, 1, 9, 40),
+                                               (1, 256, 256, 3, 33, 17), (2, 128, 128, 2, 27, 30), (1, 64, 128, 40, 64, 64)])
+def test_conv_halo_kernel(L, nsrc, c, cout, n, h, w):
+    """csrc/conv_halo.cu: one halo tile per channel chunk, nine shifted descriptors, streamed weights"""
+    g = torch.Generator(device="cuda").manual_seed(c + cout + h)
+    srcs = [torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16() for _ in range(nsrc)]
+    cin = nsrc * c
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g)
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wh, bh = wt.float().cpu().contiguous(), b.cpu().contiguous()
+    L.check(L.lib().cetpick_conv_halo_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c,
+                                           n, h, w, wh.data_ptr(), bh.data_ptr(), cout, 1, out.data_ptr(),
+                                           L.stream_ptr()), "cetpick_conv_halo_bf16")
+    torch.cuda.synchronize()
+    xin = torch.cat(srcs, 3).float().permute(0, 3, 1, 2)
+    ref = F.relu(F.conv2d(xin, wt.float(), b, padding=1)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
