@@ -157,6 +157,7 @@ def run_b200(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from cet_pick_b200 import _lib, synth
+    from cet_pick_b200.shard import gather_picks, shard_range
     from cet_pick_b200.models.decode import tomo_decode
     from cet_pick_b200.models.model import create_model
 
@@ -167,8 +168,7 @@ def run_b200(a, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     D, H, W = (int(v) for v in a.shape.split(","))
-    n_local = a.batch // world + (1 if rank < a.batch % world else 0)
-    first = sum(a.batch // world + (1 if r < a.batch % world else 0) for r in range(rank))
+    first, n_local = shard_range(a.batch, rank, world)
 
     torch.manual_seed(317)                                    # opts.py:47 default seed
     model = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)   # random init (W0)
@@ -195,11 +195,9 @@ def run_b200(a, rank, world, local_rank):
 
     def step_resident():
         outs = [one(x) for x in pool]
-        if world > 1 and outs:                     # the only collective: gather the pick lists
-            mine = torch.cat(outs, 0)
-            if a.batch % world == 0:
-                allp = torch.empty((world * mine.shape[0],) + mine.shape[1:], device=dev)
-                dist.all_gather_into_tensor(allp, mine)
+        if world > 1:                              # the only collective: gather the pick lists
+            mine = torch.cat(outs, 0) if outs else torch.empty((0, a.K, 5), device=dev)
+            gather_picks(mine, a.batch)
         return outs
 
     copy_stream = torch.cuda.Stream(dev)
@@ -282,7 +280,7 @@ def run_b200(a, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
-                         "kernel": "conv_march_kernel + conv_tc_kernel (all tcgen05 conv layers of one forward)",
+                         "kernel": "conv_march_kernel + conv_halo_kernel + conv_up_kernel (all tcgen05 conv layers of one forward)",
                          "peak_source": pk["src"] + " sustained cuBLAS bf16", "share_of_forward": conv_ms / tot_ms if tot_ms else None,
                          "layers_ms": {k: round(v[0], 3) for k, v in layers.items()},
                          "layers_tflops": {k: round(v[1] / v[0] / 1e9, 1) for k, v in layers.items() if v[0] > 0 and v[1] > 0}},

@@ -1,0 +1,80 @@
+"""End-to-end detector mirror (detectors/tomo_det.py) on the GPU: pick files against the reference's
+golden text, and run() through opts + checkpoint loading against the oracle pipeline."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _detector(opt_kw):
+    import types
+    from cet_pick_b200.detectors.tomo_det import TomodetDetector
+    det = TomodetDetector.__new__(TomodetDetector)
+    det.opt = types.SimpleNamespace(down_ratio=2, out_thresh=0.25, cutoff_z=3, compress=False, fiber=False,
+                                    spike=False, with_score=False, nms=3, K=120)
+    for k, v in opt_kw.items():
+        setattr(det.opt, k, v)
+    return det
+
+
+@pytest.mark.parametrize("tag,kw", [("plain", {}), ("score", dict(with_score=True)), ("compress", dict(compress=True))])
+def test_pick_files_match_reference_golden(golden, tmp_path, tag, kw):
+    """decode on the GPU + post_process + save_detection reproduce the reference's `<name>.txt` byte for byte
+    (fixture written by the unmodified reference, tests/golden/make_golden.py)."""
+    from cet_pick_b200 import synth
+    from cet_pick_b200.models.decode import tomo_decode
+    g = golden("pickfile")
+    D, H, W = (int(v) for v in g["shape"])
+    hm = synth.heatmap_tiefree_np(D, H, W, int(g["seed"]))[None, None]
+    hm = ((hm - hm.min()) / (hm.max() - hm.min())).astype(np.float32)
+    hm_t = torch.from_numpy(hm).cuda()
+    dets = tomo_decode(hm_t, kernel=3, K=120)
+    assert np.array_equal(dets.cpu().numpy().view(np.uint32), g["dets"].view(np.uint32))
+    det = _detector(kw)
+    preds, name = det.post_process(dets.clone(), {"name": ["tomoA"]}, z_dim_tot=D)
+    det.save_detection(hm_t, preds, str(tmp_path), None, name=name)
+    assert open(os.path.join(tmp_path, "tomoA.txt")).read() == str(g["txt_" + tag])
+    assert os.path.exists(os.path.join(tmp_path, "tomoA_hm.mrc"))
+
+
+def test_run_end_to_end_from_checkpoint(tmp_path, monkeypatch):
+    """opts -> detector_factory -> load_model(checkpoint) -> run(): picks agree with the oracle pipeline
+    (fp32 forward + decode) within one voxel for every pick whose score clears the K-th by the BF16 tolerance."""
+    from cet_pick_b200 import synth
+    from cet_pick_b200.detectors.detector_factory import detector_factory
+    from cet_pick_b200.opts import opts
+    from oracle import decode_oracle as do
+    from oracle import unet_oracle as uo
+    sd = synth.unet_state_dict_torch(317, 4)
+    ckpt = os.path.join(tmp_path, "model.pth")
+    torch.save({"epoch": 3, "state_dict": {"module." + k: v for k, v in sd.items()}}, ckpt)
+    monkeypatch.chdir(tmp_path)
+    K = 60
+    opt = opts().init(["semi", "--arch", "unet_4", "--load_model", ckpt, "--K", str(K), "--out_thresh", "0.0",
+                       "--cutoff_z", "0", "--with_score", "--out_id", "out", "--exp_id", "e2e", "--gpus", "0"])
+    os.makedirs(opt.save_dir, exist_ok=True)
+    det = detector_factory[opt.task](opt)
+    D, H, W = 12, 96, 128
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, 5))[None]
+    ret = det.run(x, {"name": ["tomoB"]})
+    assert set(ret) == {"tot_time", "load", "pre", "net", "dec"}
+    lines = [ln.split("\t") for ln in open(os.path.join(opt.out_path, "tomoB.txt")).read().splitlines()]
+    got = np.array([[float(v) for v in ln] for ln in lines])          # x, z, y, score
+    with torch.no_grad():
+        hm = uo.sigmoid_clamp(uo.forward(x, sd, want_proj=False)["hm"]).numpy()
+    ref = do.tomo_decode(hm, 3, None, K)[0]                             # x+.25, y+.25, z, s, s (half-res)
+    tol = 1e-2
+    kth = ref[-1, 3]
+    strong = ref[ref[:, 3] > kth + 2 * tol]
+    assert len(strong) > 0
+    for r in strong:
+        x2, y2, z = 2 * int(np.floor(r[0])), 2 * int(np.floor(r[1])), int(r[2])
+        if not (20 < x2 < 2 * hm.shape[-1] - 20 and 20 < y2 < 2 * hm.shape[-2] - 20):
+            continue                                                  # the writer drops the 20-pixel border
+        d = np.abs(got[:, :3] - np.array([x2, z, y2])).max(axis=1)
+        j = int(np.argmin(d))
+        assert d[j] <= 2, (r, got[j])                                  # 1 voxel at half resolution = 2 input pixels
+        assert abs(got[j, 3] - r[3]) <= tol

@@ -1,0 +1,58 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: tomogram sharding + the pick-list gather."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cet_pick_b200.shard import gather_picks, shard_range
+
+
+def test_shard_range_partitions_everything():
+    for n in (0, 1, 5, 64, 65):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                first, cnt = shard_range(n, r, world)
+                seen += list(range(first, first + cnt))
+            assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _picks(i, K):
+    g = torch.Generator().manual_seed(1000 + i)
+    return torch.rand((K, 5), generator=g)
+
+
+def _worker(rank, world, port, n_items, K, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        first, cnt = shard_range(n_items, rank, world)
+        local = torch.stack([_picks(first + i, K) for i in range(cnt)]) if cnt else torch.empty((0, K, 5))
+        allp = gather_picks(local, n_items)
+        ref = torch.stack([_picks(i, K) for i in range(n_items)])
+        q.put((rank, bool(torch.equal(allp, ref))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [4, 5])
+def test_gather_picks_world2_gloo(n_items):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, 7, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
