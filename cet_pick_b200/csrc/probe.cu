@@ -63,6 +63,61 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ P
   if (warp == 1) ptx::tmem_dealloc(tmem, 32);
 }
 
+// MMA issue-rate probe: one thread issues `iters` tcgen05.mma (M = 128, N, K = 16) back to back on
+// operands that stay in shared memory (contents irrelevant), cycling through `ntap` A start offsets
+// (a_step bytes apart) and `ndst` accumulators, then commits and waits.  out[cta] = cycles per MMA.
+struct RateParams {
+  int N, KC, sbo_a, a_step, ntap, ndst, iters, layout_type;
+  float* out;
+};
+
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(const RateParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  // finite operand bytes (0x3c3c.. = small positive bf16)
+  for (int i = threadIdx.x; i < (96 * 1024) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar_done, 1); ptx::fence_barrier_init(); }
+  if (warp == 1) { ptx::tmem_alloc(&s_tmem, 512); ptx::tmem_relinquish(); }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp == 0) {
+    const uint32_t a_hi = ptx::smem_desc_hi((uint32_t)p.sbo_a, (uint32_t)p.layout_type);
+    const uint32_t b_hi = ptx::smem_desc_hi((uint32_t)(16 * p.KC), (uint32_t)p.layout_type);
+    const uint32_t a_lo = ptx::smem_desc_lo(ptx::smem_u32(smem));
+    const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(smem + 64 * 1024));
+    const uint32_t idesc = ptx::make_idesc_bf16(128, p.N);
+    const int k16 = p.KC / 16;
+    long long t0 = 0, t1 = 0;
+    if (ptx::elect_one()) {
+      t0 = clock64();
+      int tap = 0, dst = 0, kk = 0;
+      for (int i = 0; i < p.iters; ++i) {
+        ptx::umma_bf16_lohi(tmem + (uint32_t)(dst * p.N), a_lo + (uint32_t)((tap * p.a_step + kk * 32) >> 4), a_hi,
+                            b_lo + (uint32_t)((tap * p.N * p.KC * 2 / 1 % (24 * 1024) + kk * 32) >> 4), b_hi, idesc);
+        if (++kk == k16) { kk = 0; if (++tap == p.ntap) { tap = 0; if (++dst == p.ndst) dst = 0; } }
+      }
+      ptx::umma_commit(&bar_done);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&bar_done, 0);
+    t1 = clock64();
+    const long long dt = __shfl_sync(0xffffffffu, t1, 0) - __shfl_sync(0xffffffffu, t0, 0);
+    long long mx = t0;
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) p.out[blockIdx.x] = (float)((double)(t1 - mx) / p.iters);
+    (void)dt;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -107,6 +162,23 @@ extern "C" int cetpick_probe_umma(const void* A_big, int R, const void* B, int K
   const size_t smem = (size_t)(R + 32) * KC * 2 + 2048;
   CETPICK_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+// Test / tuning hook: tcgen05.mma issue rate for (N, swizzle width KC, A group stride, tap pattern).
+extern "C" int cetpick_probe_mma_rate(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
+                                      float* out_cycles, int grid, void* stream) {
+  if (!out_cycles || N < 16 || N > 256 || (N % 16) || (KC != 16 && KC != 32 && KC != 64) || ntap < 1 || ndst < 1 ||
+      ndst * N > 512 || iters < 1 || grid < 1)
+    return CETPICK_ERR_BAD_ARG;
+  RateParams p;
+  p.N = N; p.KC = KC; p.sbo_a = sbo_a; p.a_step = a_step; p.ntap = ntap; p.ndst = ndst; p.iters = iters;
+  p.layout_type = KC == 64 ? 2 : KC == 32 ? 4 : 6;
+  p.out = out_cycles;
+  const size_t smem = 97 * 1024 + 1024;
+  CETPICK_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }

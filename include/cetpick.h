@@ -177,6 +177,13 @@ int cetpick_conv_halo_bf16(int nsrc, const void* src0, const void* src1, int C, 
 int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,
                        int base_offset, float* out, void* stream);
 
+/* Hardware probe (tuning hook): cycles per tcgen05.mma (M=128, N, K=16, bf16) issued back to back from
+ * shared-memory operands; KC selects the swizzle width, sbo_a the A 8-row group stride, the A start
+ * address cycles through ntap offsets a_step bytes apart and the accumulator through ndst TMEM
+ * regions.  out_cycles: `grid` floats (device). */
+int cetpick_probe_mma_rate(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
+                           float* out_cycles, int grid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
