@@ -50,6 +50,10 @@ struct alignas(64) MarchParams {
   int relu;
   const float* bias;
   __nv_bfloat16* out;
+  // epilogue constants live in the kernel-parameter constant bank: FADD/FFMA read them as c[0][imm]
+  // operands, so the epilogue puts no load on the shared-memory pipe the UMMA operands stream through
+  float bias_c[64];        // 2-D bias / 3-D bias of the interior tap-validity class (row 63 of bias_tab)
+  float hmw_c[96];         // fused hm head weights [3][32]
   const float* bias_tab;   // 3-D: [64][COUT] tap-validity dependent bias (or null)
   const float* hm_w;       // 3-D: fused hm head weights [3][COUT] (or null)
   float* hm_out;
@@ -113,9 +117,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
   __shared__ uint32_t s_tmem_base;
-  __shared__ float s_bias[COUT];
-  __shared__ __align__(16) float s_btab[MODE == MARCH_3D_PLANES ? 64 * COUT : 4];
-  __shared__ float s_hmw[MODE == MARCH_3D_PLANES ? 3 * COUT : 4];
+  __shared__ __align__(16) float s_btab[MODE == MARCH_3D_PLANES ? 64 * COUT : 4];   // border classes only
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
@@ -138,13 +140,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     ptx::tmem_alloc(&s_tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (warp == 3) {
-    for (int c = lane; c < COUT; c += 32) s_bias[c] = p.bias ? p.bias[c] : 0.f;
-    if (MODE == MARCH_3D_PLANES) {
-      for (int c = lane; c < 64 * COUT; c += 32) s_btab[c] = p.bias_tab ? p.bias_tab[c] : 0.f;
-      for (int c = lane; c < 3 * COUT; c += 32) s_hmw[c] = p.hm_w ? p.hm_w[c] : 0.f;
-    }
-  }
+  if (warp == 3 && MODE == MARCH_3D_PLANES)
+    for (int c = lane; c < 64 * COUT; c += 32) s_btab[c] = p.bias_tab ? p.bias_tab[c] : p.bias_c[c % COUT];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -297,13 +294,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           if (MODE == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
           else { x = s.x0 + t * 8 + (m & 7); y = s.y0 + (m >> 3); z = r; }
           const bool valid = x < p.W && y < p.H;
-          const float* brow = s_bias;
+          int cls = 63;                       // 3-D: which taps are inside the volume (63 = all of them)
           if (MODE == MARCH_3D_PLANES) {
             const int cz = (z >= 1) + 2 * (z + 1 < p.NIMG);
             const int cy = (y >= DIL3D) + 2 * (y + DIL3D < p.H);
             const int cx = (x >= DIL3D) + 2 * (x + DIL3D < p.W);
-            brow = s_btab + ((cz * 4 + cy) * 4 + cx) * COUT;
+            cls = (cz * 4 + cy) * 4 + cx;
           }
+          const float* brow = s_btab + cls * COUT;
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
           uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
 #pragma unroll
@@ -311,15 +309,16 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              f[i] = __uint_as_float(v[c0 + i]) + brow[c0 + i];
+              const float bv = (MODE == MARCH_3D_PLANES && cls != 63) ? brow[c0 + i] : p.bias_c[c0 + i];
+              f[i] = __uint_as_float(v[c0 + i]) + bv;
               if (p.relu) f[i] = fmaxf(f[i], 0.f);
             }
             if (fuse_hm) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                d0 = fmaf(f[i], s_hmw[c0 + i], d0);
-                d1 = fmaf(f[i], s_hmw[COUT + c0 + i], d1);
-                d2 = fmaf(f[i], s_hmw[2 * COUT + c0 + i], d2);
+                d0 = fmaf(f[i], p.hmw_c[(c0 + i) % 32], d0);
+                d1 = fmaf(f[i], p.hmw_c[32 + (c0 + i) % 32], d1);
+                d2 = fmaf(f[i], p.hmw_c[64 + (c0 + i) % 32], d2);
               }
             }
             if (valid && p.out) {
@@ -475,6 +474,12 @@ int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
   p.chunks = L.C / KC;
   p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
+  if ((L.bias != nullptr) != (L.bias_host != nullptr) || (L.bias_tab != nullptr) != (L.bias_tab_host != nullptr) ||
+      (L.hm_w != nullptr) != (L.hm_w_host != nullptr))
+    return CETPICK_ERR_BAD_ARG;             // every epilogue constant comes with its host copy
+  for (int c = 0; c < L.Cout; ++c)
+    p.bias_c[c] = L.bias_tab_host ? L.bias_tab_host[63 * L.Cout + c] : L.bias_host ? L.bias_host[c] : 0.f;
+  if (L.hm_w_host) memcpy(p.hmw_c, L.hm_w_host, 96 * sizeof(float));
   if (L.mode == MARCH_3D_PLANES) {
     p.bias_tab = L.bias_tab; p.hm_w = L.hm_w; p.hm_out = L.hm_out; p.hm_sigmoid = L.hm_sigmoid;
     if ((L.hm_out != nullptr) != (L.hm_w != nullptr)) return CETPICK_ERR_BAD_ARG;
@@ -510,10 +515,16 @@ extern "C" int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = CETPICK_OK;
   if (cudaMemcpyAsync(d, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = CETPICK_ERR_CUDA;
+  std::vector<float> bh;
+  if (rc == CETPICK_OK && bias) {
+    bh.resize(Cout);
+    if (cudaMemcpy(bh.data(), bias, (size_t)Cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = CETPICK_ERR_CUDA;
+  }
   if (rc == CETPICK_OK) {
     MarchLaunch L;
     L.mode = mode; L.dil = dil; L.nsrc = nsrc; L.src[0] = src0; L.src[1] = src1; L.C = C;
     L.NIMG = NIMG; L.H = H; L.W = W; L.wpk = d; L.Cout = Cout; L.bias = bias; L.relu = relu; L.out = out;
+    L.bias_host = bias ? bh.data() : nullptr;
     rc = conv_march_launch(L, st);
   }
   cudaError_t e = cudaStreamSynchronize(st);

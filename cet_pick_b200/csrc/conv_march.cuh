@@ -21,7 +21,8 @@ struct MarchLaunch {
   int NIMG = 0, H = 0, W = 0;
   const void* wpk = nullptr;    // device, layout of march_pack_weights()
   int Cout = 0;             // 32 or 64
-  const float* bias = nullptr;  // [Cout] fp32 or null
+  const float* bias = nullptr;  // [Cout] fp32 or null (device)
+  const float* bias_host = nullptr;      // the same values on the host: they travel in the kernel parameters
   int relu = 0;
   void* out = nullptr;      // bf16 [NIMG][H][W][Cout] (may be null when hm_out is set)
   // 3-D mode extras -------------------------------------------------------------------------
@@ -30,9 +31,11 @@ struct MarchLaunch {
   // This is how a 1x1 conv with bias in FRONT of a zero-padded conv is folded into it exactly
   // (conv_final -> feature_head.0, unet.py:882 -> unet_small.py:85).
   const float* bias_tab = nullptr;
+  const float* bias_tab_host = nullptr;
   // fused `hm` head (unet_small.py:53-61,89): Conv3d(Cout,1,(3,1,1),pad (1,0,0)) on the ReLU output,
   // kept in fp32 registers across the march; hm_w = [3][Cout] fp32 (kz major), hm_out = (D,H,W) fp32.
   const float* hm_w = nullptr;
+  const float* hm_w_host = nullptr;
   float* hm_out = nullptr;
   int hm_sigmoid = 0;       // models/utils.py:167-169 _sigmoid fused
 };

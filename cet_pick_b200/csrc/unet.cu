@@ -367,7 +367,9 @@ WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W) {
 
 struct HeadExtras {
   const float* bias_tab = nullptr;
+  const float* bias_tab_host = nullptr;
   const float* hm_w = nullptr;
+  const float* hm_w_host = nullptr;
   float* hm_out = nullptr;
   int hm_sigmoid = 0;
 };
@@ -385,7 +387,11 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
     M.NIMG = NIMG; M.H = H; M.W = W;
     M.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off;
     M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out;
-    if (ex) { M.bias_tab = ex->bias_tab; M.hm_w = ex->hm_w; M.hm_out = ex->hm_out; M.hm_sigmoid = ex->hm_sigmoid; }
+    M.bias_host = pc.has_bias ? reinterpret_cast<const float*>(m->blob.data() + pc.b_off) : nullptr;
+    if (ex) {
+      M.bias_tab = ex->bias_tab; M.bias_tab_host = ex->bias_tab_host;
+      M.hm_w = ex->hm_w; M.hm_w_host = ex->hm_w_host; M.hm_out = ex->hm_out; M.hm_sigmoid = ex->hm_sigmoid;
+    }
     return conv_march_launch(M, st);
   }
   if (pc.halo) {
@@ -656,13 +662,15 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
     } else {
       HeadExtras ex;
       ex.bias_tab = reinterpret_cast<const float*>(blob + m->fh0_btab);
+      ex.bias_tab_host = reinterpret_cast<const float*>(m->blob.data() + m->fh0_btab);
       if ((rc = run_conv(m, "fhead0+conv_final", m->fh0, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st, &ex))) return rc;
       f_in = buf(0, 1);
     }
     __nv_bfloat16* f_out = (f_in == buf(0, 1)) ? buf(0, 0) : buf(0, 1);
     if (!proj && m->fh2.march >= 0) {
       HeadExtras ex;
-      ex.hm_w = hmw; ex.hm_out = hm; ex.hm_sigmoid = apply_sigmoid;
+      ex.hm_w = hmw; ex.hm_w_host = reinterpret_cast<const float*>(m->blob.data() + m->hm_w);
+      ex.hm_out = hm; ex.hm_sigmoid = apply_sigmoid;
       if ((rc = run_conv(m, "fhead2+hm", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, nullptr, 0, 0, 0, st, &ex))) return rc;
     } else {
       if ((rc = run_conv(m, "fhead2", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, f_out, 0, 0, 0, st))) return rc;

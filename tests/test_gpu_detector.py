@@ -66,9 +66,10 @@ def test_run_end_to_end_from_checkpoint(tmp_path, monkeypatch):
     with torch.no_grad():
         hm = uo.sigmoid_clamp(uo.forward(x, sd, want_proj=False)["hm"]).numpy()
     ref = do.tomo_decode(hm, 3, None, K)[0]                             # x+.25, y+.25, z, s, s (half-res)
-    tol = 1e-2
-    kth = ref[-1, 3]
-    strong = ref[ref[:, 3] > kth + 2 * tol]
+    tol = 1e-2                     # stated BF16 heat-map tolerance (scores)
+    margin = 4e-3                  # picks this far above the K-th score cannot drop out of the top-K (measured
+    kth = ref[-1, 3]               # heat-map error is <= 2e-3); nearer ones may legitimately reorder
+    strong = ref[ref[:, 3] > kth + margin]
     assert len(strong) > 0
     for r in strong:
         x2, y2, z = 2 * int(np.floor(r[0])), 2 * int(np.floor(r[1])), int(r[2])
