@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "../../include/cetpick.h"
@@ -54,5 +55,19 @@ inline uint16_t f2bf_host(float f) {
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Kernel launch with explicit configuration (decode.cu).  Programmatic dependent launch was tried for
+// the ~19 short kernels of one decode and measured SLOWER on B200 (0.70 -> 1.0-1.18 ms at 512x1024x1024,
+// profiles/r1g): dependents that become resident early and park in griddepcontrol.wait take issue and
+// memory slots from the streaming kernel; plain stream order is kept.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 }  // namespace cetpick

@@ -20,6 +20,7 @@
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace cetpick {
 
@@ -63,6 +64,7 @@ struct alignas(64) ScanParams {
   int zlo, zhi;        // planes whose voxels are emitted
   int mode;            // MODE_*
   int nms_mode;        // CETPICK_NMS_NONE / 3D / FIBER
+  int P;               // xy half-width of the NMS window (sieve_kernel; scan_kernel has it as a template argument)
   int shift, bits;     // HIST digit
   int last_pass;       // HIST: this pass resolves the last digit
   int ZC;              // planes per work item
@@ -143,6 +145,37 @@ __device__ void select_digit(uint32_t* ghist, int nb, uint32_t kleft, uint32_t* 
     }
   }
   __syncthreads();
+}
+
+// thread 0 of the last CTA of a COLLECT pass: decide what the EQ pass / fallback have to do
+__device__ void collect_plan(const ScanParams& p, DecodeState* st) {
+  const uint32_t n = st->cand_count;      // list entries incl. chunk padding (space check)
+  const uint32_t nr = st->n_real;         // voxels above the threshold
+  st->n_gt = nr;
+  st->n_real = 0;
+  st->eq_need = 0;
+  st->eq_zc = -1;
+  st->done_ctr = 0;
+  if (n > p.cap_gt) {
+    if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; }
+    else st->flags |= FLAG_INTERNAL;
+    st->cand_count = 0;
+  } else if (nr < (uint32_t)p.K) {
+    const uint32_t need = (uint32_t)p.K - nr;
+    uint32_t cum = 0;
+    int zc = -1;
+    for (int z = p.zlo; z < p.zhi; ++z) {
+      cum += p.eqcnt[z];
+      if (cum >= need) { zc = z; break; }
+    }
+    if (zc < 0) {  // the sampled bound was not valid (cannot happen) -> exact path
+      if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; st->cand_count = 0; }
+      else st->flags |= FLAG_INTERNAL;
+    } else {
+      st->eq_need = need;
+      st->eq_zc = zc;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -659,36 +692,194 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       for (int i = threadIdx.x; i < D; i += NT) p.eqcnt[i] = 0;
     }
   } else {  // MODE_COLLECT: plan the EQ pass
-    if (threadIdx.x == 0) {
-      const uint32_t n = st->cand_count;      // list entries incl. chunk padding (space check)
-      const uint32_t nr = st->n_real;         // voxels above the threshold
-      st->n_gt = nr;
-      st->n_real = 0;
-      st->eq_need = 0;
-      st->eq_zc = -1;
-      st->done_ctr = 0;
-      if (n > p.cap_gt) {
-        if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; }
-        else st->flags |= FLAG_INTERNAL;
-        st->cand_count = 0;
-      } else if (nr < (uint32_t)p.K) {
-        const uint32_t need = (uint32_t)p.K - nr;
-        uint32_t cum = 0;
-        int zc = -1;
-        for (int z = p.zlo; z < p.zhi; ++z) {
-          cum += p.eqcnt[z];
-          if (cum >= need) { zc = z; break; }
-        }
-        if (zc < 0) {  // the sampled bound was not valid (cannot happen) -> exact path
-          if (p.phase == 0) { st->need_fallback = 1; st->flags |= FLAG_FALLBACK; st->cand_count = 0; }
-          else st->flags |= FLAG_INTERNAL;
-        } else {
-          st->eq_need = need;
-          st->eq_zc = zc;
-        }
+    if (threadIdx.x == 0) collect_plan(p, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sieve_kernel: the COLLECT pass as a pure stream.  With a threshold t0 > 0 in hand only voxels with
+// heat >= t0 can be selected, and those are rare (a fraction ~ 64K/N of the map), so the map is read
+// ONCE with coalesced 16-byte loads, every voxel costs one compare, and the 3-D NMS test
+// (decode.py:27-33; fiber: :11-25) runs only for the hits: each warp queues its hits in shared memory
+// and, 32 at a time, one lane per hit reads the hit's (3 x k x k) neighbourhood straight from global
+// memory (L2: the neighbour planes were just streamed or are about to be).  A degenerate threshold
+// (t0 <= 0, where suppressed voxels matter too) or a map that is one big plateau >= t0 takes the same
+// path with every voxel a hit -- slower (L1-bound) but exact, no second code path.
+// Needs 16-byte aligned rows (p.vec_ok); other maps keep scan_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int SIEVE_THREADS = 256;
+constexpr int SIEVE_QUEUE = 64;    // per-warp hit ring (entries); a push adds <= 32, a drain takes 32
+
+// NOT L1::no_allocate: those loads are looked up evict-first in L2, the streamed planes are gone
+// again before a hit asks for its neighbourhood and every neighbour read goes to DRAM (+30 % traffic,
+// profiles/r1h); with the default policy the last ~100 MB of the stream stay L2-resident.
+template <int LD>
+__device__ __forceinline__ float4 ldg_stream4(const float4* ptr) {
+  float4 v;
+  if (LD == 0)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  else
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr));
+  return v;
+}
+
+// NMS output key of voxel idx (the caller knows it is in the volume)
+__device__ __forceinline__ uint32_t sieve_okey(const float* __restrict__ heat, uint32_t idx, int D, int H, int W,
+                                               int P, int nms_mode, bool& is_nan) {
+  const int hw = H * W;
+  const int z = (int)(idx / (uint32_t)hw);
+  const int r = (int)(idx - (uint32_t)z * (uint32_t)hw);
+  const int y = r / W, x = r - y * W;
+  const float c = __ldg(heat + idx);
+  is_nan = (c != c);
+  if (nms_mode == CETPICK_NMS_NONE) return is_nan ? KEY_ZERO : f2key(c);
+  const int ylo = max(y - P, 0), yhi = min(y + P, H - 1), xlo = max(x - P, 0), xhi = min(x + P, W - 1);
+  auto mxy = [&](int zz) -> float {      // in-plane window maximum around (zz, y, x); NaN ignored (fmaxf)
+    const float* pl = heat + (size_t)zz * hw;
+    float m = -INFINITY;
+    for (int yy = ylo; yy <= yhi; ++yy)
+      for (int xx = xlo; xx <= xhi; ++xx) m = fmaxf(m, __ldg(pl + (size_t)yy * W + xx));
+    return m;
+  };
+  if (nms_mode == CETPICK_NMS_FIBER) {   // decode.py:11-25: xy suppression, then z suppression of the result
+    if (!(c == mxy(z))) return KEY_ZERO;   // xy-suppressed to 0 * c: whatever z says, the key is that of zero
+    const float o1 = c;
+    float m = o1;
+#pragma unroll
+    for (int dz = -1; dz <= 1; dz += 2) {
+      const int zz = z + dz;
+      if (zz < 0 || zz >= D) continue;
+      const float cb = __ldg(heat + (size_t)zz * hw + r);
+      const float ob = (cb == mxy(zz)) ? cb : cb * 0.0f;
+      m = fmaxf(m, ob);
+    }
+    return (o1 == m) ? f2key(o1) : KEY_ZERO;
+  }
+  // staged: most hits sit on the flank of a peak and fail in their own plane, which is in L2
+  if (!(c == mxy(z))) return KEY_ZERO;
+  if (z > 0 && !(c >= mxy(z - 1))) return KEY_ZERO;          // window maxima hold no NaN (fmaxf), c is not NaN here
+  if (z + 1 < D && !(c >= mxy(z + 1))) return KEY_ZERO;
+  return f2key(c);
+}
+
+template <int U, int CTAS, int LD>
+__global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid_constant__ ScanParams p) {
+  __shared__ uint32_t s_q[SIEVE_THREADS / 32][SIEVE_QUEUE];
+  __shared__ uint32_t s_ticket;
+  DecodeState* st = p.st;
+  const uint32_t t0key = st->t0key;
+  const float t0f = key2f(t0key);
+  const bool all = (KEY_ZERO >= t0key);            // suppressed voxels (key of 0) matter: every voxel is a hit
+  const int D = p.D, H = p.H, W = p.W, hw = H * W;
+  const int P = (p.nms_mode == CETPICK_NMS_NONE) ? 0 : p.P;
+  const uint32_t n4 = (uint32_t)(((size_t)D * hw) >> 2);
+  const float4* heat4 = reinterpret_cast<const float4*>(p.heat);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* q = s_q[warp];
+  uint32_t q_head = 0, q_n = 0;                    // warp-uniform
+  uint32_t w_base = 0, w_used = CAND_CHUNK;        // this warp's chunk of the candidate list
+  bool saw_nan = false;
+
+  // one lane per queued hit: NMS test, then append (ok > t0) / count (ok == t0)
+  auto drain = [&](uint32_t cnt) {
+    const bool act = (uint32_t)lane < cnt;
+    uint32_t idx = 0, ok = KEY_ZERO;
+    if (act) {
+      idx = q[(q_head + lane) % SIEVE_QUEUE];
+      bool nan;
+      ok = sieve_okey(p.heat, idx, D, H, W, P, p.nms_mode, nan);
+      saw_nan |= nan;
+    }
+    q_head = (q_head + cnt) % SIEVE_QUEUE;
+    q_n -= cnt;
+    const bool take = act && (ok > t0key);
+    const bool eq = act && (ok == t0key);
+    if (__any_sync(0xffffffffu, eq)) {
+      const int z = eq ? (int)(idx / (uint32_t)hw) : -1 - lane;   // one atomic per distinct plane in the warp
+      const unsigned peers = __match_any_sync(0xffffffffu, z);
+      if (eq && lane == __ffs(peers) - 1) atomicAdd(&p.eqcnt[z], (uint32_t)__popc(peers));
+    }
+    const unsigned tb = __ballot_sync(0xffffffffu, take);
+    if (tb) {
+      const uint32_t tot = __popc(tb);
+      if (w_used + tot > CAND_CHUNK) {             // next chunk; pad the unused tail with composite 0
+        for (uint32_t k = w_used + lane; k < CAND_CHUNK; k += 32)
+          if (w_base + k < p.cap_gt) p.cand[w_base + k] = 0ull;
+        uint32_t nb = 0;
+        if (lane == 0) nb = atomicAdd(&st->cand_count, (uint32_t)CAND_CHUNK);
+        w_base = __shfl_sync(0xffffffffu, nb, 0);
+        w_used = 0;
+      }
+      const uint32_t off = w_base + w_used + __popc(tb & ((1u << lane) - 1u));
+      w_used += tot;
+      if (lane == 0) atomicAdd(&st->n_real, tot);
+      if (take && off < p.cap_gt) p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
+    }
+  };
+
+  const uint32_t stride = gridDim.x * (uint32_t)(SIEVE_THREADS * U);
+  for (uint32_t base = blockIdx.x * (uint32_t)(SIEVE_THREADS * U); base < n4; base += stride) {
+    float4 v[U];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i4 = base + (uint32_t)(u * SIEVE_THREADS) + threadIdx.x;
+      if (i4 < n4) { v[u] = ldg_stream4<LD>(heat4 + i4); valid |= 0xFu << (4 * u); }
+      else v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    // hit = !(c < t0): c >= t0 or NaN
+    uint32_t hits = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      hits |= (!(v[u].x < t0f) ? 1u : 0u) << (4 * u);
+      hits |= (!(v[u].y < t0f) ? 2u : 0u) << (4 * u);
+      hits |= (!(v[u].z < t0f) ? 4u : 0u) << (4 * u);
+      hits |= (!(v[u].w < t0f) ? 8u : 0u) << (4 * u);
+    }
+    if (all) {
+      hits = valid;
+    } else if (P >= 1 && hits) {
+      // a hit with a strictly larger x-neighbour inside its own float4 cannot survive any window with
+      // P >= 1 (3-D: suppressed; fiber: xy-suppressed to zero) and t0 > 0 here: drop it before the queue
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t kill = 0;
+        kill |= (v[u].y > v[u].x) ? 1u : 0u;
+        kill |= (v[u].x > v[u].y || v[u].z > v[u].y) ? 2u : 0u;
+        kill |= (v[u].y > v[u].z || v[u].w > v[u].z) ? 4u : 0u;
+        kill |= (v[u].z > v[u].w) ? 8u : 0u;
+        hits &= ~(kill << (4 * u));
       }
     }
+    hits &= valid;
+    while (__any_sync(0xffffffffu, hits != 0)) {   // push one hit per lane per round
+      const bool has = hits != 0;
+      const unsigned hb = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int b = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const uint32_t i4 = base + (uint32_t)((b >> 2) * SIEVE_THREADS) + threadIdx.x;
+        q[(q_head + q_n + __popc(hb & ((1u << lane) - 1u))) % SIEVE_QUEUE] = i4 * 4u + (uint32_t)(b & 3);
+      }
+      q_n += __popc(hb);
+      __syncwarp();
+      if (q_n >= 32) drain(32);
+    }
   }
+  if (q_n) drain(q_n);
+  for (uint32_t k = w_used + lane; k < CAND_CHUNK; k += 32)   // pad the tail of the warp's last chunk
+    if (w_base + k < p.cap_gt) p.cand[w_base + k] = 0ull;
+  if (saw_nan) atomicOr(&st->flags, (uint32_t)FLAG_NAN);
+
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->done_ctr, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (threadIdx.x == 0) collect_plan(p, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -709,9 +900,15 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
   const uint32_t dmask = (1u << bits) - 1u;
   for (int i = threadIdx.x; i < HIST_BINS; i += CAND_THREADS) s_hist[i] = 0;
   __syncthreads();
-  for (uint32_t i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
-    const unsigned long long c = cand[i];
-    if (first || (c >> hs) == prefix) atomicAdd(&s_hist[(uint32_t)(c >> shift) & dmask], 1u);
+  for (uint32_t i0 = blockIdx.x * CAND_THREADS; i0 < n; i0 += gridDim.x * CAND_THREADS) {   // CTA-uniform trip count
+    const uint32_t i = i0 + threadIdx.x;
+    const unsigned long long c = (i < n) ? cand[i] : 0ull;
+    // candidates sit just above the threshold, so whole warps fall into one bin of the upper digits:
+    // one shared-memory atomic per group of equal bins instead of a 32-way serialised one
+    const bool in = (i < n) && (first || (c >> hs) == prefix);
+    const uint32_t bin = in ? ((uint32_t)(c >> shift) & dmask) : (0x80000000u | (threadIdx.x & 31));
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < (1 << bits); i += CAND_THREADS)
@@ -938,7 +1135,7 @@ int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
     CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  kern<<<grid, SCAN_THREADS, smem, s>>>(p);
+  CETPICK_CUDA(launch_k(kern, dim3(grid), dim3(SCAN_THREADS), smem, s, p));
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }
@@ -1008,7 +1205,7 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
 
   ScanParams p = {};
   p.heat = heat; p.D = D; p.H = H; p.W = W;
-  p.nms_mode = nms_mode; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand;
+  p.nms_mode = nms_mode; p.P = P; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand;
   p.cap_gt = L.cap_gt; p.cap_total = L.cap_total;
   p.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   p.use_tma = 0;
@@ -1038,6 +1235,24 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   auto run_collect = [&](int gate, int phase, int all) -> int {
     ScanParams q = p;
     q.mode = MODE_COLLECT; q.zlo = 0; q.zhi = D; q.gate = gate; q.phase = phase; q.collect_all = all;
+    if (p.vec_ok && !gate && !all) {   // the usual pass: threshold-first stream (sieve_kernel)
+      const uint32_t n4 = (uint32_t)(n >> 2);
+      static const int variant = getenv("CETPICK_SIEVE_VARIANT") ? atoi(getenv("CETPICK_SIEVE_VARIANT")) : 0;
+      auto go = [&](auto kern, int U, int ctas) -> int {
+        const int grid = (int)std::min<uint32_t>((uint32_t)(num_sms() * ctas), ceil_div<uint32_t>(n4, SIEVE_THREADS * U));
+        CETPICK_CUDA(launch_k(kern, dim3(grid), dim3(SIEVE_THREADS), 0, s, q));
+        CETPICK_LAUNCH_CHECK();
+        return CETPICK_OK;
+      };
+      switch (variant) {
+        case 1: return go(sieve_kernel<8, 4, 1>, 8, 4);
+        case 2: return go(sieve_kernel<8, 3, 1>, 8, 3);
+        case 3: return go(sieve_kernel<4, 6, 1>, 4, 6);
+        case 4: return go(sieve_kernel<8, 4, 0>, 8, 4);
+        case 5: return go(sieve_kernel<2, 8, 1>, 2, 8);
+        default: return go(sieve_kernel<4, 4, 1>, 4, 4);
+      }
+    }
     const int grid = scan_grid(D, H, W, 0, D, &q.ZC);
     return launch_scan_p(P, q, grid, s);
   };
@@ -1068,17 +1283,19 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     const int cs[6] = {53, 42, 32, 21, 10, 0}, cb[6] = {11, 11, 10, 11, 11, 10};
     const int grid = std::min<int>(num_sms() * 2, std::max<uint32_t>(1, ceil_div<uint32_t>(L.cap_total, CAND_THREADS * 8)));
     for (int i = 0; i < 6; ++i) {
-      cand_hist_kernel<<<grid, CAND_THREADS, 0, s>>>(cand, st, hist, cs[i], cb[i], i == 0, i == 5,
-                                                     L.cap_total, K);
+      CETPICK_CUDA(launch_k(cand_hist_kernel, dim3(grid), dim3(CAND_THREADS), 0, s, cand, st, hist, cs[i], cb[i],
+                              (int)(i == 0), (int)(i == 5), L.cap_total, K));
       CETPICK_LAUNCH_CHECK();
     }
-    cand_compact_kernel<<<grid, CAND_THREADS, 0, s>>>(cand, st, outb, L.cap_total, K);
+    CETPICK_CUDA(launch_k(cand_compact_kernel, dim3(grid), dim3(CAND_THREADS), 0, s, cand, st, outb, L.cap_total, K));
     CETPICK_LAUNCH_CHECK();
   }
   if (K <= RANK_MAX_K) {
-    rank_kernel<<<dim3(ceil_div(K, RANK_THREADS), RANK_PARTS), RANK_THREADS, 0, s>>>(outb, K, ranks);
+    CETPICK_CUDA(launch_k(rank_kernel, dim3(ceil_div(K, RANK_THREADS), RANK_PARTS), dim3(RANK_THREADS), 0, s, outb, K,
+                            ranks));
     CETPICK_LAUNCH_CHECK();
-    rank_write_kernel<<<ceil_div(K, 256), 256, 0, s>>>(outb, K, ranks, heat, reg, D, H, W, dets, inds);
+    CETPICK_CUDA(launch_k(rank_write_kernel, dim3(ceil_div(K, 256)), dim3(256), 0, s, outb, K, ranks, heat, reg, D, H, W,
+                            dets, inds));
     CETPICK_LAUNCH_CHECK();
   } else {
     const int use_smem = L.npad <= SORT_SMEM_MAX;
@@ -1089,7 +1306,8 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
                                         SORT_SMEM_MAX * 8));
       attr_done = true;
     }
-    sort_write_kernel<<<1, 1024, smem, s>>>(outb, K, L.npad, use_smem, heat, reg, D, H, W, dets, inds);
+    CETPICK_CUDA(launch_k(sort_write_kernel, dim3(1), dim3(1024), smem, s, outb, K, L.npad, use_smem, heat, reg, D, H, W,
+                            dets, inds));
     CETPICK_LAUNCH_CHECK();
   }
   return CETPICK_OK;

@@ -148,6 +148,54 @@ def test_oracle_medium_plateau_eq_path(dec, do):
     assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, 2000)))
 
 
+# ---- sieve_kernel (threshold-first COLLECT; aligned rows, volumes above the candidate capacity) ----
+@pytest.mark.parametrize("kernel,fiber,K", [(5, False, 800), (7, False, 300), (3, True, 1000), (1, False, 500)])
+def test_sieve_window_modes(dec, do, kernel, fiber, K):
+    D, H, W = 40, 256, 256
+    hm = synth.heatmap_tiefree_np(D, H, W, 100 + kernel)[None, None]
+    out = dec.tomo_decode(cu(hm), kernel=kernel, K=K, if_fiber=fiber).cpu().numpy()
+    assert np.array_equal(bits(out), bits(do.tomo_decode(hm, kernel, None, K, fiber)))
+    flags, _ = dec.decode_status()
+    assert flags == 0
+
+
+def test_sieve_plain_topk(dec, do):
+    """no NMS (P = 0, no z neighbourhood): every voxel is its own window maximum."""
+    D, H, W = 40, 256, 256
+    hm = synth.heatmap_tiefree_np(D, H, W, 9)[None, None]
+    ts, zs, ys, xs, ti = dec._topk(cu(hm), K=1500)
+    rs, rz, ry, rx, ri = do.topk(hm, 1500)
+    assert np.array_equal(ti.cpu().numpy(), ri) and np.array_equal(bits(ts.cpu().numpy()[:, 0]), bits(rs))
+
+
+def test_sieve_degenerate_threshold_negative_map(dec, do):
+    """all-negative map: the K largest NMS outputs are the -0.0 products of suppressed voxels, the
+    threshold is 0 and every voxel is a hit (the exact slow path of the sieve)."""
+    D, H, W = 36, 256, 256
+    u = synth.uniform_np(11, D * H * W).reshape(1, 1, D, H, W)
+    hm = (u - np.float32(2.0)).astype(np.float32)
+    out = dec.tomo_decode(cu(hm), kernel=3, K=777).cpu().numpy()
+    assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, 777)))
+
+
+def test_sieve_dense_plateau_at_threshold(dec, do):
+    """the K-th score sits on a huge plateau (map clipped from above): hits are dense, picks come
+    from the plateau in index order through the EQ pass."""
+    D, H, W = 36, 256, 256
+    hm = np.minimum(synth.heatmap_tiefree_np(D, H, W, 5), np.float32(0.75))[None, None]
+    out = dec.tomo_decode(cu(hm), kernel=3, K=900).cpu().numpy()
+    assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, 900)))
+
+
+def test_sieve_nan_flag(dec):
+    D, H, W = 36, 256, 256
+    hm = synth.heatmap_tiefree_np(D, H, W, 6).copy()
+    hm[17, 100, 31] = np.nan
+    dec.tomo_decode(cu(hm[None, None]), kernel=3, K=100)
+    flags, _ = dec.decode_status()
+    assert flags & 1
+
+
 def test_topk_plain_full_ranking(dec, do):
     """_topk has no NMS: the full descending ranking (K == N) of a random map must match."""
     D, H, W = 9, 24, 40
