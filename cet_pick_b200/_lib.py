@@ -43,6 +43,7 @@ SIGNATURES = {
                                        _vp, _vp]),
     "cetpick_upconv_bf16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _vp, _int, _int, _vp]),
     "cetpick_conv_halo_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
+    "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "cetpick_probe_mma_rate": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),

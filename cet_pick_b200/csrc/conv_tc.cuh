@@ -43,6 +43,10 @@ int tmap_encode_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t
 int tmap_encode_f32_nanfill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                             const uint64_t* strides_bytes, const uint32_t* box);
 
+// fp32 tiled tensor map without swizzle whose out-of-bounds elements read as zero.
+int tmap_encode_f32_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box);
+
 // Enqueue the convolution.  Returns a CETPICK_* code.
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
 

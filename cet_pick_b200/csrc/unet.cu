@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_march.cuh"
+#include "conv_stem.cuh"
 #include "conv_up.cuh"
 #include "conv_halo.cuh"
 
@@ -226,7 +227,8 @@ struct cetpick_unet {
   std::vector<uint8_t> blob;     // host staging of all packed weights
   void* d_blob = nullptr;
   // packed layers
-  size_t stem_w = 0, stem_b = 0, hm_w = 0;
+  size_t stem_w = 0, stem_b = 0, stem_tc_w = 0, hm_w = 0;
+  float stem_shift[16] = {};
   bool fold_cf = false;          // conv_final folded into feature_head.0 (weights + tap-validity bias table)
   size_t fh0_btab = 0;
   std::vector<PackedConv> down1, down2, upc, up1, up2;
@@ -459,7 +461,12 @@ extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
     for (int c = 0; c < 16; ++c) {
       for (int t = 0; t < 49; ++t) sw[t * 16 + c] = (float)((double)(*w)[c * 49 + t] * f.scale[c]);
       sb[c] = (float)f.shift[c];
+      m->stem_shift[c] = (float)f.shift[c];
     }
+    // tensor-core image of the same weights (conv_stem.cu)
+    const std::vector<uint16_t> pk = stem_pack_weights(w->data(), f.scale.data());
+    m->stem_tc_w = blob_alloc(m, pk.size() * 2);
+    memcpy(m->blob.data() + m->stem_tc_w, pk.data(), pk.size() * 2);
   }
   int outs = 16;
   for (int i = 0; i < nb; ++i) {
@@ -609,12 +616,19 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   {
     g_prof.begin();
     g_prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
-    const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
-    const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
-    stem_kernel<<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
-                                      reinterpret_cast<const float*>(blob + m->stem_w),
-                                      reinterpret_cast<const float*>(blob + m->stem_b), buf(0, 0));
-    CETPICK_LAUNCH_CHECK();
+    if (stem_tc_supported(tomo, W)) {          // tensor-core march (conv_stem.cu)
+      StemLaunch SL;
+      SL.in = tomo; SL.D = D; SL.H = H; SL.W = W; SL.wpk = blob + m->stem_tc_w; SL.out = buf(0, 0);
+      memcpy(SL.bias, m->stem_shift, sizeof(SL.bias));
+      if ((rc = conv_stem_launch(SL, st))) return rc;
+    } else {                                    // rows not 16-byte aligned: CUDA-core kernel
+      const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
+      const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
+      stem_kernel<<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
+                                        reinterpret_cast<const float*>(blob + m->stem_w),
+                                        reinterpret_cast<const float*>(blob + m->stem_b), buf(0, 0));
+      CETPICK_LAUNCH_CHECK();
+    }
   }
   // encoder: level i: in Y0 -> conv1 -> Y1 -> conv2 -> Y2 (skip) -> pool -> next level's Y0
   for (int i = 0; i < nb; ++i) {

@@ -172,6 +172,13 @@ int cetpick_conv_halo_bf16(int nsrc, const void* src0, const void* src1, int C, 
                            const float* w_host, const float* bias_host, int Cout, int relu, void* out,
                            void* stream);
 
+/* Test hook: the detector stem Conv2d(1,16,7,stride 2,pad 3)+BN+ReLU through the tensor-core march of
+ * csrc/conv_stem.cu (replaces cet_pick/models/networks/unet_small.py:35-37,72-74).  in: fp32 device (D,H,W)
+ * with W % 4 == 0; w_host: fp32 HOST weight (16,1,7,7); scale_host/shift_host: folded BatchNorm (HOST, [16],
+ * nullable); out: bf16 device (D,(H-1)/2+1,(W-1)/2+1,16).  Packs, uploads, launches and synchronises. */
+int cetpick_conv_stem_bf16(const float* in, int D, int H, int W, const float* w_host,
+                           const float* scale_host, const float* shift_host, void* out, void* stream);
+
 /* Hardware probe (test hook): D[128][32] = A_big[rows] * B^T where the A descriptor starts r0 rows
  * into a TMA-written swizzled tile, with 8-row groups sbo_bytes apart and the given base_offset. */
 int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, int sbo_bytes,

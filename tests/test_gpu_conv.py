@@ -245,3 +245,29 @@ def test_conv_halo_kernel(L, nsrc, c, cout, n, h, w):
     xin = torch.cat(srcs, 3).float().permute(0, 3, 1, 2)
     ref = F.relu(F.conv2d(xin, wt.float(), b, padding=1)).permute(0, 2, 3, 1)
     assert (out.float() - ref).abs().max().item() <= 2e-2
+
+
+# ---- tensor-core stem (csrc/conv_stem.cu): Conv2d(1,16,7,s2,p3)+BN+ReLU, unet_small.py:35-37,72-74 ----
+@pytest.mark.parametrize("d,h,w", [(2, 32, 64), (3, 37, 68), (1, 5, 8), (2, 300, 520), (1, 129, 1028), (2, 2, 4)])
+def test_stem_tensor_core_march(L, d, h, w):
+    g = torch.Generator(device="cuda").manual_seed(d * 100 + h + w)
+    x = torch.rand(d, h, w, device="cuda", generator=g)
+    wt = (torch.rand(16, 1, 7, 7, device="cuda", generator=g) * 2 - 1) / 7
+    scale = torch.rand(16, device="cuda", generator=g) + 0.5
+    shift = torch.randn(16, device="cuda", generator=g) * 0.1
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.full((d, ho, wo, 16), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wh, sh, bh = wt.cpu().contiguous(), scale.cpu().contiguous(), shift.cpu().contiguous()
+    rc = L.lib().cetpick_conv_stem_bf16(x.data_ptr(), d, h, w, wh.data_ptr(), sh.data_ptr(), bh.data_ptr(),
+                                        out.data_ptr(), L.stream_ptr())
+    L.check(rc, "cetpick_conv_stem_bf16")
+    torch.cuda.synchronize()
+    # reference on the same bf16-rounded operands (input and BN-folded weight), fp32 accumulate
+    wf = (wt * scale.view(16, 1, 1, 1)).bfloat16().float()
+    ref = F.relu(F.conv2d(x.bfloat16().float()[:, None], wf, shift, stride=2, padding=3)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1.5e-2, err      # one bf16 rounding of O(1) outputs + accumulation order
+    # and against the exact fp32 conv: operand rounding adds ~2^-9 relative per product
+    ref32 = F.relu(F.conv2d(x[:, None], wt * scale.view(16, 1, 1, 1), shift, stride=2, padding=3)).permute(0, 2, 3, 1)
+    assert (out.float() - ref32).abs().max().item() <= 3e-2
