@@ -27,6 +27,9 @@ SIGNATURES = {
     "cetpick_decode_status": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_i64)]),
     "cetpick_decode_debug_state": (_int, [_vp, _vp, _vp]),
     "cetpick_nms_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
+    "cetpick_greedy_nms_workspace_bytes": (_int, [_i64, _i64, _i64, _i64, C.POINTER(_sz)]),
+    "cetpick_greedy_nms_f32": (_int, [_vp, _i64, _i64, _i64, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp, _i64,
+                                      C.POINTER(_i64), C.POINTER(_int), _vp, _sz, _vp]),
     "cetpick_sigmoid_clamp_f32": (_int, [_vp, _i64, _vp]),
     "cetpick_unet_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
     "cetpick_unet_destroy": (None, [_vp]),
@@ -41,6 +44,8 @@ SIGNATURES = {
     "cetpick_probe_umma": (_int, [_vp, _int, _vp, _int, _int, _int, _int, _vp, _vp]),
     "cetpick_conv_march_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
                                        _vp, _vp]),
+    "cetpick_conv_march_pool_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
+                                            _vp, _vp, _vp]),
     "cetpick_upconv_bf16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _vp, _int, _int, _vp]),
     "cetpick_conv_halo_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

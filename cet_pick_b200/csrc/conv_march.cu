@@ -50,6 +50,7 @@ struct alignas(64) MarchParams {
   int relu;
   const float* bias;
   __nv_bfloat16* out;
+  __nv_bfloat16* pool_out; // 2-D: fused MaxPool2d(2, ceil) output or null
   // epilogue constants live in the kernel-parameter constant bank: FADD/FFMA read them as c[0][imm]
   // operands, so the epilogue puts no load on the shared-memory pipe the UMMA operands stream through
   float bias_c[64];        // 2-D bias / 3-D bias of the interior tap-validity class (row 63 of bias_tab)
@@ -269,12 +270,16 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
       Strip s;
       decode_strip<MODE, MT>(p, k, s);
       float hmA = 0.f, hmB = 0.f;     // fused hm head: partial sums of hm[r-1] and hm[r] (this thread's pixel)
+      const bool pool = MODE == MARCH_2D_ROWS && p.pool_out != nullptr;
+      uint32_t prow[MODE == MARCH_2D_ROWS ? COUT / 2 : 1];   // fused pool: the even row of the pair (packed bf16)
       for (int r = s.ma; r < s.mb; ++r) {
         const uint32_t q = q0 + (uint32_t)(r - s.ma);
         const uint32_t slot = q & smask, par = (q >> sshift) & 1u;
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
-          if ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg) continue;
+          // one epilogue group per (row, M-tile); with the fused pool a group keeps both rows of a pair
+          // (MT = 2: group = M-tile; MT = 1: groups alternate row PAIRS; strips start on even rows)
+          if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) continue;
           ptx::mbar_wait(&bar_afull[slot], par);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
@@ -321,11 +326,37 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
                 d2 = fmaf(f[i], p.hmw_c[64 + (c0 + i) % 32], d2);
               }
             }
-            if (valid && p.out) {
-              uint4 w;
-              w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
-              w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-              dst[c0 / 8] = w;
+            uint4 w;
+            w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
+            w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
+            if (valid && p.out) dst[c0 / 8] = w;
+            if (MODE == MARCH_2D_ROWS && pool) {
+              // max with the even row of the pair (values are post-ReLU, so a missing pixel counts as 0)
+              auto mx = [](uint32_t a, uint32_t b) {
+                __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+                return *reinterpret_cast<uint32_t*>(&r2);
+              };
+              if (!valid) w = make_uint4(0u, 0u, 0u, 0u);
+              if (r & 1) { w.x = mx(w.x, prow[c0 / 2]); w.y = mx(w.y, prow[c0 / 2 + 1]); w.z = mx(w.z, prow[c0 / 2 + 2]); w.w = mx(w.w, prow[c0 / 2 + 3]); }
+              prow[c0 / 2] = w.x; prow[c0 / 2 + 1] = w.y; prow[c0 / 2 + 2] = w.z; prow[c0 / 2 + 3] = w.w;
+            }
+          }
+          if (MODE == MARCH_2D_ROWS && pool && ((r & 1) || r == p.L - 1)) {
+            // prow = max over the row pair; now the x pair (lanes m, m^1) and the even lane stores
+            auto mx = [](uint32_t a, uint32_t b) {
+              __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+              return *reinterpret_cast<uint32_t*>(&r2);
+            };
+            const int Hp = (p.H + 1) >> 1, Wp = (p.W + 1) >> 1;
+            uint4* pd = reinterpret_cast<uint4*>(p.pool_out + (((size_t)z * Hp + (r >> 1)) * Wp + (x >> 1)) * COUT);
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 8; ++c4) {
+              uint4 o;
+              o.x = mx(prow[c4 * 4], __shfl_xor_sync(0xffffffffu, prow[c4 * 4], 1));
+              o.y = mx(prow[c4 * 4 + 1], __shfl_xor_sync(0xffffffffu, prow[c4 * 4 + 1], 1));
+              o.z = mx(prow[c4 * 4 + 2], __shfl_xor_sync(0xffffffffu, prow[c4 * 4 + 2], 1));
+              o.w = mx(prow[c4 * 4 + 3], __shfl_xor_sync(0xffffffffu, prow[c4 * 4 + 3], 1));
+              if (valid && !(m & 1)) pd[c4] = o;
             }
           }
           if (fuse_hm) {
@@ -427,16 +458,19 @@ int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
   const int sms = num_sms();
   int best_n = 1;
   double best_eff = -1.0;
+  const bool even_rows = MODE == MARCH_2D_ROWS && p.pool_out != nullptr;   // fused pool: row pairs stay in one strip
+  int best_R = p.L + (even_rows ? (p.L & 1) : 0);
   for (int n = 1; n <= std::max(1, p.L / 8); ++n) {
-    const int R = ceil_div(p.L, n);
-    if (ceil_div(p.L, R) != n) continue;
-    const long long strips = base_strips * n;
+    int R = ceil_div(p.L, n);
+    if (even_rows) R += R & 1;
+    const int nn = ceil_div(p.L, R);
+    const long long strips = base_strips * nn;
     const double waves = (double)ceil_div<long long>(strips, sms);
     const double eff = ((double)strips / (waves * sms)) * ((double)R / (R + 2));
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_n = n; }
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_n = nn; best_R = R; }
   }
   p.nchunk = best_n;
-  p.R = ceil_div(p.L, best_n);
+  p.R = best_R;
   p.total_strips = base_strips * p.nchunk;
 
   int rc;
@@ -474,6 +508,8 @@ int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
   p.chunks = L.C / KC;
   p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.relu = L.relu; p.bias = L.bias; p.out = static_cast<__nv_bfloat16*>(L.out);
+  p.pool_out = static_cast<__nv_bfloat16*>(L.pool_out);
+  if (L.pool_out && (L.mode != MARCH_2D_ROWS || !L.relu)) return CETPICK_ERR_BAD_ARG;
   if ((L.bias != nullptr) != (L.bias_host != nullptr) || (L.bias_tab != nullptr) != (L.bias_tab_host != nullptr) ||
       (L.hm_w != nullptr) != (L.hm_w_host != nullptr))
     return CETPICK_ERR_BAD_ARG;             // every epilogue constant comes with its host copy
@@ -503,9 +539,20 @@ using namespace cetpick;
 
 // Test hook: one marching convolution from a PyTorch-layout fp32 host weight (packs, uploads,
 // launches, synchronises, frees) -- tests/test_gpu_conv.py.
+extern "C" int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
+                                            int NIMG, int H, int W, const float* w_host, int Cout,
+                                            const float* bias, int relu, void* out, void* pool_out, void* stream);
+
 extern "C" int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
                                        int NIMG, int H, int W, const float* w_host, int Cout,
                                        const float* bias, int relu, void* out, void* stream) {
+  return cetpick_conv_march_pool_bf16(mode, dil, nsrc, src0, src1, C, NIMG, H, W, w_host, Cout, bias, relu, out,
+                                      nullptr, stream);
+}
+
+extern "C" int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
+                                            int NIMG, int H, int W, const float* w_host, int Cout,
+                                            const float* bias, int relu, void* out, void* pool_out, void* stream) {
   g_launches = 0;
   if (!w_host) return CETPICK_ERR_BAD_ARG;
   if (!march_supported(mode, C, nsrc, Cout)) return CETPICK_ERR_UNSUPPORTED;
@@ -524,6 +571,7 @@ extern "C" int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* 
     MarchLaunch L;
     L.mode = mode; L.dil = dil; L.nsrc = nsrc; L.src[0] = src0; L.src[1] = src1; L.C = C;
     L.NIMG = NIMG; L.H = H; L.W = W; L.wpk = d; L.Cout = Cout; L.bias = bias; L.relu = relu; L.out = out;
+    L.pool_out = pool_out;
     L.bias_host = bias ? bh.data() : nullptr;
     rc = conv_march_launch(L, st);
   }

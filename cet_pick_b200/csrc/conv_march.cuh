@@ -25,6 +25,9 @@ struct MarchLaunch {
   const float* bias_host = nullptr;      // the same values on the host: they travel in the kernel parameters
   int relu = 0;
   void* out = nullptr;      // bf16 [NIMG][H][W][Cout] (may be null when hm_out is set)
+  // 2-D mode: also write MaxPool2d(2, ceil_mode=True) of the output (unet.py:225,237-238) as bf16
+  // [NIMG][(H+1)/2][(W+1)/2][Cout] from the epilogue registers (needs relu: padding compares as 0)
+  void* pool_out = nullptr;
   // 3-D mode extras -------------------------------------------------------------------------
   // bias_tab: [64][Cout] fp32 or null: a bias that depends on which taps fall inside the volume,
   // row = (cz*4 + cy)*4 + cx with c = (lower neighbour inside) + 2*(upper neighbour inside) per axis.

@@ -378,7 +378,7 @@ struct HeadExtras {
 
 int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
              int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st,
-             const HeadExtras* ex = nullptr) {
+             const HeadExtras* ex = nullptr, void* pool_out = nullptr) {
   g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : pc.halo ? ":halo" : ":tc")).c_str(),
               pc.flops_per_pixel * (double)NIMG * H * W, st);
   const float* bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
@@ -388,7 +388,7 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
     M.mode = pc.march; M.dil = 4; M.nsrc = pc.nsrc; M.src[0] = s0; M.src[1] = s1; M.C = pc.C[0];
     M.NIMG = NIMG; M.H = H; M.W = W;
     M.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off;
-    M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out;
+    M.Cout = pc.Ntot; M.bias = bias; M.relu = pc.relu; M.out = out; M.pool_out = pool_out;
     M.bias_host = pc.has_bias ? reinterpret_cast<const float*>(m->blob.data() + pc.b_off) : nullptr;
     if (ex) {
       M.bias_tab = ex->bias_tab; M.bias_tab_host = ex->bias_tab_host;
@@ -634,8 +634,11 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   for (int i = 0; i < nb; ++i) {
     const int h = dims[i].h, w = dims[i].w;
     if ((rc = run_conv(m, "down" + std::to_string(i) + ".c1", m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
-    if ((rc = run_conv(m, "down" + std::to_string(i) + ".c2", m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st))) return rc;
-    if (i < nb - 1) {
+    // MaxPool2d(2, ceil) (unet.py:225) comes out of the marching kernel's epilogue where that kernel runs
+    const bool fuse_pool = (i < nb - 1) && m->down2[i].march == MARCH_2D_ROWS && m->down2[i].relu;
+    if ((rc = run_conv(m, "down" + std::to_string(i) + ".c2", m->down2[i], buf(i, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 2), 0, 0, 0, st,
+                       nullptr, fuse_pool ? buf(i + 1, 0) : nullptr))) return rc;
+    if (i < nb - 1 && !fuse_pool) {
       const int C = 32 << i;
       g_prof.mark("pool2x2", 0.0, st);
       const size_t total = (size_t)D * dims[i + 1].h * dims[i + 1].w * (C / 8);

@@ -94,6 +94,54 @@ def tomo_decode(heat, kernel=3, reg=None, K=900, if_fiber=False):
     return dets
 
 
+def non_maximum_suppression_3d(x, d, scale=1.0, threshold=float("-inf"), max_candidates=None):
+    """decode.py:42-79: greedy distance-threshold suppression of a (D,H,W) score volume.  Accepts a numpy
+    array or a tensor (moved to the current CUDA device); returns numpy `(scores[j], coords[j,3])` with
+    coords = (x, y, z) int32, like the reference.  The loop runs on the device (csrc/greedy_nms.cu)."""
+    import numpy as np
+    t = torch.as_tensor(x)
+    if t.dim() != 3:
+        raise ValueError(f"non_maximum_suppression_3d: expected a (D,H,W) volume, got {tuple(t.shape)}")
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise RuntimeError("non_maximum_suppression_3d: no CUDA device (there is no CPU fallback)")
+        t = t.cuda()
+    t = t.float().contiguous()
+    D, H, W = t.shape
+    n = D * H * W
+    L = _lib.lib()
+    thr = float(threshold)
+    cap = int(max_candidates) if max_candidates else int(min(n, max(1 << 20, int((t.double() > thr).sum().item()))))
+    nbytes = C.c_size_t(0)
+    _lib.check(L.cetpick_greedy_nms_workspace_bytes(D, H, W, cap, C.byref(nbytes)), "non_maximum_suppression_3d")
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=t.device)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    max_out = cap
+    scores = torch.empty(max_out, dtype=torch.float32, device=t.device)
+    coords = torch.empty((max_out, 3), dtype=torch.int32, device=t.device)
+    n_out, rounds = C.c_int64(0), C.c_int(0)
+    _lib.check(L.cetpick_greedy_nms_f32(t.data_ptr(), D, H, W, float(d), float(scale), thr, cap, scores.data_ptr(),
+                                        coords.data_ptr(), max_out, C.byref(n_out), C.byref(rounds), ws_ptr,
+                                        ws.numel() - (ws_ptr - ws.data_ptr()), _lib.stream_ptr()),
+               "non_maximum_suppression_3d")
+    j = min(n_out.value, max_out)
+    non_maximum_suppression_3d.last_rounds = rounds.value
+    return scores[:j].cpu().numpy(), coords[:j].cpu().numpy()
+
+
+def tomo_decode_classify(heat, r, threshold):
+    """decode.py:108-120: (C=1,D,H,W) heat -> (n,4) float32 CPU tensor rows [x, y, z, score] (the
+    reference builds it from numpy on the host; callers index it with numpy, tomo_det_classify.py:184-186)."""
+    heat = heat.unsqueeze(0)
+    if heat.dim() != 5:
+        raise ValueError(f"tomo_decode_classify: expected a (C,D,H,W) tensor, got {tuple(heat.shape[1:])}")
+    vol = heat.squeeze()
+    scores, coords = non_maximum_suppression_3d(vol, r, threshold=threshold)
+    scores = torch.from_numpy(scores).unsqueeze(1)
+    coords = torch.from_numpy(coords)
+    return torch.cat([coords, scores], dim=1)
+
+
 def decode_status(device=None):
     """(flags, n_candidates) of the last decode on the current stream (synchronises)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device

@@ -227,3 +227,21 @@ def unet_state_dict_torch(seed: int = 317, n_blocks: int = 4, heads=None, head_c
     import torch
     return OrderedDict((k, torch.from_numpy(np.array(v)) if v.ndim else torch.tensor(int(v)))
                        for k, v in unet_state_dict_np(seed, n_blocks, heads, head_conv).items())
+
+
+def fullres_stub_model():
+    """A detector stand-in for the semiclass tile path (detectors/tomo_det_classify.py): maps (B,D,H,W)
+    to [{'hm': (B,1,D,H,W)}] at the INPUT resolution with a one-voxel receptive field halo, using only
+    separately-rounded elementwise fp32 operations so CPU and CUDA results are bit-identical."""
+    import torch
+    import torch.nn.functional as F
+
+    class FullResStub(torch.nn.Module):
+        def forward(self, x):
+            xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+            y = x * 6.0 - 3.0
+            y = y + 0.5 * xp[:, :-2, 1:-1, 1:-1]
+            y = y + 0.25 * xp[:, 1:-1, 2:, 1:-1]
+            return [{"hm": y[:, None]}]
+
+    return FullResStub()

@@ -88,6 +88,20 @@ int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out16);
 int cetpick_nms_f32(const float* heat, float* out, int64_t B, int64_t D, int64_t H, int64_t W,
                     int kernel, int mode, void* stream);
 
+/* Greedy distance-threshold suppression = cet_pick/models/decode.py:42-79 `non_maximum_suppression_3d`
+ * (through `tomo_decode_classify`, decode.py:108-120; caller detectors/tomo_det_classify.py:112,146).
+ * heat: fp32 device (D,H,W).  Voxels with heat > threshold are visited in (score desc, index asc) order;
+ * a visited voxel not yet suppressed is a pick and suppresses the flat-index deltas of the ball of radius
+ * scale*d/2 (wrap-around across rows kept as in the reference).  scores: fp32 device [max_out];
+ * coords: int32 device [max_out][3] = (x, y, z); *n_out = number of picks (may exceed max_out: only the
+ * first max_out are written).  max_candidates bounds the voxels above threshold the workspace can hold
+ * (CETPICK_ERR_WORKSPACE if exceeded).  Synchronises the stream (the result length is data dependent). */
+int cetpick_greedy_nms_workspace_bytes(int64_t D, int64_t H, int64_t W, int64_t max_candidates, size_t* bytes);
+int cetpick_greedy_nms_f32(const float* heat, int64_t D, int64_t H, int64_t W, double d, double scale,
+                           double threshold, int64_t max_candidates, float* scores, int32_t* coords,
+                           int64_t max_out, int64_t* n_out, int* rounds_out, void* ws, size_t ws_bytes,
+                           void* stream);
+
 /* models/utils.py:167-169 `_sigmoid`: x <- clamp(sigmoid(x), 1e-4, 1-1e-4), in place. */
 int cetpick_sigmoid_clamp_f32(float* x, int64_t n, void* stream);
 
@@ -157,6 +171,12 @@ int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void* src1, int 
 int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
                             int NIMG, int H, int W, const float* w_host, int Cout,
                             const float* bias, int relu, void* out, void* stream);
+
+/* Same as cetpick_conv_march_bf16 (mode 0, relu != 0) with the fused MaxPool2d(2, ceil_mode=True) of
+ * cet_pick/models/networks/unet.py:225,237-238: pool_out = bf16 device [NIMG][(H+1)/2][(W+1)/2][Cout] or null. */
+int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
+                                 int NIMG, int H, int W, const float* w_host, int Cout,
+                                 const float* bias, int relu, void* out, void* pool_out, void* stream);
 
 /* Test hook: ConvTranspose2d(Cin,Cout,2,stride 2)+bias+ReLU through csrc/conv_up.cu.  src: bf16 device
  * [NIMG][h][w][Cin]; w_host: fp32 HOST weight in PyTorch layout (Cin,Cout,2,2); bias_host: fp32 HOST

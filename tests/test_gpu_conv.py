@@ -271,3 +271,32 @@ def test_stem_tensor_core_march(L, d, h, w):
     # and against the exact fp32 conv: operand rounding adds ~2^-9 relative per product
     ref32 = F.relu(F.conv2d(x[:, None], wt * scale.view(16, 1, 1, 1), shift, stride=2, padding=3)).permute(0, 2, 3, 1)
     assert (out.float() - ref32).abs().max().item() <= 3e-2
+
+
+# ---- MaxPool2d(2, ceil_mode=True) fused into the marching conv's epilogue (unet.py:225,237-238) ----
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (2, 12, 40, 16, 32),        # MT = 1 (one M-tile), even sizes
+    (1, 13, 21, 32, 32),        # odd H and W: ceil mode, last row / column pooled alone
+    (2, 38, 300, 32, 32),       # MT = 2, several strips, x block with a ragged tail
+    (2, 19, 35, 64, 64),        # Cout 64: row pairs alternate between the two epilogue groups
+    (1, 64, 257, 32, 64),
+    (1, 1, 7, 32, 32),          # a single row
+])
+def test_march_fused_maxpool(L, n, h, w, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(n + h + w + cin)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g) * 0.2
+    out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    hp, wp = (h + 1) // 2, (w + 1) // 2
+    pool = torch.full((n, hp, wp, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wh = wt.float().cpu().contiguous()
+    rc = L.lib().cetpick_conv_march_pool_bf16(0, 1, 1, x.data_ptr(), None, cin, n, h, w, wh.data_ptr(), cout,
+                                              b.data_ptr(), 1, out.data_ptr(), pool.data_ptr(), L.stream_ptr())
+    L.check(rc, "cetpick_conv_march_pool_bf16")
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2e-2
+    # the pooled tensor is EXACTLY the ceil-mode max-pool of the bf16 output the kernel wrote
+    pref = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, ceil_mode=True).permute(0, 2, 3, 1)
+    assert torch.equal(pool.float(), pref)
