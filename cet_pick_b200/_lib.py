@@ -7,7 +7,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcetpick_sm100a.so")
+LIB_PATH = os.environ.get("CETPICK_LIB") or os.path.join(_PKG, "libcetpick_sm100a.so")   # explicit override for A/B builds
 
 OK = 0
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_STATE, ERR_SHAPE = -1, -2, -3, -4, -5, -6

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           const float* brow = s_btab + cls * COUT;
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
           uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)z * p.H + y) * p.W + x) * COUT);
+          uint4 wprev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 8) {
             float f[8];
@@ -329,7 +330,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
             uint4 w;
             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
             w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-            if (valid && p.out) dst[c0 / 8] = w;
+            if (c0 & 8) { if (valid && p.out) ptx::st_global_256(dst + c0 / 8 - 1, wprev, w); }
+            else wprev = w;
             if (MODE == MARCH_2D_ROWS && pool) {
               // max with the even row of the pair (values are post-ReLU, so a missing pixel counts as 0)
               auto mx = [](uint32_t a, uint32_t b) {

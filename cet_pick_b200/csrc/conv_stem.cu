@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
             pk[i] = pack2(fmaxf(__uint_as_float(v[2 * i]) + p.bias_c[2 * i], 0.f),
                           fmaxf(__uint_as_float(v[2 * i + 1]) + p.bias_c[2 * i + 1], 0.f));
           uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)s.z * p.h + r) * p.w + x) * COUT);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          ptx::st_global_256(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
         }
       }
       q0 += (uint32_t)(s.mb - s.ma);

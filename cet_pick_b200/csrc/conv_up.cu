@@ -164,8 +164,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) conv_up_kernel(const __grid_con
             w0.z = pack_bf16x2(f[4], f[5]);   w0.w = pack_bf16x2(f[6], f[7]);
             w1.x = pack_bf16x2(f[8], f[9]);   w1.y = pack_bf16x2(f[10], f[11]);
             w1.z = pack_bf16x2(f[12], f[13]); w1.w = pack_bf16x2(f[14], f[15]);
-            dst[0] = w0;
-            dst[1] = w1;
+            ptx::st_global_256(dst, w0, w1);
           }
         }
       }

@@ -54,7 +54,11 @@ struct DecodeState {
   uint32_t n_final;        // number of candidates the final select saw
   uint32_t csel_done;     // candidate select resolved after the key digits (no ties at the K-th key)
   uint32_t n_real;        // COLLECT: voxels above the threshold (cand_count also counts chunk padding)
-  uint32_t pad[1];
+  uint32_t t_run;         // sieve: running strict threshold key (0 = not raised yet), only ever grows
+  uint32_t hit_total;     // sieve: voxels >= threshold queued so far (reported in batches)
+  uint32_t dense;         // sieve: hit density too high for the hit-by-hit path: bail out
+  uint32_t need_dense;    // set by the sieve's last CTA: scan_kernel COLLECT (gate 2) takes over with the same t0
+  uint32_t pad2;
 };
 
 struct alignas(64) ScanParams {
@@ -68,7 +72,7 @@ struct alignas(64) ScanParams {
   int shift, bits;     // HIST digit
   int last_pass;       // HIST: this pass resolves the last digit
   int ZC;              // planes per work item
-  int gate;            // 1: run only when state->need_fallback
+  int gate;            // 1: run only when state->need_fallback; 2: only when state->need_dense
   int phase;           // 0 = first COLLECT (may request fallback), 1 = fallback COLLECT
   int collect_all;     // COLLECT: append every voxel (small volumes)
   int vec_ok;          // rows are 16-byte aligned: use 16-byte cp.async
@@ -80,6 +84,7 @@ struct alignas(64) ScanParams {
   DecodeState* st;
   uint32_t* hist;      // HIST_BINS global bins
   uint32_t* eqcnt;     // D per-plane counts of o == t0
+  uint32_t* rhist;     // sieve: REFINE_BINS counts of appended candidates by distance of their key from t0
   unsigned long long* cand;
 };
 
@@ -324,7 +329,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
   __shared__ uint32_t s_ticket;
 
   DecodeState* st = p.st;
-  if (p.gate && st->need_fallback == 0) return;
+  if (p.gate == 1 && st->need_fallback == 0) return;
+  if (p.gate == 2 && st->need_dense == 0) return;
   int zlo = p.zlo, zhi = p.zhi;
   if (((MODE_T >= 0) ? MODE_T : p.mode) == MODE_EQ) {
     if (st->eq_need == 0) return;
@@ -681,14 +687,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       st->sel_kleft = s_sel[1];
       if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
       if (p.last_pass) {
+        // the K-th key's bin of the SAMPLE alone holds many times K survivors: the map is a few huge
+        // plateaus of tied values (a random-init detector), not peaks -- leave COLLECT to scan_kernel
+        if (p.gate == 0 && s_sel[2] > 8u * (uint32_t)p.K) st->need_dense = 1;
         st->t0key = np << p.shift;   // all 32 bits after three digits; the bin's lower edge after two
-        if (p.gate) {  // fallback select finished: restart the candidate list for COLLECT phase 1
+        if (p.gate == 1) {  // fallback select finished: restart the candidate list for COLLECT phase 1
           st->cand_count = 0;
         }
       }
       st->done_ctr = 0;
     }
-    if (p.last_pass && p.gate) {
+    if (p.last_pass && p.gate == 1) {
       for (int i = threadIdx.x; i < D; i += NT) p.eqcnt[i] = 0;
     }
   } else {  // MODE_COLLECT: plan the EQ pass
@@ -708,7 +717,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
 // Needs 16-byte aligned rows (p.vec_ok); other maps keep scan_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int SIEVE_THREADS = 256;
+constexpr uint32_t SIEVE_CHUNK = 16;   // candidate-list entries a warp reserves at a time (few candidates per warp)
 constexpr int SIEVE_QUEUE = 64;    // per-warp hit ring (entries); a push adds <= 32, a drain takes 32
+
+// Running threshold.  The sampled bound t0 admits ~64 K candidates; every candidate the sieve appends
+// is a true NMS survivor, so as soon as K of them have keys >= T the threshold may be raised to T
+// (still a lower bound of the K-th largest output).  Appended keys are counted in a global histogram
+// over delta = key - t0key with scale-free bins; a publisher CTA re-reads it every microsecond, publishes the lower edge of the bin where
+// the count from the top reaches K, and all warps pick the new value up a few iterations later.  Hits
+// (and the final candidate list) then shrink roughly like K ln(64) instead of 64 K.  Stale thresholds
+// are merely lower, i.e. still exact.
+constexpr int REFINE_BINS = 2048;
+// scale-free bins over delta = key - t0key: exact below 64, then 64 mantissa steps per octave (1.6 %)
+__device__ __forceinline__ uint32_t refine_bin(uint32_t delta) {
+  if (delta < 64u) return delta;
+  const int e = 31 - __clz(delta);                        // 6..31
+  return 64u + (uint32_t)(e - 6) * 64u + ((delta >> (e - 6)) & 0x3Fu);
+}
+__device__ __forceinline__ uint32_t refine_bin_lo(uint32_t b) {   // smallest delta that falls into bin b
+  if (b < 64u) return b;
+  const uint32_t e = 6u + ((b - 64u) >> 6), m = (b - 64u) & 0x3Fu;
+  return (1u << e) | (m << (e - 6u));
+}
 
 // NOT L1::no_allocate: those loads are looked up evict-first in L2, the streamed planes are gone
 // again before a hit asks for its neighbourhood and every neighbour read goes to DRAM (+30 % traffic,
@@ -726,7 +756,13 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* ptr) {
 }
 
 // NMS output key of voxel idx (the caller knows it is in the volume)
-__device__ __forceinline__ uint32_t sieve_okey(const float* __restrict__ heat, uint32_t idx, int D, int H, int W,
+// (not inlined: the stream loop of sieve_kernel must keep its registers; drains are rare)
+#ifdef SIEVE_INLINE
+#define SIEVE_NOINLINE __forceinline__
+#else
+#define SIEVE_NOINLINE __noinline__
+#endif
+__device__ SIEVE_NOINLINE uint32_t sieve_okey(const float* __restrict__ heat, uint32_t idx, int D, int H, int W,
                                                int P, int nms_mode, bool& is_nan) {
   const int hw = H * W;
   const int z = (int)(idx / (uint32_t)hw);
@@ -735,6 +771,19 @@ __device__ __forceinline__ uint32_t sieve_okey(const float* __restrict__ heat, u
   const float c = __ldg(heat + idx);
   is_nan = (c != c);
   if (nms_mode == CETPICK_NMS_NONE) return is_nan ? KEY_ZERO : f2key(c);
+  if (P == 1 && nms_mode == CETPICK_NMS_3D && z >= 1 && z + 1 < D && y >= 1 && y + 1 < H && x >= 1 && x + 1 < W) {
+    // interior voxel of the usual 3x3x3 window: 27 independent loads, one round trip (a drain stalls
+    // the warp's stream, so its latency matters more than the bytes it touches)
+    const float* c0 = heat + idx;
+    float m = c;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) m = fmaxf(m, __ldg(c0 + dz * hw + dy * W + dx));
+    return (c == m) ? f2key(c) : KEY_ZERO;
+  }
   const int ylo = max(y - P, 0), yhi = min(y + P, H - 1), xlo = max(x - P, 0), xhi = min(x + P, W - 1);
   auto mxy = [&](int zz) -> float {      // in-plane window maximum around (zz, y, x); NaN ignored (fmaxf)
     const float* pl = heat + (size_t)zz * hw;
@@ -764,13 +813,51 @@ __device__ __forceinline__ uint32_t sieve_okey(const float* __restrict__ heat, u
   return f2key(c);
 }
 
+// The publisher CTA (the last CTA of the grid; it streams nothing, so refreshing the threshold delays no
+// stream warp -- a stream warp that did this every few iterations became the kernel's 0.1 ms straggler)
+// recomputes the running threshold: stage the histogram, walk it from the top until K appended candidates
+// are covered, publish the lower edge of that bin.
+__device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K, uint32_t t0key, uint32_t* t_run) {
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < REFINE_BINS; i += SIEVE_THREADS) s_rh[i] = __ldcg(&rhist[i]);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    constexpr int PER = REFINE_BINS / 32;
+    uint32_t sum = 0;
+    for (int i = 0; i < PER; ++i) sum += s_rh[REFINE_BINS - 1 - lane * PER - i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - sum;
+    if ((excl < K) && (incl >= K)) {
+      uint32_t cum = excl;
+      int b = REFINE_BINS - 1 - lane * PER;
+      for (int i = 0; i < PER; ++i, --b) {
+        cum += s_rh[b];
+        if (cum >= K) break;
+      }
+      // >= K appended survivors have delta >= lo: key > t0key + lo - 1 keeps all of them
+      const uint32_t lo = refine_bin_lo((uint32_t)b);
+      if (lo > 0) atomicMax(t_run, t0key + lo - 1u);
+    }
+  }
+  __syncthreads();
+}
+
 template <int U, int CTAS, int LD>
 __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid_constant__ ScanParams p) {
   __shared__ uint32_t s_q[SIEVE_THREADS / 32][SIEVE_QUEUE];
+  __shared__ uint32_t s_rh[REFINE_BINS];
+  __shared__ volatile uint32_t s_trun, s_dense;
   __shared__ uint32_t s_ticket;
   DecodeState* st = p.st;
+  if (st->need_dense) return;                      // the sample pass already handed COLLECT to scan_kernel (gate 2)
   const uint32_t t0key = st->t0key;
-  const float t0f = key2f(t0key);
+  float t0f = key2f(t0key);                        // hit test: heat >= t0f (or NaN)
+  uint32_t t_take = t0key;                         // append test: key > t_take (raised by the running threshold)
   const bool all = (KEY_ZERO >= t0key);            // suppressed voxels (key of 0) matter: every voxel is a hit
   const int D = p.D, H = p.H, W = p.W, hw = H * W;
   const int P = (p.nms_mode == CETPICK_NMS_NONE) ? 0 : p.P;
@@ -778,8 +865,25 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   const float4* heat4 = reinterpret_cast<const float4*>(p.heat);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* q = s_q[warp];
+  if (threadIdx.x == 0) { s_trun = 0u; s_dense = 0u; }
+  __syncthreads();
+  const uint32_t nstream = gridDim.x - 1u;         // the last CTA is the publisher
+  if (blockIdx.x == nstream) {
+    // refresh the running threshold until every stream CTA has taken its ticket (or the pass was abandoned)
+    uint32_t done = 0;
+    while (done < nstream) {
+      if (!all) sieve_publish(p.rhist, s_rh, (uint32_t)p.K, t0key, &st->t_run);
+      __nanosleep(1000);
+      done = __ldcg(&st->done_ctr);
+      done = __shfl_sync(0xffffffffu, done, 0);    // warp-uniform ...
+      if (threadIdx.x == 0) s_ticket = done;
+      __syncthreads();
+      done = s_ticket;                             // ... and CTA-uniform (sieve_publish has CTA barriers)
+      __syncthreads();
+    }
+  } else {
   uint32_t q_head = 0, q_n = 0;                    // warp-uniform
-  uint32_t w_base = 0, w_used = CAND_CHUNK;        // this warp's chunk of the candidate list
+  uint32_t w_base = 0, w_used = SIEVE_CHUNK;        // this warp's chunk of the candidate list
   bool saw_nan = false;
 
   // one lane per queued hit: NMS test, then append (ok > t0) / count (ok == t0)
@@ -794,7 +898,7 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
     }
     q_head = (q_head + cnt) % SIEVE_QUEUE;
     q_n -= cnt;
-    const bool take = act && (ok > t0key);
+    const bool take = act && (ok > t_take);
     const bool eq = act && (ok == t0key);
     if (__any_sync(0xffffffffu, eq)) {
       const int z = eq ? (int)(idx / (uint32_t)hw) : -1 - lane;   // one atomic per distinct plane in the warp
@@ -804,11 +908,11 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
     const unsigned tb = __ballot_sync(0xffffffffu, take);
     if (tb) {
       const uint32_t tot = __popc(tb);
-      if (w_used + tot > CAND_CHUNK) {             // next chunk; pad the unused tail with composite 0
-        for (uint32_t k = w_used + lane; k < CAND_CHUNK; k += 32)
+      if (w_used + tot > SIEVE_CHUNK) {             // next chunk; pad the unused tail with composite 0
+        for (uint32_t k = w_used + lane; k < SIEVE_CHUNK; k += 32)
           if (w_base + k < p.cap_gt) p.cand[w_base + k] = 0ull;
         uint32_t nb = 0;
-        if (lane == 0) nb = atomicAdd(&st->cand_count, (uint32_t)CAND_CHUNK);
+        if (lane == 0) nb = atomicAdd(&st->cand_count, max((uint32_t)SIEVE_CHUNK, tot));   // a drain may exceed a chunk
         w_base = __shfl_sync(0xffffffffu, nb, 0);
         w_used = 0;
       }
@@ -816,11 +920,38 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
       w_used += tot;
       if (lane == 0) atomicAdd(&st->n_real, tot);
       if (take && off < p.cap_gt) p.cand[off] = ((unsigned long long)ok << 32) | (unsigned long long)(~idx);
+      if (!all) {                                  // one atomic per distinct bin of the drain (tied values share a bin)
+        const uint32_t bin = take ? refine_bin(ok - t0key) : (0x80000000u | (uint32_t)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (take && lane == __ffs(peers) - 1) atomicAdd(&p.rhist[bin], (uint32_t)__popc(peers));
+      }
     }
   };
 
-  const uint32_t stride = gridDim.x * (uint32_t)(SIEVE_THREADS * U);
-  for (uint32_t base = blockIdx.x * (uint32_t)(SIEVE_THREADS * U); base < n4; base += stride) {
+  const uint32_t stride = nstream * (uint32_t)(SIEVE_THREADS * U);
+  // Density watchdog: the hit-by-hit path is for RARE hits.  On a map where a few per cent of all voxels
+  // reach the threshold (smooth, nearly flat maps: a random-init detector) it is slower than the tiled
+  // stencil of scan_kernel, so warps report their hit counts, and once hits exceed 1/32 of the voxels
+  // streamed so far (plus slack) the pass is abandoned and scan_kernel redoes COLLECT with the same bound.
+  uint32_t iter = 0, tr_new = 0, dn_new = 0, w_hits = 0;
+  for (uint32_t base = blockIdx.x * (uint32_t)(SIEVE_THREADS * U); base < n4; base += stride, ++iter) {
+    // running threshold: warp 0 fetched it one iteration ago (one L2 request per CTA, not per warp: 4736
+    // warps polling one line was a measured 15 % stall) and relays it through shared memory
+    if (warp == 0 && tr_new > s_trun) s_trun = tr_new;
+#ifndef SIEVE_NO_WATCHDOG
+    if (warp == 0 && dn_new) s_dense = 1u;
+    if (s_dense) break;
+#endif
+    {
+      const uint32_t tr = s_trun;
+      if (tr > t_take) { t_take = tr; t0f = key2f(tr + 1u); }
+    }
+    if (!all) {
+      if (warp == 0) {   // consumed at the top of the next iteration (latency overlapped)
+        tr_new = __ldcg(&st->t_run);
+        dn_new = __ldcg(&st->dense);
+      }
+    }
     float4 v[U];
     uint32_t valid = 0;
 #pragma unroll
@@ -864,14 +995,26 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
         q[(q_head + q_n + __popc(hb & ((1u << lane) - 1u))) % SIEVE_QUEUE] = i4 * 4u + (uint32_t)(b & 3);
       }
       q_n += __popc(hb);
+      w_hits += __popc(hb);
       __syncwarp();
       if (q_n >= 32) drain(32);
     }
+#ifndef SIEVE_NO_WATCHDOG
+    if (w_hits >= 256u) {       // warp-uniform
+      if (lane == 0) {
+        const uint32_t tot = atomicAdd(&st->hit_total, w_hits) + w_hits;
+        const unsigned long long streamed = (unsigned long long)(iter + 1u) * stride * 4ull;   // all CTAs advance together
+        if ((unsigned long long)tot > 65536ull + streamed / 32ull) atomicExch(&st->dense, 1u);
+      }
+      w_hits = 0;
+    }
+#endif
   }
   if (q_n) drain(q_n);
-  for (uint32_t k = w_used + lane; k < CAND_CHUNK; k += 32)   // pad the tail of the warp's last chunk
+  for (uint32_t k = w_used + lane; k < SIEVE_CHUNK; k += 32)   // pad the tail of the warp's last chunk
     if (w_base + k < p.cap_gt) p.cand[w_base + k] = 0ull;
   if (saw_nan) atomicOr(&st->flags, (uint32_t)FLAG_NAN);
+  }   // stream CTAs
 
   __threadfence();
   __syncthreads();
@@ -879,7 +1022,12 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
-  if (threadIdx.x == 0) collect_plan(p, st);
+  if (__ldcg(&st->dense)) {     // abandoned: hand COLLECT to scan_kernel (gate 2) from a clean slate
+    for (int i = threadIdx.x; i < D; i += SIEVE_THREADS) p.eqcnt[i] = 0;
+    if (threadIdx.x == 0) { st->cand_count = 0; st->n_real = 0; st->need_dense = 1; st->done_ctr = 0; }
+  } else if (threadIdx.x == 0) {
+    collect_plan(p, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1045,7 +1193,7 @@ __global__ void __launch_bounds__(1024) sort_write_kernel(
 }
 
 __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqcnt, int D,
-                                  uint32_t t0key, uint32_t* ranks, int n_ranks) {
+                                  uint32_t t0key, uint32_t* ranks, int n_ranks, uint32_t* rhist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     DecodeState z = {};
@@ -1056,6 +1204,7 @@ __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqc
   if (i < HIST_BINS) hist[i] = 0;
   for (int k = i; k < D; k += gridDim.x * blockDim.x) eqcnt[k] = 0;
   for (int k = i; k < n_ranks; k += gridDim.x * blockDim.x) ranks[k] = 0;
+  for (int k = i; k < REFINE_BINS; k += gridDim.x * blockDim.x) rhist[k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1100,7 +1249,7 @@ __global__ void sigmoid_clamp_kernel(float* __restrict__ x, size_t n) {
 }
 
 struct WsLayout {
-  size_t off_state, off_hist, off_eq, off_cand, off_out, off_rank, total;
+  size_t off_state, off_hist, off_eq, off_rhist, off_cand, off_out, off_rank, total;
   uint32_t cap_gt, cap_total;
   int npad;
 };
@@ -1119,6 +1268,7 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   L.off_state = o; o = align_up(o + sizeof(DecodeState), 256);
   L.off_hist = o;  o = align_up(o + HIST_BINS * sizeof(uint32_t), 256);
   L.off_eq = o;    o = align_up(o + (size_t)D * sizeof(uint32_t), 256);
+  L.off_rhist = o; o = align_up(o + (size_t)REFINE_BINS * sizeof(uint32_t), 256);
   L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
   L.off_out = o;   o = align_up(o + (size_t)npad * 8, 256);
   L.off_rank = o;  o = align_up(o + (size_t)std::min<int64_t>(K, RANK_MAX_K) * 4, 256);
@@ -1200,12 +1350,13 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
 
   uint32_t* ranks = reinterpret_cast<uint32_t*>(base + L.off_rank);
   const int n_ranks = std::min(K, RANK_MAX_K);
-  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, ranks, n_ranks);
+  uint32_t* rhist = reinterpret_cast<uint32_t*>(base + L.off_rhist);
+  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, ranks, n_ranks, rhist);
   CETPICK_LAUNCH_CHECK();
 
   ScanParams p = {};
   p.heat = heat; p.D = D; p.H = H; p.W = W;
-  p.nms_mode = nms_mode; p.P = P; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand;
+  p.nms_mode = nms_mode; p.P = P; p.K = K; p.st = st; p.hist = hist; p.eqcnt = eqcnt; p.cand = cand; p.rhist = rhist;
   p.cap_gt = L.cap_gt; p.cap_total = L.cap_total;
   p.vec_ok = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
   p.use_tma = 0;
@@ -1237,21 +1388,14 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     q.mode = MODE_COLLECT; q.zlo = 0; q.zhi = D; q.gate = gate; q.phase = phase; q.collect_all = all;
     if (p.vec_ok && !gate && !all) {   // the usual pass: threshold-first stream (sieve_kernel)
       const uint32_t n4 = (uint32_t)(n >> 2);
-      static const int variant = getenv("CETPICK_SIEVE_VARIANT") ? atoi(getenv("CETPICK_SIEVE_VARIANT")) : 0;
-      auto go = [&](auto kern, int U, int ctas) -> int {
-        const int grid = (int)std::min<uint32_t>((uint32_t)(num_sms() * ctas), ceil_div<uint32_t>(n4, SIEVE_THREADS * U));
-        CETPICK_CUDA(launch_k(kern, dim3(grid), dim3(SIEVE_THREADS), 0, s, q));
-        CETPICK_LAUNCH_CHECK();
-        return CETPICK_OK;
-      };
-      switch (variant) {
-        case 1: return go(sieve_kernel<8, 4, 1>, 8, 4);
-        case 2: return go(sieve_kernel<8, 3, 1>, 8, 3);
-        case 3: return go(sieve_kernel<4, 6, 1>, 4, 6);
-        case 4: return go(sieve_kernel<8, 4, 0>, 8, 4);
-        case 5: return go(sieve_kernel<2, 8, 1>, 2, 8);
-        default: return go(sieve_kernel<4, 4, 1>, 4, 4);
-      }
+      // U = 8 loads of 16 bytes in flight per thread, 4 CTAs of 256 threads per SM: the best of the
+      // measured variants (profiles/r1i, r1n); the pure stream of this shape runs at 6.2 TB/s
+      constexpr int U = 8, CTAS = 4;
+      // stream CTAs + 1 publisher CTA, all resident at once (the publisher polls the others' tickets)
+      const int grid = 1 + (int)std::min<uint32_t>((uint32_t)(num_sms() * CTAS - 1), ceil_div<uint32_t>(n4, SIEVE_THREADS * U));
+      CETPICK_CUDA(launch_k(sieve_kernel<U, CTAS, 1>, dim3(grid), dim3(SIEVE_THREADS), 0, s, q));
+      CETPICK_LAUNCH_CHECK();
+      return CETPICK_OK;
     }
     const int grid = scan_grid(D, H, W, 0, D, &q.ZC);
     return launch_scan_p(P, q, grid, s);
@@ -1261,14 +1405,16 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   if (collect_all) {
     if ((rc = run_collect(0, 1, 1))) return rc;
   } else {
-    // sample: a centred z-range holding >= max(4K, N/64) voxels (>= K is what exactness needs)
+    // sample: a centred z-range holding >= max(4K, N/256) voxels (>= K is what exactness needs)
     const uint64_t hw = (uint64_t)H * W;
-    uint64_t want = std::max<uint64_t>(4ull * (uint64_t)K, n / 64);
+    // (the running threshold of the sieve makes a tight first bound unnecessary: 1/256 of the volume)
+    uint64_t want = std::max<uint64_t>(4ull * (uint64_t)K, n / 256);
     int sp = (int)std::min<uint64_t>((uint64_t)D, ceil_div<uint64_t>(want, hw));
     sp = std::max(sp, 1);
     const int zlo = (D - sp) / 2, zhi = zlo + sp;
     if ((rc = run_select(zlo, zhi, 0, 2))) return rc;
     if ((rc = run_collect(0, 0, 0))) return rc;
+    if (p.vec_ok && (rc = run_collect(2, 0, 0))) return rc;   // taken only if the sieve found the hits dense
     // exact fallback (device-gated): full-volume select, then COLLECT again
     if ((rc = run_select(0, D, 1, 3))) return rc;
     if ((rc = run_collect(1, 1, 0))) return rc;

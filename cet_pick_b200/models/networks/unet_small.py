@@ -88,6 +88,12 @@ class TomoConvUNet(nn.Module):
             fc = nn.Conv3d(head_conv, classes, kernel_size=(3, 1, 1), padding=(1, 0, 0), bias=False)
             nn.init.normal_(fc.weight, std=0.001)
             setattr(self, head, fc)
+        # z-slab streaming (north_star "sliding-slab scheduler"; the reference forwards the whole volume,
+        # tomo_det.py:26): None = whole volume, int = core slices per slab, "auto" = largest slab whose
+        # workspace fits in free device memory.  The 2-D trunk is per-slice and the 3-D head reaches
+        # +-3 slices (feature_head.0, feature_head.2, hm/proj: one slice each), so every slab is
+        # forwarded with a 3-slice recompute halo and only its core slices are kept: exact.
+        self.slab_z = None
         self.compute_proj = "proj" in heads      # detectors switch this off (they never read 'proj')
         self.fuse_sigmoid = False                # TomodetDetector fuses _sigmoid into the hm epilogue
         self._plan = None
@@ -131,6 +137,28 @@ class TomoConvUNet(nn.Module):
         return h
 
     # ------------------------------------------------------------------ forward
+    HEAD_HALO = 3
+
+    def _slab_depth(self, plan, d, h, w, device):
+        """core slices per slab (>= 1), or d when the whole volume is forwarded at once"""
+        if self.slab_z is None:
+            return d
+        if self.slab_z != "auto":
+            return max(1, min(int(self.slab_z), d))
+        L = _lib.lib()
+        free, _ = torch.cuda.mem_get_info(device)
+        budget = int(0.8 * free) + (self._ws.numel() if self._ws is not None and self._ws.device == device else 0)
+        nb = C.c_size_t(0)
+        _lib.check(L.cetpick_unet_workspace_bytes(plan, d, h, w, 0, C.byref(nb)), "unet_workspace_bytes")
+        if nb.value <= budget:
+            return d
+        _lib.check(L.cetpick_unet_workspace_bytes(plan, 1, h, w, 0, C.byref(nb)), "unet_workspace_bytes")
+        per_slice = max(1, nb.value)                       # the workspace is linear in the slab depth
+        depth = budget // per_slice - 2 * self.HEAD_HALO
+        if depth < 1:
+            raise RuntimeError("TomoConvUNet: not enough device memory for a one-slice slab")
+        return int(min(depth, d))
+
     def forward(self, x):
         _lib.require_cuda(x, "TomoConvUNet.forward")
         if x.dim() > 4:
@@ -142,8 +170,11 @@ class TomoConvUNet(nn.Module):
         plan = self.plan()
         L = _lib.lib()
         oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        slab = self._slab_depth(plan, d, h, w, x.device)
+        halo = self.HEAD_HALO if slab < d else 0
+        dmax = min(d, slab + 2 * halo)
         nbytes = C.c_size_t(0)
-        _lib.check(L.cetpick_unet_workspace_bytes(plan, d, h, w, 0, C.byref(nbytes)), "unet_workspace_bytes")
+        _lib.check(L.cetpick_unet_workspace_bytes(plan, dmax, h, w, 0, C.byref(nbytes)), "unet_workspace_bytes")
         if self._ws is None or self._ws.numel() < nbytes.value or self._ws.device != x.device:
             self._ws = None
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
@@ -152,13 +183,32 @@ class TomoConvUNet(nn.Module):
         proj = torch.empty((b, pc, d, oh, ow), dtype=torch.float32, device=x.device) \
             if (self.compute_proj and pc > 0) else None
         self.last_launches = 0
-        for i in range(b):
-            _lib.check(L.cetpick_unet_forward(plan, x[i].data_ptr(), d, h, w, hm[i].data_ptr(),
-                                              1 if self.fuse_sigmoid else 0,
-                                              proj[i].data_ptr() if proj is not None else None,
+        self.last_slabs = 0
+        sig = 1 if self.fuse_sigmoid else 0
+
+        def run(src, depth, hm_dst, proj_dst):
+            _lib.check(L.cetpick_unet_forward(plan, src.data_ptr(), depth, h, w, hm_dst.data_ptr(), sig,
+                                              proj_dst.data_ptr() if proj_dst is not None else None,
                                               self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
                        "cetpick_unet_forward")
             self.last_launches += L.cetpick_last_launch_count()
+            self.last_slabs += 1
+
+        for i in range(b):
+            if slab >= d:
+                run(x[i], d, hm[i], proj[i] if proj is not None else None)
+                continue
+            hm_s = torch.empty((dmax, oh, ow), dtype=torch.float32, device=x.device)
+            pj_s = torch.empty((pc, dmax, oh, ow), dtype=torch.float32, device=x.device) if proj is not None else None
+            for z0 in range(0, d, slab):
+                z1 = min(d, z0 + slab)
+                lo, hi = max(0, z0 - halo), min(d, z1 + halo)
+                # (pc, depth, oh, ow) output of a slab is contiguous only for the slab's own depth
+                pj_v = pj_s.view(-1)[:pc * (hi - lo) * oh * ow].view(pc, hi - lo, oh, ow) if pj_s is not None else None
+                run(x[i, lo:hi], hi - lo, hm_s, pj_v)
+                hm[i, 0, z0:z1].copy_(hm_s[z0 - lo:z0 - lo + (z1 - z0)])
+                if pj_v is not None:
+                    proj[i, :, z0:z1].copy_(pj_v[:, z0 - lo:z0 - lo + (z1 - z0)])
         ret = {"hm": hm}
         if proj is not None:
             ret["proj"] = proj

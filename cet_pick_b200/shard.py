@@ -8,6 +8,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+HEAD_HALO = 3      # z reach of the 3-D head (feature_head.0, feature_head.2, hm: one slice each, unet_small.py:39-61)
+
 
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous share [first, first + count) of `n_items` for `rank`; the first n % world ranks get one more."""
@@ -37,3 +39,53 @@ def gather_picks(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
         _, cnt = shard_range(n_items, r, world)
         parts.append(out[r * max_count:r * max_count + cnt])
     return torch.cat(parts, 0)
+
+
+def slab_range(depth: int, rank: int, world: int, halo: int = HEAD_HALO):
+    """z-slab of ONE oversized volume for `rank`: core slices [z0, z1) it owns and the slices [lo, hi) it has
+    to forward (core + recompute halo, clipped at the true volume boundary where zero padding is exact)."""
+    z0, cnt = shard_range(depth, rank, world)
+    z1 = z0 + cnt
+    return z0, z1, max(0, z0 - halo), min(depth, z1 + halo)
+
+
+def forward_z_sharded(forward_fn, volume_slab_fn, depth: int, group=None, halo: int = HEAD_HALO):
+    """Heat-map of one volume whose z-slabs are spread over the ranks (the 2-D trunk is
+    per-slice, the head needs +-3 slices, so each rank recomputes a 3-slice halo instead of exchanging features).
+
+    volume_slab_fn(lo, hi) -> this rank's input slices (hi-lo, H, W) (only those are ever loaded);
+    forward_fn(slab)       -> heat-map slices (hi-lo, h, w) of that slab.
+    Every rank returns the full (depth, h, w) heat-map: ONE all_gather of the core slabs (padded to the
+    largest share), after which decode runs on identical data everywhere (picks bit-identical to 1 GPU)."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    z0, z1, lo, hi = slab_range(depth, rank, world, halo)
+    if z1 > z0:
+        hm_slab = forward_fn(volume_slab_fn(lo, hi))
+        core = hm_slab[z0 - lo:z0 - lo + (z1 - z0)].contiguous()
+    else:
+        core = None
+    if world == 1:
+        return core
+    # shapes: every rank needs (h, w); ranks without slices learn them from the gathered meta
+    meta = torch.tensor([core.shape[1], core.shape[2]] if core is not None else [0, 0], dtype=torch.int64,
+                        device=core.device if core is not None else _default_device(group))
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    h, w = (int(v) for v in max((m for m in metas), key=lambda m: int(m[0])).tolist())
+    max_cnt = -(-depth // world)
+    dev = meta.device
+    buf = torch.zeros((max_cnt, h, w), dtype=torch.float32, device=dev)
+    if core is not None:
+        buf[:z1 - z0] = core
+    out = torch.empty((world * max_cnt, h, w), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    parts = []
+    for r in range(world):
+        _, cnt = shard_range(depth, r, world)
+        parts.append(out[r * max_cnt:r * max_cnt + cnt])
+    return torch.cat(parts, 0)
+
+
+def _default_device(group=None):
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")

@@ -252,3 +252,18 @@ def test_large_vs_torch_cuda_reference(dec):
     assert torch.equal(out[0, :, 2], z[0].float())
     assert torch.equal(out[0, :, 1], torch.floor(t.float() / W)[0] + 0.25)
     assert torch.equal(out[0, :, 0], (t % W)[0].float() + 0.25)
+
+
+def test_sieve_dense_hits_hand_over_to_scan(dec, do):
+    """a smooth, nearly flat map (what a random-init detector emits): a few per cent of all voxels reach the
+    sampled bound, the sieve's density watchdog abandons the hit-by-hit pass and scan_kernel redoes COLLECT."""
+    D, H, W = 48, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((1, 1, D, H, W), device="cuda", generator=g)
+    hm = torch.nn.functional.avg_pool3d(x, 7, 1, 3)
+    hm = torch.sigmoid(0.05 * hm).contiguous()
+    out = dec.tomo_decode(hm, kernel=3, K=900).cpu().numpy()
+    st = dec.decode_debug_state()
+    assert np.array_equal(bits(out), bits(do.tomo_decode(hm.cpu().numpy(), 3, None, 900)))
+    flags, _ = dec.decode_status()
+    assert flags == 0

@@ -56,3 +56,63 @@ def test_gather_picks_world2_gloo(n_items):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+# ---- z-slab sharding of ONE oversized volume (shard.forward_z_sharded): recompute halo + one all_gather ----
+def _fake_forward(slab):
+    """a stand-in with the detector's z reach: per-slice 2x down-sampling + a +-3-slice zero-padded z filter"""
+    x = slab[:, ::2, ::2]
+    k = torch.tensor([1.0, -2.0, 3.0, 5.0, 0.5, -1.5, 2.5])
+    xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 3, 3))
+    return sum(k[i] * xp[i:i + x.shape[0]] for i in range(7))
+
+
+def test_slab_range_covers_depth_with_halo():
+    from cet_pick_b200.shard import slab_range
+    for depth in (1, 5, 16, 17):
+        for world in (1, 2, 3, 8):
+            cores = []
+            for r in range(world):
+                z0, z1, lo, hi = slab_range(depth, r, world)
+                cores += list(range(z0, z1))
+                assert lo == max(0, z0 - 3) and hi == min(depth, z1 + 3)
+            assert cores == list(range(depth))
+
+
+def _zworker(rank, world, port, depth, q):
+    from cet_pick_b200.shard import forward_z_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vol = torch.rand((depth, 12, 10), generator=torch.Generator().manual_seed(5))
+        loaded = []
+
+        def slab_fn(lo, hi):
+            loaded.append((lo, hi))
+            return vol[lo:hi]
+
+        hm = forward_z_sharded(_fake_forward, slab_fn, depth)
+        ok = torch.allclose(hm, _fake_forward(vol), atol=1e-6) and hm.shape[0] == depth
+        # each rank touched only its slab plus the 3-slice halo
+        ok = ok and len(loaded) <= 1 and all(hi - lo <= -(-depth // world) + 6 for lo, hi in loaded)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("depth", [16, 9, 1])
+def test_forward_z_sharded_world2_gloo(depth):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_zworker, args=(r, 2, port, depth, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
