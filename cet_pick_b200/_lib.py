@@ -30,6 +30,13 @@ SIGNATURES = {
     "cetpick_greedy_nms_workspace_bytes": (_int, [_i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_greedy_nms_f32": (_int, [_vp, _i64, _i64, _i64, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp, _i64,
                                       C.POINTER(_i64), C.POINTER(_int), _vp, _sz, _vp]),
+    "cetpick_pre_gather_f64": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp, _vp]),
+    "cetpick_pre_stats_workspace_bytes": (_int, [C.POINTER(_sz)]),
+    "cetpick_pre_mean_std_f64": (_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "cetpick_pre_zscore_f64": (_int, [_vp, _i64, _vp, _vp]),
+    "cetpick_pre_gauss1d_f64": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _int, _vp]),
+    "cetpick_pre_quantize_u8": (_int, [_vp, _i64, C.c_double, C.c_double, _vp, _vp]),
+    "cetpick_pre_minmax_normalize": (_int, [_vp, _i64, _vp, _vp, _int, _vp]),
     "cetpick_sigmoid_clamp_f32": (_int, [_vp, _i64, _vp]),
     "cetpick_unet_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
     "cetpick_unet_destroy": (None, [_vp]),

@@ -28,12 +28,17 @@ def write_mrc(path, data: np.ndarray):
         f.write(data.tobytes())
 
 
+_MODES = {0: "i1", 1: "<i2", 2: "<f4", 6: "<u2"}
+
+
 def read_mrc(path) -> np.ndarray:
+    """(nz, ny, nx) array of an MRC file, like `mrcfile.open(path).data` (modes 0, 1, 2, 6)."""
     with open(path, "rb") as f:
         hdr = f.read(1024)
         nx, ny, nz, mode = struct.unpack_from("<4i", hdr, 0)
         nsymbt = struct.unpack_from("<i", hdr, 92)[0]
-        if mode != 2:
-            raise ValueError("only mode-2 (float32) MRC files are supported")
+        if mode not in _MODES:
+            raise ValueError(f"MRC mode {mode} is not supported (0, 1, 2, 6 are)")
+        dt = np.dtype(_MODES[mode])
         f.seek(1024 + nsymbt)
-        return np.frombuffer(f.read(nx * ny * nz * 4), dtype="<f4").reshape(nz, ny, nx)
+        return np.frombuffer(f.read(nx * ny * nz * dt.itemsize), dtype=dt).reshape(nz, ny, nx)

@@ -102,6 +102,30 @@ int cetpick_greedy_nms_f32(const float* heat, int64_t D, int64_t H, int64_t W, d
                            int64_t max_out, int64_t* n_out, int* rounds_out, void* ws, size_t ws_bytes,
                            void* stream);
 
+/* ---- pre-processing in front of the path: cet_pick/utils/loader.py:16-25 (quantize), :27-88
+ * (load_rec), :90-121 (preprocess), all float64 like the reference ------------------------------------------------ */
+
+/* load_rec's slice loop (loader.py:44-58,70-84): out[j][a][b] = src[a*sa + b*sb + z*sz] with z = j, or the max over
+ * z in {2j, 2j+1} (z < Z) when pair_max (`--compress`).  src_dtype: 0 float32, 1 int16, 2 uint16, 3 int8, 4 float64
+ * (MRC modes 2/1/6/0); strides in ELEMENTS (the caller folds the `order` axis swaps of loader.py:32-36 into them). */
+int cetpick_pre_gather_f64(const void* src, int src_dtype, int64_t A, int64_t B, int64_t J, int64_t sa,
+                           int64_t sb, int64_t sz, int64_t Z, int pair_max, double* out, void* stream);
+/* stats[0] = mean, stats[1] = population std (np.mean / np.std, loader.py:59-60,85-86,104,118); two-stage fixed-grid
+ * reduction (reproducible); ws >= cetpick_pre_stats_workspace_bytes. */
+int cetpick_pre_stats_workspace_bytes(size_t* bytes);
+int cetpick_pre_mean_std_f64(const double* x, int64_t n, double* stats, void* ws, size_t ws_bytes, void* stream);
+/* x = (x - stats[0]) / stats[1] in place. */
+int cetpick_pre_zscore_f64(double* x, int64_t n, const double* stats, void* stream);
+/* One axis of scipy.ndimage.gaussian_filter(mode='reflect') (loader.py:103) on a C-contiguous (n0,n1,n2) volume;
+ * weights_host = the 2*radius+1 taps of scipy's _gaussian_kernel1d (HOST); in != out. */
+int cetpick_pre_gauss1d_f64(const double* in, double* out, int64_t n0, int64_t n1, int64_t n2, int axis,
+                            const double* weights_host, int radius, void* stream);
+/* quantize (loader.py:16-25): q = uint8(round_half_even(clip(255*(x - mi)/(ma - mi), 0, 255))). */
+int cetpick_pre_quantize_u8(const double* x, int64_t n, double mi, double ma, unsigned char* q, void* stream);
+/* (q - min q) / (max q - min q) (loader.py:106,120) as float64 (out_f64 = 1) or float32; minmax = device int[2]. */
+int cetpick_pre_minmax_normalize(const unsigned char* q, int64_t n, int* minmax, void* out, int out_f64,
+                                 void* stream);
+
 /* models/utils.py:167-169 `_sigmoid`: x <- clamp(sigmoid(x), 1e-4, 1-1e-4), in place. */
 int cetpick_sigmoid_clamp_f32(float* x, int64_t n, void* stream);
 
