@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
           if (lane == 0) ptx::mbar_arrive(&bar_tempty[acc]);
         }
         if (valid) {
+          uint4 wprev = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             float f[8];
@@ -216,7 +217,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(const __grid
             uint4 w;
             w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]);
             w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-            reinterpret_cast<uint4*>(dst + c0)[g] = w;
+            if (g & 1) ptx::st_global_256(reinterpret_cast<uint4*>(dst + c0) + g - 1, wprev, w);   // one full sector per store
+            else wprev = w;
           }
         }
       }

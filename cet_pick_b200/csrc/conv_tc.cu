@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           w1.x = pack_bf16x2(f[8], f[9]);   w1.y = pack_bf16x2(f[10], f[11]);
           w1.z = pack_bf16x2(f[12], f[13]); w1.w = pack_bf16x2(f[14], f[15]);
           if (store) {
-            reinterpret_cast<uint4*>(dst)[0] = w0;
-            reinterpret_cast<uint4*>(dst)[1] = w1;
+            if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) ptx::st_global_256(dst, w0, w1);   // one full sector
+            else { reinterpret_cast<uint4*>(dst)[0] = w0; reinterpret_cast<uint4*>(dst)[1] = w1; }
           }
         } else if (p.epi == EPI_F32_ROWMAJOR) {
           float* dst = reinterpret_cast<float*>(p.out) +
