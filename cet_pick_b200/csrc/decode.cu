@@ -79,6 +79,7 @@ struct alignas(64) ScanParams {
   int use_tma;         // rows are 16-byte aligned: TMA ring (host-side choice)
   int K;
   uint32_t k_select;   // HIST pass 0: rank to select
+  uint32_t sample_ratio;   // HIST on the sample: volume voxels / sample voxels
   uint32_t cap_gt;     // capacity reserved for COLLECT entries
   uint32_t cap_total;
   DecodeState* st;
@@ -689,7 +690,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
       if (p.last_pass) {
         // the K-th key's bin of the SAMPLE alone holds many times K survivors: the map is a few huge
         // plateaus of tied values (a random-init detector), not peaks -- leave COLLECT to scan_kernel
-        if (p.gate == 0 && s_sel[2] > 8u * (uint32_t)p.K) st->need_dense = 1;
+        if (p.gate == 0 && s_sel[2] > 8u * (uint32_t)p.K) {
+          // ... and if the whole volume would overflow the candidate list anyway, go straight to the exact select
+          if ((unsigned long long)s_sel[2] * (unsigned long long)p.sample_ratio > (unsigned long long)p.cap_gt) {
+            st->need_fallback = 1; st->flags |= FLAG_FALLBACK;
+          } else {
+            st->need_dense = 1;
+          }
+        }
         st->t0key = np << p.shift;   // all 32 bits after three digits; the bin's lower edge after two
         if (p.gate == 1) {  // fallback select finished: restart the candidate list for COLLECT phase 1
           st->cand_count = 0;
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   __shared__ volatile uint32_t s_trun, s_dense;
   __shared__ uint32_t s_ticket;
   DecodeState* st = p.st;
-  if (st->need_dense) return;                      // the sample pass already handed COLLECT to scan_kernel (gate 2)
+  if (st->need_dense || st->need_fallback) return;   // the sample pass already handed COLLECT to scan_kernel
   const uint32_t t0key = st->t0key;
   float t0f = key2f(t0key);                        // hit test: heat >= t0f (or NaN)
   uint32_t t_take = t0key;                         // append test: key > t_take (raised by the running threshold)
@@ -1412,6 +1420,7 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     int sp = (int)std::min<uint64_t>((uint64_t)D, ceil_div<uint64_t>(want, hw));
     sp = std::max(sp, 1);
     const int zlo = (D - sp) / 2, zhi = zlo + sp;
+    p.sample_ratio = (uint32_t)std::max<uint64_t>(1, n / ((uint64_t)sp * hw));
     if ((rc = run_select(zlo, zhi, 0, 2))) return rc;
     if ((rc = run_collect(0, 0, 0))) return rc;
     if (p.vec_ok && (rc = run_collect(2, 0, 0))) return rc;   // taken only if the sieve found the hits dense

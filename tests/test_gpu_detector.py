@@ -79,3 +79,44 @@ def test_run_end_to_end_from_checkpoint(tmp_path, monkeypatch):
         j = int(np.argmin(d))
         assert d[j] <= 2, (r, got[j])                                  # 1 voxel at half resolution = 2 input pixels
         assert abs(got[j, 3] - r[3]) <= tol
+
+
+def test_pipeline_mrc_to_pick_file(tmp_path, monkeypatch):
+    """The refinement-step pipeline of test.py with every arithmetic stage on the device: an int16 MRC
+    reconstruction -> load_tomos_from_list (order xzy, --compress, --gauss 0.8; csrc/preproc.cu) -> detector.run
+    (forward + decode) -> `<name>.txt`.  The pre-processed volume equals the oracle's 256-level volume, and the
+    heat-map written next to the picks is within the BF16 tolerance of the fp32 oracle forward on it."""
+    from cet_pick_b200 import synth
+    from cet_pick_b200.detectors.detector_factory import detector_factory
+    from cet_pick_b200.opts import opts
+    from cet_pick_b200.utils import loader, mrcio
+    from oracle import preproc_oracle as po
+    from oracle import unet_oracle as uo
+    sd = synth.unet_state_dict_torch(317, 4)
+    ckpt = os.path.join(tmp_path, "model.pth")
+    torch.save({"epoch": 1, "state_dict": sd}, ckpt)
+    monkeypatch.chdir(tmp_path)
+    # stored MRC array (nz', ny, nx) = (x, z, y) for order 'xzy': 64 x-columns, 24 z-slices, 96 y-rows
+    raw = (synth.tomogram_np(64, 24, 96, 11) * 900 - 300).astype(np.int16)
+    path = os.path.join(tmp_path, "tomoC.mrc")
+    hdr_src = raw.astype(np.float32)
+    mrcio.write_mrc(path, hdr_src)                     # float32 file with integer-valued voxels
+    opt = opts().init(["semi", "--arch", "unet_4", "--load_model", ckpt, "--K", "40", "--out_thresh", "0.0",
+                       "--cutoff_z", "0", "--with_score", "--compress", "--gauss", "0.8", "--out_id", "out",
+                       "--exp_id", "pipe", "--gpus", "0"])
+    os.makedirs(opt.save_dir, exist_ok=True)
+    ims = loader.load_tomos_from_list(["tomoC"], [path], order=opt.order, compress=opt.compress, denoise=opt.gauss,
+                                      dtype=torch.float32)
+    vol = ims["tomoC"]                                  # (12, 64, 96) float32 on the device
+    ref_vol = po.preprocess(po.load_rec(hdr_src, order="xzy", compress=True), denoise=0.8).astype(np.float32)
+    assert tuple(vol.shape) == ref_vol.shape == (12, 64, 96)
+    assert np.array_equal(vol.cpu().numpy(), ref_vol)
+    det = detector_factory[opt.task](opt)
+    ret = det.run(vol[None], {"name": ["tomoC"]})
+    assert ret["tot_time"] > 0
+    lines = open(os.path.join(opt.out_path, "tomoC.txt")).read().splitlines()
+    assert len(lines) > 0 and all(len(ln.split("\t")) == 4 for ln in lines)
+    hm_file = mrcio.read_mrc(os.path.join(opt.out_path, "tomoC_hm.mrc"))           # axes (H', D, W')
+    with torch.no_grad():
+        hm_ref = uo.sigmoid_clamp(uo.forward(torch.from_numpy(ref_vol)[None], sd, want_proj=False)["hm"]).numpy()[0, 0]
+    assert np.abs(np.swapaxes(hm_file, 1, 0) - hm_ref).max() <= 1e-2
