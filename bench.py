@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 METRIC = "tomograms_per_sec"
 UNIT = "tomograms/s"
 FLOP_PER_VOXEL_NO_PROJ = 102328 - 1536      # unet_4 algorithmic conv FLOPs, 'proj' head skipped
+# dram__bytes_read.sum + dram__bytes_write.sum of the 19 tcgen05 conv launches of ONE 1024x1024x256 forward, from the
+# `ncu --set full` capture summarised in profiles/r1y_conv_full.txt (ids 0-20 without pool2x2 and stem)
+CONV_DRAM_BYTES_PER_FORWARD_C2 = 92.84e9
 
 
 def parse():
@@ -279,7 +282,10 @@ def run_b200(a, rank, world, local_rank):
             "gpu_launches": n_launch,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / pk["bf16_sustained"]) if achieved else None,
+                         "traffic": CONV_DRAM_BYTES_PER_FORWARD_C2 if (D, H, W) == (256, 1024, 1024) else None,
+                         "traffic_source": "profiles/r1y_conv_full.txt (ncu --set full, per forward like `achieved`)",
+                         "algorithmic_flops_per_forward": conv_fl,
                          "kernel": "conv_march_kernel + conv_halo_kernel + conv_up_kernel (all tcgen05 conv layers of one forward)",
                          "peak_source": pk["src"] + " sustained cuBLAS bf16", "share_of_forward": conv_ms / tot_ms if tot_ms else None,
                          "layers_ms": {k: round(v[0], 3) for k, v in layers.items()},

@@ -555,12 +555,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         if (!zgen) {
           if (mode == MODE_HIST) {
             zero_cnt += __popc(vmask) - __popc(mask);
+            // Plateau maps put most survivors of a thread, and of a warp, into ONE bin: run-length compress per
+            // thread, then one shared-memory atomic per distinct bin of the warp (a 32 x 16-way serialised
+            // same-address atomic made these passes 0.4 ms on a random-init detector's map).
+            uint32_t rb = 0xffffffffu, rc = 0;
             for (uint32_t m = mask; m; m &= m - 1) {
               const uint32_t ok = f2key(centre(__ffs(m) - 1));
               if (hs < 32 && (ok >> hs) != prefix) continue;
-              if (ok == KEY_ZERO) ++zero_cnt;
-              else atomicAdd(&s_hist[(ok >> p.shift) & dmask], 1u);
+              if (ok == KEY_ZERO) { ++zero_cnt; continue; }
+              const uint32_t bin = (ok >> p.shift) & dmask;
+              if (bin == rb) { ++rc; }
+              else { if (rc) atomicAdd(&s_hist[rb], rc); rb = bin; rc = 1; }
             }
+            const unsigned peers = __match_any_sync(0xffffffffu, rc ? rb : (0x80000000u | (uint32_t)lane));
+            const uint32_t tot = __reduce_add_sync(peers, rc);
+            if (rc && lane == __ffs(peers) - 1) atomicAdd(&s_hist[rb], tot);
           } else {
             for (uint32_t m = mask; m; m &= m - 1) {
               const int b = __ffs(m) - 1;
@@ -765,12 +774,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float4* ptr) {
 
 // NMS output key of voxel idx (the caller knows it is in the volume)
 // (not inlined: the stream loop of sieve_kernel must keep its registers; drains are rare)
-#ifdef SIEVE_INLINE
-#define SIEVE_NOINLINE __forceinline__
-#else
-#define SIEVE_NOINLINE __noinline__
-#endif
-__device__ SIEVE_NOINLINE uint32_t sieve_okey(const float* __restrict__ heat, uint32_t idx, int D, int H, int W,
+__device__ __noinline__ uint32_t sieve_okey(const float* __restrict__ heat, uint32_t idx, int D, int H, int W,
                                                int P, int nms_mode, bool& is_nan) {
   const int hw = H * W;
   const int z = (int)(idx / (uint32_t)hw);
@@ -946,10 +950,8 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
     // running threshold: warp 0 fetched it one iteration ago (one L2 request per CTA, not per warp: 4736
     // warps polling one line was a measured 15 % stall) and relays it through shared memory
     if (warp == 0 && tr_new > s_trun) s_trun = tr_new;
-#ifndef SIEVE_NO_WATCHDOG
     if (warp == 0 && dn_new) s_dense = 1u;
     if (s_dense) break;
-#endif
     {
       const uint32_t tr = s_trun;
       if (tr > t_take) { t_take = tr; t0f = key2f(tr + 1u); }
@@ -1007,7 +1009,6 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
       __syncwarp();
       if (q_n >= 32) drain(32);
     }
-#ifndef SIEVE_NO_WATCHDOG
     if (w_hits >= 256u) {       // warp-uniform
       if (lane == 0) {
         const uint32_t tot = atomicAdd(&st->hit_total, w_hits) + w_hits;
@@ -1016,7 +1017,6 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
       }
       w_hits = 0;
     }
-#endif
   }
   if (q_n) drain(q_n);
   for (uint32_t k = w_used + lane; k < SIEVE_CHUNK; k += 32)   // pad the tail of the warp's last chunk
@@ -1265,7 +1265,10 @@ struct WsLayout {
 WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   WsLayout L;
   const uint64_t n = (uint64_t)D * H * W;
-  uint64_t cap_gt = std::max<uint64_t>(1ull << 21, 256ull * (uint64_t)K);
+  // room for the voxels above the sampled bound: 256 K on a map with peaks; n/8 so that a map made of a few
+  // huge plateaus of tied values (a random-init detector: ~10 % of all voxels tie for the top) is still
+  // selected from the candidate list instead of three more passes over the volume
+  uint64_t cap_gt = std::max<uint64_t>(std::max<uint64_t>(1ull << 21, 256ull * (uint64_t)K), n / 8);
   if (n <= cap_gt) cap_gt = n;  // collect-all path
   L.cap_gt = (uint32_t)cap_gt;
   L.cap_total = (uint32_t)(cap_gt + (uint64_t)H * W + (uint64_t)K + 1024);
