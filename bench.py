@@ -104,7 +104,7 @@ def run_reference(a, rank):
                                    "(configs[1])", "arch": "unet_4", "K": a.K, "nms": a.nms},
             "cpu_baseline": {**{k: best[k] for k in ("unit", "cores", "kind", "sample")}, "value": v},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -293,13 +293,26 @@ def run_b200(a, rank, world, local_rank):
         }
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample((D, H, W), a.K, a.nms, a.cpu_sample_slices)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line of the contract goes to the process's real stdout"""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    global _JSON_OUT
+    # Libraries write banners to fd 1 (NCCL prints "NCCL version ..." there when NCCL_DEBUG is WARN/VERSION): keep
+    # the real stdout for the JSON line only and send everything else that targets fd 1 to stderr.
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -6,6 +6,7 @@ set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
 tail -4 gpurun_out/${TAG}_pytest.log
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_c2_batch64.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cut -c1-400 gpurun_out/${TAG}_bench_c2_batch64.json
 timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2>> gpurun_out/${TAG}_bench.err
