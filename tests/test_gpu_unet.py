@@ -171,3 +171,33 @@ def test_config0_full_size_vs_oracle():
     m.slab_z = 48
     hm2 = m(x_in.cuda())[-1]["hm"]
     assert (hm2 - hm).abs().max().item() <= 2e-7 and m.last_slabs == 3
+
+
+def test_unaligned_width_takes_the_fallback_kernels():
+    """W not a multiple of 4: rows are not 16-byte aligned, so the stem runs as the CUDA-core kernel and decode
+    as the cp.async scan (no TMA): same tolerances against the oracle."""
+    from oracle import unet_oracle as uo, decode_oracle as do
+    from cet_pick_b200.models.decode import tomo_decode
+    D, H, W, K = 5, 46, 50, 25
+    sd = synth.unet_state_dict_torch(317, 4)
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, 8))[None]
+    with torch.no_grad():
+        ref = uo.sigmoid_clamp(uo.forward(x, sd, want_proj=False)["hm"]).numpy()
+    m = build_model(4, 317)
+    m.compute_proj = False
+    m.fuse_sigmoid = True
+    hm = m(x.cuda())[-1]["hm"]
+    assert hm.shape == ref.shape == (1, 1, D, 23, 25)
+    assert np.abs(hm.cpu().numpy() - ref).max() <= HM_TOL
+    dets = tomo_decode(hm, kernel=3, K=K).cpu().numpy()
+    assert np.array_equal(dets.view(np.uint32), do.tomo_decode(hm.cpu().numpy(), 3, None, K).view(np.uint32))
+
+
+def test_batch_of_two_volumes():
+    m = build_model(4, 317)
+    m.fuse_sigmoid = True
+    x = torch.from_numpy(np.stack([synth.tomogram_np(4, 32, 48, s) for s in (1, 2)])).cuda()
+    both = m(x)[-1]
+    for i in range(2):
+        one = m(x[i:i + 1])[-1]
+        assert torch.equal(both["hm"][i], one["hm"][0]) and torch.equal(both["proj"][i], one["proj"][0])

@@ -1,0 +1,35 @@
+"""The flag system against the unmodified reference's opts.py (CPU; skipped where /root/reference is absent):
+same defaults and same derived fields for the command lines of docs/refine.md."""
+import os
+
+import pytest
+
+from oracle import refbridge
+
+pytestmark = pytest.mark.skipif(not refbridge.available(), reason="reference checkout not present")
+
+CASES = [
+    ["semi", "--arch", "unet_4", "--load_model", "m.pth", "--K", "900", "--compress", "--gauss", "0.8",
+     "--test_img_txt", "t.txt", "--out_id", "out", "--with_score"],
+    ["semi"],
+    ["semiclass", "--nms", "5", "--out_thresh", "0.4", "--cutoff_z", "7", "--gpus", "0"],
+    ["semi", "--arch", "unet_5", "--fiber", "--exp_id", "abc", "--down_ratio", "2", "--order", "zxy"],
+]
+
+
+@pytest.mark.parametrize("argv", CASES)
+def test_parse_matches_reference(argv, tmp_path, monkeypatch):
+    refbridge.install()
+    from cet_pick.opts import opts as ref_opts
+    from cet_pick_b200.opts import opts as our_opts
+    monkeypatch.chdir(tmp_path)
+    ref = vars(ref_opts().parse(list(argv)))
+    ours = vars(our_opts().parse(list(argv)))
+    skip = {"root_dir", "data_dir", "exp_dir", "save_dir", "debug_dir", "out_path", "device"}   # absolute paths of each checkout
+    common = (set(ref) & set(ours)) - skip
+    assert len(common) >= 60
+    diff = {k: (ref[k], ours[k]) for k in common if ref[k] != ours[k]}
+    assert not diff, diff
+    for k in ("save_dir", "debug_dir", "out_path"):          # same layout below the respective root
+        if k in ref and k in ours:
+            assert os.path.relpath(ref[k], ref["root_dir"]) == os.path.relpath(ours[k], ours["root_dir"])
