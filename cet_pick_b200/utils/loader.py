@@ -1,6 +1,6 @@
 """Mirror of the pre-processing functions of cet_pick/utils/loader.py (quantize :16-25, load_rec :27-88,
 preprocess :90-121, load_tomos_from_list :165-173) for reconstructed tomograms (`is_tilt=False`, what the
-refinement step uses).  Same names, arguments and float64 arithmetic; the volume lives on the GPU and every step
+refinement step uses) and for tilt series (`is_tilt=True`: per-slice statistics).  Same names, arguments and float64 arithmetic; the volume lives on the GPU and every step
 is a kernel of csrc/preproc.cu, so the results are CUDA tensors (float64, like the reference's numpy arrays;
 `load_tomos_from_list(..., dtype=torch.float32)` gives the detector's input type directly, which is what the
 reference's datasets produce with `.astype(np.float32)`, datasets/particle_moco.py:176-178)."""
@@ -71,10 +71,8 @@ def quantize(x, mi=-2.5, ma=2, dtype=torch.uint8):
 
 
 def load_rec(path, order="xyz", compress=False, is_tilt=False):
-    """loader.py:27-88.  `path` may also be the (nz,ny,nx) array `mrcfile` would return.  -> float64 CUDA tensor."""
-    if is_tilt:
-        raise NotImplementedError("load_rec(is_tilt=True): per-slice tilt-series normalisation is outside the "
-                                  "localisation path (DESIGN.md)")
+    """loader.py:27-88.  `path` may also be the (nz,ny,nx) array `mrcfile` would return.  -> float64 CUDA tensor.
+    is_tilt: every output slice is z-scored on its own (:48-49,56-57) instead of the volume as a whole (:59-60)."""
     rec = read_mrc(path) if isinstance(path, (str, bytes)) or hasattr(path, "__fspath__") else path
     t, code = _to_device(rec)
     if t.dim() != 3:
@@ -102,6 +100,10 @@ def load_rec(path, order="xyz", compress=False, is_tilt=False):
     out = torch.empty((J, A, B), dtype=torch.float64, device=t.device)
     _lib.check(_lib.lib().cetpick_pre_gather_f64(t.data_ptr(), code, A, B, J, sa, sb, sz, Z, 1 if compress else 0,
                                                  out.data_ptr(), _lib.stream_ptr()), "pre_gather")
+    if is_tilt:
+        for j in range(J):                            # (new_slice - new_slice.mean()) / new_slice.std()
+            _zscore_(out[j])
+        return out
     return _zscore_(out)                              # (new_slices - mean) / std, loader.py:59-60,85-86
 
 
@@ -120,8 +122,11 @@ def gaussian_filter(x: torch.Tensor, sigma) -> torch.Tensor:
     w, radius = gaussian_kernel1d(sigma)
     w = np.ascontiguousarray(w, dtype=np.float64)
     a, b = x, torch.empty_like(x)
-    n0, n1, n2 = x.shape
-    for axis in range(3):
+    if x.dim() == 2:                                  # a single image: filter its two axes
+        n0, (n1, n2), axes = 1, x.shape, (1, 2)
+    else:
+        (n0, n1, n2), axes = x.shape, (0, 1, 2)
+    for axis in axes:
         _lib.check(_lib.lib().cetpick_pre_gauss1d_f64(a.data_ptr(), b.data_ptr(), n0, n1, n2, axis,
                                                       w.ctypes.data_as(C.c_void_p), radius, _lib.stream_ptr()),
                    "pre_gauss1d")
@@ -132,12 +137,21 @@ def gaussian_filter(x: torch.Tensor, sigma) -> torch.Tensor:
 def preprocess(mrc, denoise=0, is_tilt=False, dtype=torch.float64):
     """loader.py:90-121 (reconstruction branch): [Gaussian sigma=denoise] -> z-score -> 256 levels on [-3,3]
     (or [-2.5,2] without denoising) -> min-max to [0,1].  -> CUDA tensor of `dtype` (float64 like the reference)."""
-    if is_tilt:
-        raise NotImplementedError("preprocess(is_tilt=True): tilt-series branch is outside the localisation path")
     x, _ = _to_device(mrc)
     x = x.to(torch.float64)
     if x.dim() != 3:
         raise ValueError(f"preprocess: expected a 3-D volume, got {tuple(x.shape)}")
+    if is_tilt:
+        # :92-100,108-116: per slice [2-D Gaussian] -> z-score -> quantize(-2.5, 2) -> cv2.normalize(NORM_MINMAX, CV_32F)
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        mm = torch.empty(2, dtype=torch.int32, device=x.device)
+        for j in range(x.shape[0]):
+            dd = gaussian_filter(x[j], denoise) if denoise > 0 else x[j].clone()
+            _zscore_(dd)
+            q = quantize(dd)
+            _lib.check(_lib.lib().cetpick_pre_minmax_normalize(q.data_ptr(), q.numel(), mm.data_ptr(), out[j].data_ptr(),
+                                                               0, _lib.stream_ptr()), "pre_minmax_normalize")
+        return out                                    # float32 like np.asarray of the CV_32F slices
     if denoise > 0:
         im = gaussian_filter(x, denoise)
         mi, ma = -3.0, 3.0

@@ -73,7 +73,21 @@ def test_quantize_half_to_even_and_errors(ld):
     q = ld.quantize(x.cuda(), mi=-2.5, ma=2).cpu().numpy().ravel()
     ref = np.round(np.clip(255 * (x.numpy().ravel() + 2.5) / 4.5, 0, 255)).astype(np.uint8)
     assert np.array_equal(q, ref)
-    with pytest.raises(NotImplementedError):
-        ld.load_rec(np.zeros((2, 2, 2), np.float32), is_tilt=True)
     with pytest.raises(IndexError):
         ld.load_rec(np.zeros((3, 4, 4), np.float32), order="zxy", compress=True)
+
+
+@pytest.mark.parametrize("name", ["preproc_tilt_zxy_g0", "preproc_tilt_zxy_g1", "preproc_tilt_xzy_c"])
+def test_tilt_branch_reference_golden(golden, ld, name):
+    """is_tilt=True: per-slice z-score / 2-D Gaussian / quantize / min-max.  The reference takes the slice
+    statistics in float32 (the file's dtype), the device in float64: values agree to float32 rounding, and a
+    voxel that sits on a level boundary may land one level away."""
+    g = golden(name)
+    v = pre_volume(g["shape"], g["seed"])
+    rec = ld.load_rec(v, order=str(g["order"]), compress=bool(g["compress"]), is_tilt=True)
+    assert rec.dtype == torch.float64 and tuple(rec.shape) == g["rec"].shape
+    assert np.abs(rec.cpu().numpy() - g["rec"]).max() <= 5e-6
+    im = ld.preprocess(torch.from_numpy(g["rec"]), denoise=float(g["sigma"]), is_tilt=True)   # same input as the reference
+    assert im.dtype == torch.float32
+    d = np.abs(im.cpu().numpy() - g["im"])
+    assert (d > 1e-6).mean() <= 2e-3 and d.max() <= 1.0 / 100
