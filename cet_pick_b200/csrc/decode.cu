@@ -32,6 +32,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int HIST_BINS = 2048;
 constexpr int MAX_ZC = 64;
 constexpr int SORT_SMEM_MAX = 16384;  // composites sortable in one CTA's shared memory
+constexpr int RANK_MAX_K = 16384;     // largest list the rank-sort stage orders (rank_kernel)
 
 enum { MODE_HIST = 0, MODE_COLLECT = 1, MODE_EQ = 2 };
 enum { FLAG_NAN = 1, FLAG_FALLBACK = 2, FLAG_INTERNAL = 4 };
@@ -58,7 +59,7 @@ struct DecodeState {
   uint32_t hit_total;     // sieve: voxels >= threshold queued so far (reported in batches)
   uint32_t dense;         // sieve: hit density too high for the hit-by-hit path: bail out
   uint32_t need_dense;    // set by the sieve's last CTA: scan_kernel COLLECT (gate 2) takes over with the same t0
-  uint32_t pad2;
+  uint32_t n_sel;         // entries handed to the rank stage: K, or (fast final select) the M >= K candidates of the last histogram bin and above
 };
 
 struct alignas(64) ScanParams {
@@ -829,8 +830,11 @@ __device__ __noinline__ uint32_t sieve_okey(const float* __restrict__ heat, uint
 // stream warp -- a stream warp that did this every few iterations became the kernel's 0.1 ms straggler)
 // recomputes the running threshold: stage the histogram, walk it from the top until K appended candidates
 // are covered, publish the lower edge of that bin.
-__device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K, uint32_t t0key, uint32_t* t_run) {
+__device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K, uint32_t t0key, uint32_t* t_run,
+                              uint32_t* s_res /*[2]: delta of the bin edge, candidates at or above it (0 = fewer than K)*/) {
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { s_res[0] = 0u; s_res[1] = 0u; }
+  __syncthreads();
   for (int i = threadIdx.x; i < REFINE_BINS; i += SIEVE_THREADS) s_rh[i] = __ldcg(&rhist[i]);
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -854,6 +858,7 @@ __device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K,
       // >= K appended survivors have delta >= lo: key > t0key + lo - 1 keeps all of them
       const uint32_t lo = refine_bin_lo((uint32_t)b);
       if (lo > 0) atomicMax(t_run, t0key + lo - 1u);
+      s_res[0] = lo; s_res[1] = cum;
     }
   }
   __syncthreads();
@@ -864,7 +869,7 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   __shared__ uint32_t s_q[SIEVE_THREADS / 32][SIEVE_QUEUE];
   __shared__ uint32_t s_rh[REFINE_BINS];
   __shared__ volatile uint32_t s_trun, s_dense;
-  __shared__ uint32_t s_ticket;
+  __shared__ uint32_t s_ticket, s_res[2];
   DecodeState* st = p.st;
   if (st->need_dense || st->need_fallback) return;   // the sample pass already handed COLLECT to scan_kernel
   const uint32_t t0key = st->t0key;
@@ -884,7 +889,7 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
     // refresh the running threshold until every stream CTA has taken its ticket (or the pass was abandoned)
     uint32_t done = 0;
     while (done < nstream) {
-      if (!all) sieve_publish(p.rhist, s_rh, (uint32_t)p.K, t0key, &st->t_run);
+      if (!all) sieve_publish(p.rhist, s_rh, (uint32_t)p.K, t0key, &st->t_run, s_res);
       __nanosleep(1000);
       done = __ldcg(&st->done_ctr);
       done = __shfl_sync(0xffffffffu, done, 0);    // warp-uniform ...
@@ -1033,8 +1038,24 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   if (__ldcg(&st->dense)) {     // abandoned: hand COLLECT to scan_kernel (gate 2) from a clean slate
     for (int i = threadIdx.x; i < D; i += SIEVE_THREADS) p.eqcnt[i] = 0;
     if (threadIdx.x == 0) { st->cand_count = 0; st->n_real = 0; st->need_dense = 1; st->done_ctr = 0; }
-  } else if (threadIdx.x == 0) {
-    collect_plan(p, st);
+  } else {
+    if (threadIdx.x == 0) collect_plan(p, st);
+    __syncthreads();
+    // Fast final select: the histogram of appended keys is complete now.  If the bin holding the K-th largest
+    // key and everything above it is a short list (M <= RANK_MAX_K), hand exactly those M candidates to the
+    // rank stage (it orders them and writes the first K) and skip the three radix-select passes over the list.
+    if (!all && blockIdx.x == nstream && (uint32_t)p.K <= (uint32_t)RANK_MAX_K && st->need_fallback == 0 &&
+        st->eq_need == 0) {
+      __threadfence();
+      sieve_publish(p.rhist, s_rh, (uint32_t)p.K, t0key, &st->t_run, s_res);
+      if (threadIdx.x == 0 && s_res[1] >= (uint32_t)p.K && s_res[1] <= (uint32_t)RANK_MAX_K) {
+        st->kth_comp = (unsigned long long)(t0key + s_res[0]) << 32;     // every composite with key >= t0key + lo
+        st->n_sel = s_res[1];
+        st->out_count = 0;
+        st->n_final = min(st->cand_count, p.cap_total);
+        st->csel_done = 2;
+      }
+    }
   }
 }
 
@@ -1049,6 +1070,7 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
   __shared__ uint32_t s_hist[HIST_BINS];
   __shared__ uint32_t s_sel[3];
   __shared__ uint32_t s_ticket;
+  if (st->csel_done == 2) return;          // fast final select (sieve_kernel): nothing to resolve
   if (!first && st->csel_done) return;     // the key digits already fixed the K-th composite
   const uint32_t n = min(st->cand_count, cap_total);
   const int hs = shift + bits;
@@ -1082,7 +1104,7 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
     st->csel_prefix = np;
     st->csel_kleft = s_sel[1];
     if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
-    if (first) st->n_final = n;
+    if (first) { st->n_final = n; st->n_sel = (uint32_t)K; }
     if (last) { st->kth_comp = np; st->out_count = 0; }
     if (shift == 32 && s_sel[1] == s_sel[2]) {
       // every candidate with the K-th key is needed (the usual case: no ties): skip the index digits
@@ -1099,11 +1121,13 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_compact_kernel(
     uint32_t cap_total, int K) {
   const uint32_t n = min(st->cand_count, cap_total);
   const unsigned long long kth = st->kth_comp;
+  const uint32_t cap_out = st->n_sel;      // K, or M >= K in the fast mode
+  (void)K;
   for (uint32_t i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
     const unsigned long long c = cand[i];
     if (c >= kth) {
       const uint32_t o = atomicAdd(&st->out_count, 1u);
-      if (o < (uint32_t)K) out[o] = c;
+      if (o < cap_out) out[o] = c;
     }
   }
 }
@@ -1112,11 +1136,13 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_compact_kernel(
 // output row.  rank_kernel counts against one slice of the list per blockIdx.y (slice in shared
 // memory, broadcast reads); rank_write_kernel writes the picks.  O(K^2 / PARTS) per thread, all SMs
 // busy: ~20 us at K = 10 000 where a one-CTA bitonic sort needs ~260 us.
-constexpr int RANK_MAX_K = 16384, RANK_PARTS = 16, RANK_THREADS = 128;
+constexpr int RANK_PARTS = 16, RANK_THREADS = 128;
 
-__global__ void __launch_bounds__(RANK_THREADS) rank_kernel(const unsigned long long* __restrict__ keys, int K,
+__global__ void __launch_bounds__(RANK_THREADS) rank_kernel(const unsigned long long* __restrict__ keys,
+                                                            const DecodeState* __restrict__ st,
                                                             uint32_t* __restrict__ ranks) {
   __shared__ unsigned long long s_k[RANK_MAX_K / RANK_PARTS];
+  const int K = (int)st->n_sel;            // entries to order (the grid is sized for RANK_MAX_K)
   const int per = ceil_div(K, RANK_PARTS);
   const int j0 = blockIdx.y * per, j1 = min(K, j0 + per);
   for (int j = j0 + threadIdx.x; j < j1; j += RANK_THREADS) s_k[j - j0] = keys[j];
@@ -1158,15 +1184,16 @@ __device__ __forceinline__ void write_pick(unsigned long long c, int r, const fl
 }
 
 __global__ void __launch_bounds__(256) rank_write_kernel(const unsigned long long* __restrict__ keys, int K,
+                                                         const DecodeState* __restrict__ st,
                                                          uint32_t* __restrict__ ranks,
                                                          const float* __restrict__ heat,
                                                          const float* __restrict__ reg, int D, int H, int W,
                                                          float* __restrict__ dets, long long* __restrict__ inds) {
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= K) return;
+  if (i >= (int)st->n_sel) return;
   const uint32_t r = ranks[i];
   ranks[i] = 0;                                               // ready for the next decode
-  write_pick(keys[i], (int)r, heat, reg, (size_t)D * H * W, H * W, W, dets, inds);
+  if (r < (uint32_t)K) write_pick(keys[i], (int)r, heat, reg, (size_t)D * H * W, H * W, W, dets, inds);
 }
 
 // One CTA: bitonic sort (descending) of K composites, then the pick writer
@@ -1281,8 +1308,8 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   L.off_eq = o;    o = align_up(o + (size_t)D * sizeof(uint32_t), 256);
   L.off_rhist = o; o = align_up(o + (size_t)REFINE_BINS * sizeof(uint32_t), 256);
   L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
-  L.off_out = o;   o = align_up(o + (size_t)npad * 8, 256);
-  L.off_rank = o;  o = align_up(o + (size_t)std::min<int64_t>(K, RANK_MAX_K) * 4, 256);
+  L.off_out = o;   o = align_up(o + (size_t)std::max(npad, RANK_MAX_K) * 8, 256);
+  L.off_rank = o;  o = align_up(o + (size_t)RANK_MAX_K * 4, 256);
   L.total = o;
   return L;
 }
@@ -1360,7 +1387,7 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   const bool collect_all = (n <= L.cap_gt);
 
   uint32_t* ranks = reinterpret_cast<uint32_t*>(base + L.off_rank);
-  const int n_ranks = std::min(K, RANK_MAX_K);
+  const int n_ranks = RANK_MAX_K;
   uint32_t* rhist = reinterpret_cast<uint32_t*>(base + L.off_rhist);
   init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, ranks, n_ranks, rhist);
   CETPICK_LAUNCH_CHECK();
@@ -1449,11 +1476,14 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     CETPICK_LAUNCH_CHECK();
   }
   if (K <= RANK_MAX_K) {
-    CETPICK_CUDA(launch_k(rank_kernel, dim3(ceil_div(K, RANK_THREADS), RANK_PARTS), dim3(RANK_THREADS), 0, s, outb, K,
-                            ranks));
+    // grids sized for the fast mode's upper bound (M <= RANK_MAX_K); surplus CTAs exit at once
+    const bool vec_fast = p.vec_ok && !collect_all;     // sieve_kernel ran: it may have chosen the fast final select
+    const int nsel_max = vec_fast ? RANK_MAX_K : K;
+    CETPICK_CUDA(launch_k(rank_kernel, dim3(ceil_div(nsel_max, RANK_THREADS), RANK_PARTS), dim3(RANK_THREADS), 0, s, outb,
+                            (const DecodeState*)st, ranks));
     CETPICK_LAUNCH_CHECK();
-    CETPICK_CUDA(launch_k(rank_write_kernel, dim3(ceil_div(K, 256)), dim3(256), 0, s, outb, K, ranks, heat, reg, D, H, W,
-                            dets, inds));
+    CETPICK_CUDA(launch_k(rank_write_kernel, dim3(ceil_div(nsel_max, 256)), dim3(256), 0, s, outb, K,
+                            (const DecodeState*)st, ranks, heat, reg, D, H, W, dets, inds));
     CETPICK_LAUNCH_CHECK();
   } else {
     const int use_smem = L.npad <= SORT_SMEM_MAX;
@@ -1518,10 +1548,11 @@ extern "C" int cetpick_decode_status(const void* ws, void* stream, int* flags, i
   return CETPICK_OK;
 }
 
-extern "C" int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out16) {
-  if (!ws || !out16) return CETPICK_ERR_BAD_ARG;
+extern "C" int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out24) {
+  if (!ws || !out24) return CETPICK_ERR_BAD_ARG;
+  static_assert(sizeof(DecodeState) >= 24 * sizeof(uint32_t), "debug view");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CETPICK_CUDA(cudaMemcpyAsync(out16, ws, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CETPICK_CUDA(cudaMemcpyAsync(out24, ws, 24 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CETPICK_CUDA(cudaStreamSynchronize(s));
   return CETPICK_OK;
 }

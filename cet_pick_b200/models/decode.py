@@ -156,14 +156,15 @@ def decode_status(device=None):
 
 
 def decode_debug_state(device=None):
-    """First 16 words of the device-side decode state (diagnostics)."""
+    """First 24 words of the device-side decode state (diagnostics)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     ws = _ws_cache.get((device.index, torch.cuda.current_stream(device).cuda_stream))
     if ws is None:
         return None
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-    out = (C.c_uint32 * 16)()
+    out = (C.c_uint32 * 24)()
     _lib.check(_lib.lib().cetpick_decode_debug_state(ws_ptr, _lib.stream_ptr(), out), "decode_debug_state")
     names = ["t0key", "sel_prefix", "sel_kleft", "flags", "cand_count", "n_gt", "need_fallback", "eq_need",
-             "eq_zc", "done_ctr", "csel_kleft", "out_count"]
+             "eq_zc", "done_ctr", "csel_kleft", "out_count", "csel_prefix_lo", "csel_prefix_hi", "kth_comp_lo",
+             "kth_comp_hi", "n_final", "csel_done", "n_real", "t_run", "hit_total", "dense", "need_dense", "n_sel"]
     return {n: int(out[i]) for i, n in enumerate(names)}

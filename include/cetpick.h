@@ -77,9 +77,9 @@ int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64_t H, int64
  * n_candidates: entries the final select saw. */
 int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_candidates);
 
-/* Diagnostics: the first 16 words of the decode state block in `ws` (t0key, select prefix, rank
+/* Diagnostics: the first 24 words of the decode state block in `ws` (t0key, select prefix, rank
  * left, flags, candidate count, n_gt, need_fallback, eq_need, eq_zc, ...).  Synchronises. */
-int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out16);
+int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out24);
 
 /* Full NMS map (decode.py:11-33): out = heat * (maxpool(heat) == heat).  mode: CETPICK_NMS_3D
  * ((3,k,k)), 3 = xy only ((1,k,k), `_nms_xy`), 4 = z only ((k,1,1), `_nms_z`). */
