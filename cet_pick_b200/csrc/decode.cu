@@ -1,21 +1,24 @@
 // Heat-map decode for sm_100a: 3-D max-pool NMS + exact top-K + pick writer.
 //
 // Replaces cet_pick/models/decode.py:11-41,82-92,123-155 (and models/utils.py:171-193 for `reg`).
-// HBM-bound design (DESIGN.md "decode"): the fp32 map is streamed ONCE by `scan_kernel` in COLLECT
-// mode; a voxel's NMS output o = heat*(maxpool==heat) is never materialised.  What is selected is
-// decided by an exact radix select:
-//   1. HIST passes over a small, L2-resident z-range (the "sample") give t0 = K-th largest o in the
-//      sample, a guaranteed lower bound of the global K-th largest o;
-//   2. COLLECT streams the whole map once and appends every voxel with o > t0 as a 64-bit composite
-//      (monotone key(o) << 32 | ~linear_index) and counts voxels with o == t0 per plane;
-//   3. if fewer than K were appended, EQ appends the o == t0 voxels of the first planes that are
-//      needed to fill K in ascending index order;
-//   4. a 6-digit radix select over the composites finds the exact K-th, the K survivors are
-//      compacted, bitonic-sorted (score desc, index asc) and written with the reference's fp32
-//      index arithmetic.
-// If the candidate buffer would overflow (adversarial map), the same HIST passes run over the whole
-// volume (exact, 3 extra reads) -- every kernel is always enqueued and exits early on device-side
-// state, so the call never synchronises the host.
+// HBM-bound design: the fp32 map is streamed ONCE; a voxel's NMS output
+// o = heat*(maxpool==heat) is never materialised.  What is selected is decided exactly:
+//   1. HIST passes of `scan_kernel` (TMA plane ring, tiled 3-D stencil) over a small z-range (the "sample",
+//      N/256 voxels) give t0 = lower edge of the bin of the K-th largest o there: a guaranteed lower bound
+//      of the global K-th largest o;
+//   2. COLLECT: `sieve_kernel` streams the map with coalesced 16-byte loads, tests the NMS window only for the
+//      rare voxels >= the threshold and appends survivors as 64-bit composites (monotone key(o) << 32 |
+//      ~linear_index); a publisher CTA keeps raising the threshold from a histogram of the appended keys.
+//      Voxels with o == t0 are counted per plane.  Maps with unaligned rows, a hit density above a few per
+//      cent (watchdog), or a sample made of huge tie plateaus use `scan_kernel` in COLLECT mode instead;
+//   3. if fewer than K were appended, EQ appends the o == t0 voxels of the first planes that are needed to fill
+//      K in ascending index order;
+//   4. final select: straight from the histogram when the K-th key's bin and above is a short list, else a
+//      radix select over the composites (3 key digits, index digits only on ties); the survivors are compacted,
+//      rank-sorted (score desc, index asc) and written with the reference's fp32 index arithmetic.
+// If the candidate buffer would overflow (adversarial map), the HIST passes run over the whole volume (exact,
+// 3 extra reads) -- every kernel is always enqueued and exits early on device-side state, so the call never
+// synchronises the host.
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "ptx.cuh"
