@@ -102,6 +102,20 @@ int cetpick_greedy_nms_f32(const float* heat, int64_t D, int64_t H, int64_t W, d
                            int64_t max_out, int64_t* n_out, int* rounds_out, void* ws, size_t ws_bytes,
                            void* stream);
 
+/* ---- exploration-step candidate generator (first half): cet_pick/utils/image.py:42-105,138-183 ---- */
+
+/* out = heat * (max_pool3d(heat, (kz,ky,kx), stride 1, same padding) == heat): image.py `_nms_xy` (1,k,k),
+ * `_nms_z` (k,1,1), `_nms` (k,k,k).  dtype: 0 float32, 1 float64; (B, D, H, W) volumes; odd window sizes. */
+int cetpick_nms_window(const void* heat, void* out, int dtype, int64_t B, int64_t D, int64_t H, int64_t W,
+                       int kz, int ky, int kx, void* stream);
+/* float64 twin of cetpick_greedy_nms_f32 (image.py:42-79 on the float64 DoG map): same arguments and conventions;
+ * equal scores are visited in ascending index order (stable sort); scores come back as float32 like the reference. */
+int cetpick_greedy_nms_f64_workspace_bytes(int64_t D, int64_t H, int64_t W, int64_t max_candidates, size_t* bytes);
+int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, int64_t W, double d, double scale,
+                           double threshold, int64_t max_candidates, float* scores, int32_t* coords,
+                           int64_t max_out, int64_t* n_out, int* rounds_out, void* ws, size_t ws_bytes,
+                           void* stream);
+
 /* ---- pre-processing in front of the path: cet_pick/utils/loader.py:16-25 (quantize), :27-88
  * (load_rec), :90-121 (preprocess), all float64 like the reference ------------------------------------------------ */
 
