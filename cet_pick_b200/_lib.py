@@ -34,6 +34,7 @@ SIGNATURES = {
     "cetpick_greedy_nms_f64_workspace_bytes": (_int, [_i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_greedy_nms_f64": (_int, [_vp, _i64, _i64, _i64, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp, _i64,
                                       C.POINTER(_i64), C.POINTER(_int), _vp, _sz, _vp]),
+    "cetpick_extract_subvols_f64": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _int, _int, _int, _vp, _vp]),
     "cetpick_pre_gather_f64": (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp, _vp]),
     "cetpick_pre_stats_workspace_bytes": (_int, [C.POINTER(_sz)]),
     "cetpick_pre_mean_std_f64": (_int, [_vp, _i64, _vp, _vp, _sz, _vp]),

@@ -133,6 +133,42 @@ __global__ void ex_write_kernel(const uint32_t* __restrict__ pos, const int* __r
   coords[3 * j + 2] = z;
 }
 
+// Candidate patches (datasets/tomo_pre_proj_angle_select_new3d_vol.py:117-128 `extract_subvols`): for candidate
+// (x, y, z) sum the z-slab [z - sz/2, z + sz/2] of the (sy x sx) window, min-max normalise in float64, cast to
+// float32.  One CTA per candidate; the slab sum is recomputed in the second pass instead of staged.
+__global__ void __launch_bounds__(EX_THREADS) ex_patch_kernel(const double* __restrict__ vol, int D, int H, int W,
+                                                               const int32_t* __restrict__ coords, int hz, int hy, int hx,
+                                                               float* __restrict__ out) {
+  __shared__ double s_mn[EX_THREADS], s_mx[EX_THREADS];
+  const int n = blockIdx.x;
+  const int x = coords[3 * n], y = coords[3 * n + 1], z = coords[3 * n + 2];
+  const int z0 = z - hz, z1 = min(z + hz + 1, D);          // numpy clips the end of the slice
+  const int py = 2 * hy, px = 2 * hx, np_ = py * px;
+  auto slab = [&](int e) -> double {
+    const int yy = y - hy + e / px, xx = x - hx + e % px;
+    double a = 0.0;
+    for (int zz = z0; zz < z1; ++zz) a += vol[((size_t)zz * H + yy) * W + xx];     // np.sum(axis=0): slice after slice
+    return a;
+  };
+  double mn = INFINITY, mx = -INFINITY;
+  for (int e = threadIdx.x; e < np_; e += EX_THREADS) {
+    const double a = slab(e);
+    mn = fmin(mn, a); mx = fmax(mx, a);
+  }
+  s_mn[threadIdx.x] = mn; s_mx[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = EX_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_mn[threadIdx.x] = fmin(s_mn[threadIdx.x], s_mn[threadIdx.x + o]);
+      s_mx[threadIdx.x] = fmax(s_mx[threadIdx.x], s_mx[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  mn = s_mn[0]; mx = s_mx[0];
+  const double range = mx - mn;
+  for (int e = threadIdx.x; e < np_; e += EX_THREADS) out[(size_t)n * np_ + e] = (float)((slab(e) - mn) / range);
+}
+
 struct ExLayout {
   size_t off_ctr, off_deltas, off_flag, off_rank, off_idx, off_idx2, off_keys, off_keys2, off_state, off_pflag, off_pos,
       off_tmp, total;
@@ -296,5 +332,20 @@ extern "C" int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, i
   CETPICK_CUDA(cudaMemcpyAsync(&np, n_sel + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
   CETPICK_CUDA(cudaStreamSynchronize(s));
   *n_out = np;
+  return CETPICK_OK;
+}
+
+// out[n] = min-max normalised z-slab sum around candidate n (float32, (2*(sub_y/2)) x (2*(sub_x/2)) per patch).
+// coords: int32 device [n][3] = (x, y, z); windows must lie inside the volume in x, y and at their low z end
+// (CETPICK_ERR_BAD_ARG otherwise is the caller's check: the kernel does not bounds-check).
+extern "C" int cetpick_extract_subvols_f64(const double* vol, int64_t D, int64_t H, int64_t W, const int32_t* coords,
+                                           int64_t n, int sub_z, int sub_y, int sub_x, float* out, void* stream) {
+  g_launches = 0;
+  if (!vol || !coords || !out || D <= 0 || H <= 0 || W <= 0 || n < 0 || sub_z < 1 || sub_y < 2 || sub_x < 2)
+    return CETPICK_ERR_BAD_ARG;
+  if (n == 0) return CETPICK_OK;
+  ex_patch_kernel<<<(unsigned)n, EX_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(vol, (int)D, (int)H, (int)W, coords,
+                                                                                    sub_z / 2, sub_y / 2, sub_x / 2, out);
+  CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }

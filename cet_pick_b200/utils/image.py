@@ -97,3 +97,25 @@ def get_potential_coords_pyramid(rec, sigmas=[2, 4], num_pyramid=3, kernel=3):
     std_nms_half = pos.std().item()                 # unbiased, like torch.Tensor.std
     cutoff_score = mean_nms + std_nms_half * 0.5
     return non_maximum_suppression_3d(nms_all, 14, threshold=cutoff_score)
+
+
+def extract_subvols(v, tomo_coords, subvol_size):
+    """datasets/tomo_pre_proj_angle_select_new3d_vol.py:117-128, batched: for every candidate (x, y, z) the z-slab
+    sum of the window, min-max normalised -> float32 CUDA tensor (n, 1, 2*(sub_y//2), 2*(sub_x//2)) (the reference
+    returns one (1, sub_y, sub_x) tensor per call).  v: (D,H,W) volume, processed in float64."""
+    v, _ = _to_device(v)
+    v = v.to(torch.float64).contiguous()
+    D, H, W = v.shape
+    c = torch.as_tensor(np.asarray(tomo_coords).reshape(-1, 3), dtype=torch.int32)
+    sub_z, sub_y, sub_x = (int(s) for s in subvol_size)
+    hz, hy, hx = sub_z // 2, sub_y // 2, sub_x // 2
+    if len(c):
+        x, y, z = c[:, 0], c[:, 1], c[:, 2]
+        ok = (x - hx >= 0) & (x + hx <= W) & (y - hy >= 0) & (y + hy <= H) & (z - hz >= 0) & (z < D)
+        if not bool(ok.all()):
+            raise ValueError("extract_subvols: a window leaves the volume (the reference filters such candidates, :207)")
+    out = torch.empty((len(c), 1, 2 * hy, 2 * hx), dtype=torch.float32, device=v.device)
+    cd = c.to(v.device).contiguous()
+    _lib.check(_lib.lib().cetpick_extract_subvols_f64(v.data_ptr(), D, H, W, cd.data_ptr(), len(c), sub_z, sub_y, sub_x,
+                                                      out.data_ptr(), _lib.stream_ptr()), "extract_subvols")
+    return out

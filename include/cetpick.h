@@ -116,6 +116,13 @@ int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, int64_t W, d
                            int64_t max_out, int64_t* n_out, int* rounds_out, void* ws, size_t ws_bytes,
                            void* stream);
 
+/* Candidate patches = `extract_subvols` of cet_pick/datasets/tomo_pre_proj_angle_select_new3d_vol.py:117-128: the
+ * z-slab [z - sub_z/2, z + sub_z/2] of the (sub_y x sub_x) window around each candidate is summed, min-max
+ * normalised in float64 and written as float32 [n][2*(sub_y/2)][2*(sub_x/2)].  coords: int32 device [n][3] =
+ * (x, y, z); the caller guarantees the windows lie inside the volume (x, y, and z - sub_z/2 >= 0). */
+int cetpick_extract_subvols_f64(const double* vol, int64_t D, int64_t H, int64_t W, const int32_t* coords,
+                                int64_t n, int sub_z, int sub_y, int sub_x, float* out, void* stream);
+
 /* ---- pre-processing in front of the path: cet_pick/utils/loader.py:16-25 (quantize), :27-88
  * (load_rec), :90-121 (preprocess), all float64 like the reference ------------------------------------------------ */
 

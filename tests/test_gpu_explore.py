@@ -52,3 +52,20 @@ def test_greedy_nms_f64_vs_oracle(im, shape, d, thr):
     sc, co = im.non_maximum_suppression_3d(x, d, threshold=thr)
     rs, rc = do.greedy_distance_nms(x, d, threshold=thr)
     assert np.array_equal(co, rc) and np.array_equal(bits(sc), bits(rs))
+
+
+def test_extract_subvols_vs_reference_formula(im):
+    """candidate patches: z-slab sum, min-max in float64, float32 out (new3d_vol.py:117-128 restated with numpy)."""
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal((20, 60, 70))
+    coords = np.array([[35, 30, 10], [20, 18, 1], [52, 41, 19], [16, 16, 5]], dtype=np.int32)     # z = 19: slab clipped at the top
+    sub = [3, 32, 32]
+    out = im.extract_subvols(v, coords, sub).cpu().numpy()
+    assert out.shape == (4, 1, 32, 32) and out.dtype == np.float32
+    for n, (x, y, z) in enumerate(coords):
+        e = v[z - 1:z + 2, y - 16:y + 16, x - 16:x + 16].copy()
+        e = np.sum(e, axis=0)
+        e = (e - np.min(e)) / (np.max(e) - np.min(e))
+        assert np.array_equal(out[n, 0], e.astype(np.float32))
+    with pytest.raises(ValueError):
+        im.extract_subvols(v, np.array([[5, 30, 10]]), sub)
