@@ -170,6 +170,12 @@ def run_b200(a, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # the native library is built in-tree (a no-op when it is up to date); one rank builds, the others wait
+    if rank == 0:
+        from cet_pick_b200 import build as _build
+        _build.build()
+    if world > 1:
+        dist.barrier()
     D, H, W = (int(v) for v in a.shape.split(","))
     first, n_local = shard_range(a.batch, rank, world)
 

@@ -1,0 +1,61 @@
+"""Host-side pieces that need no GPU: MRC I/O, Gaussian taps, post-processing buckets, error paths."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def test_mrc_roundtrip_and_modes(tmp_path):
+    from cet_pick_b200.utils import mrcio
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((5, 6, 7)).astype(np.float32)
+    p = str(tmp_path / "a.mrc")
+    mrcio.write_mrc(p, v)
+    assert np.array_equal(mrcio.read_mrc(p), v)
+    hdr = open(p, "rb").read(1024)
+    assert struct.unpack_from("<4i", hdr, 0) == (7, 6, 5, 2) and hdr[208:212] == b"MAP "
+    # integer modes as written by other packages: patch the mode word and the payload
+    for mode, dt in ((0, np.int8), (1, np.int16), (6, np.uint16)):
+        data = (rng.integers(0, 100, size=(3, 4, 5))).astype(dt)
+        h = bytearray(1024)
+        struct.pack_into("<4i", h, 0, 5, 4, 3, mode)
+        q = str(tmp_path / f"m{mode}.mrc")
+        open(q, "wb").write(bytes(h) + data.tobytes())
+        out = mrcio.read_mrc(q)
+        assert out.dtype == dt and np.array_equal(out, data)
+    h = bytearray(1024)
+    struct.pack_into("<4i", h, 0, 1, 1, 1, 4)
+    open(str(tmp_path / "bad.mrc"), "wb").write(bytes(h) + b"\0" * 8)
+    with pytest.raises(ValueError):
+        mrcio.read_mrc(str(tmp_path / "bad.mrc"))
+
+
+@pytest.mark.parametrize("sigma", [0.8, 1.0, 2.5, 5.0])
+def test_gaussian_taps_equal_scipy(sigma):
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    from cet_pick_b200.utils.loader import gaussian_kernel1d
+    w, r = gaussian_kernel1d(sigma)
+    assert r == int(4.0 * sigma + 0.5) and np.array_equal(w, _gaussian_kernel1d(sigma, 0, r))
+
+
+def test_tomo_post_process_buckets_by_z():
+    """utils/post_process.py:11-25: rows grouped by exact z, order inside a bucket preserved, last batch item wins."""
+    from cet_pick_b200.utils.post_process import tomo_post_process
+    from oracle import decode_oracle as do
+    dets = np.array([[[1.5, 2.5, 3.0, 0.9, 0.9], [4.5, 5.5, 1.0, 0.8, 0.8], [6.5, 7.5, 3.0, 0.7, 0.7]],
+                     [[0.5, 0.5, 0.0, 0.6, 0.6], [2.5, 2.5, 2.0, 0.5, 0.5], [3.5, 3.5, 2.0, 0.4, 0.4]]], dtype=np.float32)
+    ours = tomo_post_process(dets.copy(), z_dim_tot=4)
+    ref = do.tomo_post_process(dets.copy(), z_dim_tot=4)
+    assert ours == ref and sorted(ours[0].keys()) == [0, 2]
+    assert [r[0] for r in ours[0][2]] == [2.5, 3.5]
+
+
+def test_loader_and_image_have_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from cet_pick_b200.utils import image, loader
+    with pytest.raises(RuntimeError):
+        loader.preprocess(np.zeros((2, 4, 4), np.float32))
+    with pytest.raises(RuntimeError):
+        image.get_potential_coords_pyramid(np.zeros((40, 80, 80)))
