@@ -1,0 +1,66 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference imported from /root/reference (CPU; skipped on
+boxes without the checkout, where the committed fixtures in tests/golden/ are the pin).  Random tie-free inputs beyond
+the fixed fixtures: decode (all window sizes, fiber, reg), greedy distance suppression, the detector forward."""
+import numpy as np
+import pytest
+import torch
+
+from cet_pick_b200 import synth
+from oracle import decode_oracle as do
+from oracle import refbridge
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.skipif(not refbridge.available(), reason="reference checkout not present")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("shape,kernel,fiber,K,seed", [
+    ((5, 17, 23), 3, False, 60, 1), ((9, 30, 31), 5, False, 100, 2), ((4, 12, 40), 7, False, 33, 3),
+    ((6, 24, 24), 3, True, 80, 4), ((3, 9, 9), 1, False, 243, 5), ((12, 20, 18), 3, False, 1, 6),
+])
+def test_decode_against_live_reference(shape, kernel, fiber, K, seed):
+    d = refbridge.decode_module()
+    hm = synth.heatmap_tiefree_np(*shape, seed)[None, None]
+    ref = d.tomo_decode(torch.from_numpy(hm), kernel=kernel, reg=None, K=K, if_fiber=fiber).numpy()
+    out = do.tomo_decode(hm, kernel, None, K, fiber)
+    # rows beyond the last real peak have score 0 and, in torch.topk, unspecified positions
+    n = int((ref[0, :, 3] > 0).sum())
+    assert n == int((out[0, :, 3] > 0).sum()) and n > 0
+    assert np.array_equal(bits(out[:, :n]), bits(ref[:, :n]))
+    assert not out[0, n:, 3].any() and not ref[0, n:, 3].any()
+
+
+def test_decode_reg_against_live_reference():
+    d = refbridge.decode_module()
+    D, H, W, K = 5, 14, 18, 40
+    hm = np.stack([synth.heatmap_tiefree_np(D, H, W, s) for s in (7, 8)])[:, None]
+    reg = (synth.uniform_np(3, 2 * 2 * D * H * W).reshape(2, 2, D, H, W) - 0.5).astype(np.float32)
+    ref = d.tomo_decode(torch.from_numpy(hm), kernel=3, reg=torch.from_numpy(reg), K=K).numpy()
+    assert np.array_equal(bits(do.tomo_decode(hm, 3, reg, K)), bits(ref))
+
+
+@pytest.mark.parametrize("shape,dd,q", [((5, 16, 18), 3, 0.5), ((6, 20, 20), 6, 0.8), ((4, 30, 12), 9, 0.9)])
+def test_greedy_nms_against_live_reference(shape, dd, q):
+    d = refbridge.decode_module()
+    x = synth.heatmap_tiefree_np(*shape, 11 + dd)
+    thr = float(np.quantile(x, q))
+    rs, rc = d.non_maximum_suppression_3d(x, dd, threshold=thr)
+    s, c = do.greedy_distance_nms(x, dd, threshold=thr)
+    assert np.array_equal(bits(s), bits(rs)) and np.array_equal(c, rc)
+
+
+@pytest.mark.parametrize("n_blocks,shape", [(4, (3, 40, 44)), (5, (2, 32, 48))])
+def test_forward_against_live_reference(n_blocks, shape):
+    m = refbridge.create_model(f"unet_{n_blocks}", {"hm": 1, "proj": 32}, 32, last_k=3)
+    sd = synth.unet_state_dict_torch(23, n_blocks)
+    m.load_state_dict(sd)
+    m.eval()
+    x = torch.from_numpy(synth.tomogram_np(*shape, 4))[None]
+    with torch.no_grad():
+        ref = m(x)[-1]
+        out = uo.forward(x, sd)
+    assert (out["hm"] - ref["hm"]).abs().max().item() <= 1e-5
+    assert (out["proj"] - ref["proj"]).abs().max().item() <= 1e-5
