@@ -1,5 +1,7 @@
-"""Mirror of cet_pick/detectors/base_detector.py:15-106 (BaseDetector): model build + checkpoint
-load, and the run() driver returning the same timing dict."""
+"""Detector driver with the interface of cet_pick/detectors/base_detector.py:15-106 (`BaseDetector`):
+construction = build the model + load the checkpoint; `run(images, meta)` = device copy -> `process` ->
+`post_process` -> `save_detection`, returning the reference's timing dictionary
+`{'tot_time','load','pre','net','dec'}` (seconds; 'pre' is always 0 there too)."""
 from __future__ import annotations
 
 import time
@@ -9,20 +11,35 @@ import torch
 from ..models.model import create_model, load_model
 
 
+class _Laps:
+    """wall-clock laps in seconds (the reference brackets its stages with time.time())"""
+
+    def __init__(self):
+        self.t0 = self.last = time.time()
+
+    def lap(self, now=None):
+        now = time.time() if now is None else now
+        dt, self.last = now - self.last, now
+        return dt
+
+    def total(self):
+        return time.time() - self.t0
+
+
 class BaseDetector(object):
     def __init__(self, opt):
         if opt.gpus[0] < 0:
             raise RuntimeError("cet_pick_b200 has no CPU path: --gpus -1 is not supported (sm_100a only)")
         opt.device = torch.device("cuda")
         print("Creating model...")
-        self.model = create_model(opt.arch, opt.heads, opt.head_conv, last_k=opt.last_k)
-        self.model = load_model(self.model, opt.load_model)      # always loads, like the reference (:24)
-        self.model = self.model.to(opt.device)
-        self.model.eval()
+        net = create_model(opt.arch, opt.heads, opt.head_conv, last_k=opt.last_k)
+        net = load_model(net, opt.load_model)            # a checkpoint is always loaded, like the reference (:24)
+        self.model = net.to(opt.device).eval()
         self.max_per_image = 900
         self.opt = opt
         self.pause = True
 
+    # ---- hooks of the concrete detectors (tomo_det.py, tomo_det_classify.py) ----
     def process(self, images, return_time=False):
         raise NotImplementedError
 
@@ -42,23 +59,19 @@ class BaseDetector(object):
         raise NotImplementedError
 
     def run(self, image_or_path_or_tensor, meta=None):
-        """base_detector.py:62-106.  H2D copy -> process -> post_process -> save_detection."""
-        load_time = pre_time = net_time = dec_time = post_time = tot_time = 0
-        start_time = time.time()
-        loaded_time = time.time()
-        load_time += loaded_time - start_time
-        images = image_or_path_or_tensor.to(self.opt.device, non_blocking=True)
-        pre_process_time = time.time()
-        output, dets, hm, forward_time = self.process(images, return_time=True)
-        batch, cat, depth, height, width = hm.size()
-        net_time += forward_time - pre_process_time
-        decode_time = time.time()
-        dec_time += decode_time - forward_time
+        """One tomogram through the whole chain; stage times as in base_detector.py:62-106."""
+        clock = _Laps()
+        stats = {"load": clock.lap(), "pre": 0}
+        volume = image_or_path_or_tensor.to(self.opt.device, non_blocking=True)
+        clock.lap()                                      # the copy is not attributed to a stage in the reference either
+        output, dets, hm, t_forward = self.process(volume, return_time=True)
+        stats["net"] = clock.lap(t_forward)              # process() synchronises before taking t_forward
+        stats["dec"] = clock.lap()
         if self.opt.debug >= 2:
-            self.debug(None, images, dets, output)
+            self.debug(None, volume, dets, output)
+        depth = hm.size(2)                               # hm is (batch, cat, depth, height, width)
         dets, name = self.post_process(dets, meta, z_dim_tot=depth)
         torch.cuda.synchronize()
-        post_time += time.time() - decode_time
         self.save_detection(hm, dets, self.opt.out_path, meta, name=name)
-        tot_time += time.time() - start_time
-        return {"tot_time": tot_time, "load": load_time, "pre": pre_time, "net": net_time, "dec": dec_time}
+        stats["tot_time"] = clock.total()
+        return {k: stats[k] for k in ("tot_time", "load", "pre", "net", "dec")}
