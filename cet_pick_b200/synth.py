@@ -245,3 +245,75 @@ def fullres_stub_model():
             return [{"hm": y[:, None]}]
 
     return FullResStub()
+
+
+# --------------------------------------------------------------------------- SimSiam 3-D encoder (oracle groundwork)
+def simsiam3d_param_shapes(layers=(2, 2, 2), heads=("proj", "pred")):
+    """state_dict keys and shapes of cet_pick/models/networks/simsiam_model.py:159-235 `TomoResClassifier`
+    (BasicBlock, three stages; arch `simsiam3d_18` / `simsiam_18`), in registration order."""
+    sh = OrderedDict()
+
+    def bn(prefix, c, affine=True):
+        if affine:
+            sh[prefix + ".weight"] = (c,)
+            sh[prefix + ".bias"] = (c,)
+        sh[prefix + ".running_mean"] = (c,)
+        sh[prefix + ".running_var"] = (c,)
+        sh[prefix + ".num_batches_tracked"] = ()
+
+    sh["conv1.weight"] = (64, 1, 7, 7)
+    bn("bn1", 64)
+    inpl = 64
+    for li, (planes, nblk) in enumerate(zip((64, 128, 256), layers), start=1):
+        for b in range(nblk):
+            p = f"layer{li}.{b}"
+            stride_or_widen = (b == 0) and (li > 1 or inpl != planes)
+            sh[p + ".conv1.weight"] = (planes, inpl if b == 0 else planes, 3, 3)
+            bn(p + ".bn1", planes)
+            sh[p + ".conv2.weight"] = (planes, planes, 3, 3)
+            bn(p + ".bn2", planes)
+            if stride_or_widen:
+                sh[p + ".downsample.0.weight"] = (planes, inpl, 1, 1)
+        inpl = planes
+    sh["feature_3d.0.weight"] = (256, 256, 3, 3, 3)
+    bn("feature_3d.1", 256)
+    sh["fc.weight"] = (256, 256)
+    sh["fc.bias"] = (256,)
+    if "proj" in heads:
+        for i in (0, 3, 6):
+            sh[f"proj.{i}.weight"] = (256, 256)
+            bn(f"proj.{i + 1}", 256, affine=(i != 6))
+    if "pred" in heads:
+        sh["pred.0.weight"] = (256, 256)
+        bn("pred.1", 256)
+        sh["pred.3.weight"] = (256, 256)
+        sh["pred.3.bias"] = (256,)
+    return sh
+
+
+def simsiam3d_state_dict_torch(seed: int = 5, layers=(2, 2, 2), heads=("proj", "pred")):
+    """Seeded non-degenerate weights for the shapes above (BN statistics away from identity), as torch tensors."""
+    import torch
+    shapes = simsiam3d_param_shapes(layers, heads)
+    sd, off = OrderedDict(), 0
+    for name, shape in shapes.items():
+        n = int(np.prod(shape)) if shape else 1
+        u = uniform_np(seed, n, off)
+        off += n + 7
+        prefix = name.rsplit(".", 1)[0]
+        is_bn = (prefix + ".running_mean") in shapes
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.tensor(1)
+            continue
+        if name.endswith("running_var") or (is_bn and name.endswith(".weight")):
+            v = np.float32(0.5) + u
+        elif name.endswith("running_mean") or (is_bn and name.endswith(".bias")):
+            v = (u - np.float32(0.5)) * np.float32(0.4)
+        elif name.endswith(".bias"):
+            v = (u - np.float32(0.5)) * np.float32(0.2)
+        else:
+            rf = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+            bound = math.sqrt(6.0 / (shape[1] * rf + shape[0] * rf))
+            v = (u - np.float32(0.5)) * np.float32(2.0 * bound)
+        sd[name] = torch.from_numpy(v.astype(np.float32).reshape(shape).copy())
+    return sd
