@@ -267,3 +267,17 @@ def test_sieve_dense_hits_hand_over_to_scan(dec, do):
     assert np.array_equal(bits(out), bits(do.tomo_decode(hm.cpu().numpy(), 3, None, 900)))
     flags, _ = dec.decode_status()
     assert flags == 0
+
+
+@pytest.mark.parametrize("shape", [(12, 64, 64), (40, 256, 256)])
+def test_large_K_takes_the_sort_path(dec, do, shape):
+    """K above the rank-sort limit (16 384): the one-CTA bitonic sort writes the picks; small volume = collect-all
+    path, large volume = sieve path without the fast final select."""
+    D, H, W = shape
+    K = 20000
+    hm = synth.heatmap_tiefree_np(D, H, W, 77)[None, None]
+    out = dec.tomo_decode(cu(hm), kernel=3, K=K).cpu().numpy()
+    ref = do.tomo_decode(hm, 3, None, K)
+    n = int((ref[0, :, 3] > 0).sum())
+    assert np.array_equal(bits(out[:, :n]), bits(ref[:, :n]))
+    assert np.array_equal(bits(out), bits(ref))            # zero-score filler rows are canonical in both (index order)
