@@ -201,3 +201,20 @@ def test_batch_of_two_volumes():
     for i in range(2):
         one = m(x[i:i + 1])[-1]
         assert torch.equal(both["hm"][i], one["hm"][0]) and torch.equal(both["proj"][i], one["proj"][0])
+
+
+def test_unet5_medium_vs_oracle():
+    """unet_5 (five levels, 512 channels at the bottom) on a volume with several tiles per level, odd sizes on
+    the way down (ceil-mode pools, autocrop on the way up)."""
+    from oracle import unet_oracle as uo
+    D, H, W = 3, 104, 136
+    sd = synth.unet_state_dict_torch(11, 5)
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, 6))[None]
+    with torch.no_grad():
+        ref = uo.forward(x, sd)
+    m = build_model(5, 11)
+    out = m(x.cuda())[-1]
+    err = (out["hm"].cpu() - ref["hm"]).abs().max().item()
+    perr = (out["proj"].cpu() - ref["proj"]).abs().max().item()
+    print(f"unet_5 medium: raw hm err {err:.3e}, proj err {perr:.3e}")
+    assert err <= HM_TOL_RAW and perr <= 5e-2
