@@ -281,3 +281,13 @@ def test_large_K_takes_the_sort_path(dec, do, shape):
     n = int((ref[0, :, 3] > 0).sum())
     assert np.array_equal(bits(out[:, :n]), bits(ref[:, :n]))
     assert np.array_equal(bits(out), bits(ref))            # zero-score filler rows are canonical in both (index order)
+
+
+def test_sieve_batch_of_two_reuses_the_workspace(dec, do):
+    """B = 2 at a size that takes the sieve path: the second element starts from a freshly initialised state
+    (running threshold, histogram, density watchdog) in the same workspace."""
+    D, H, W, K = 40, 256, 256, 500
+    hm = np.stack([synth.heatmap_tiefree_np(D, H, W, s) for s in (41, 42)])[:, None]
+    hm[1] = np.minimum(hm[1], np.float32(0.9))            # a plateau at the top in the second element only
+    out = dec.tomo_decode(cu(hm), kernel=3, K=K).cpu().numpy()
+    assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, K)))
