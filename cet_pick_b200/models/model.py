@@ -22,46 +22,49 @@ def create_model(arch, heads, head_conv, last_k=0, local_path=None):
                      local_path=local_path)
 
 
-def load_model(model, model_path, optimizer=None, resume=False, lr=None, lr_step=None, model_only=False):
-    """Same checkpoint contract as the reference: dict with 'epoch' and 'state_dict'; a leading
-    'module.' is stripped; shape mismatches and missing keys fall back to the model's own values."""
-    start_epoch = 0
-    checkpoint = torch.load(model_path, map_location=lambda storage, loc: storage)
-    print("Loaded {}, epoch {}".format(model_path, checkpoint["epoch"]))
-    state_dict_ = checkpoint["state_dict"]
-    state_dict = {}
-    for k in state_dict_:
-        if k.startswith("module") and not k.startswith("module_list"):
-            state_dict[k[7:]] = state_dict_[k]
-        else:
-            state_dict[k] = state_dict_[k]
-    model_state_dict = model.state_dict()
-    msg = ("If you see this, your model does not fully load the pre-trained weight. Please make sure "
-           "you have correctly specified --arch xxx or set the correct --num_classes for your own dataset.")
-    for k in state_dict:
-        if k in model_state_dict:
-            if state_dict[k].shape != model_state_dict[k].shape:
-                print("Skip loading parameter {}, required shape{}, loaded shape{}. {}".format(
-                    k, model_state_dict[k].shape, state_dict[k].shape, msg))
-                state_dict[k] = model_state_dict[k]
-        else:
-            print("Drop parameter {}.".format(k) + msg)
-    for k in model_state_dict:
-        if k not in state_dict:
-            print("No param {}.".format(k) + msg)
-            state_dict[k] = model_state_dict[k]
-    model.load_state_dict(state_dict, strict=False)
+_HINT = ("the checkpoint does not cover the whole model: check --arch (and the head sizes) against the ones it "
+         "was trained with")
 
+
+def _without_data_parallel_prefix(sd):
+    """keys saved from nn.DataParallel carry a leading 'module.' (but 'module_list...' is a real name)"""
+    return {(k[7:] if k.startswith("module") and not k.startswith("module_list") else k): v for k, v in sd.items()}
+
+
+def _reconcile(loaded, own):
+    """The reference's tolerant load (model.py:207-230): tensors whose shape does not fit, and tensors the
+    checkpoint lacks, keep the model's own values; extra tensors are dropped by the non-strict load."""
+    merged = dict(loaded)
+    for k, v in loaded.items():
+        if k not in own:
+            print(f"Drop parameter {k}: {_HINT}")
+        elif v.shape != own[k].shape:
+            print(f"Skip loading parameter {k}: model has {tuple(own[k].shape)}, checkpoint has {tuple(v.shape)}; {_HINT}")
+            merged[k] = own[k]
+    for k, v in own.items():
+        if k not in merged:
+            print(f"No param {k}: {_HINT}")
+            merged[k] = v
+    return merged
+
+
+def load_model(model, model_path, optimizer=None, resume=False, lr=None, lr_step=None, model_only=False):
+    """Checkpoint contract of the reference (model.py:195-251): a dict with 'epoch' and 'state_dict' (+ 'optimizer');
+    returns the model, or (model, optimizer, start_epoch) when an optimizer is passed and `model_only` is false."""
+    ckpt = torch.load(model_path, map_location="cpu")
+    print(f"Loaded {model_path}, epoch {ckpt['epoch']}")
+    model.load_state_dict(_reconcile(_without_data_parallel_prefix(ckpt["state_dict"]), model.state_dict()), strict=False)
+    start_epoch = 0
     if optimizer is not None and resume:
-        if "optimizer" in checkpoint:
-            optimizer.load_state_dict(checkpoint["optimizer"])
-            start_epoch = checkpoint["epoch"]
+        if "optimizer" in ckpt:
+            optimizer.load_state_dict(ckpt["optimizer"])
+            start_epoch = ckpt["epoch"]
+            # the step schedule is replayed: x0.1 for every milestone already passed (:237-243)
             start_lr = lr
-            for step in lr_step:
-                if start_epoch >= step:
-                    start_lr *= 0.1
-            for param_group in optimizer.param_groups:
-                param_group["lr"] = start_lr
+            for _ in (step for step in lr_step if start_epoch >= step):
+                start_lr *= 0.1                       # repeated product, like the reference (same float)
+            for group in optimizer.param_groups:
+                group["lr"] = start_lr
             print("Resumed optimizer with start lr", start_lr)
         else:
             print("No optimizer parameters in checkpoint.")

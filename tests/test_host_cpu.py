@@ -59,3 +59,32 @@ def test_loader_and_image_have_no_cpu_path():
         loader.preprocess(np.zeros((2, 4, 4), np.float32))
     with pytest.raises(RuntimeError):
         image.get_potential_coords_pyramid(np.zeros((40, 80, 80)))
+
+
+def test_load_model_contract(tmp_path, capsys):
+    """models/model.py:195-251: 'module.' prefix stripped, shape mismatches and missing keys keep the model's own
+    tensors, extra keys dropped, optimizer resume replays the lr schedule."""
+    import torch
+    from cet_pick_b200 import synth
+    from cet_pick_b200.models.model import create_model, load_model, save_model
+    m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+    sd = synth.unet_state_dict_torch(317, 4)
+    own_hm = m.state_dict()["hm.weight"].clone()
+    bad = {("module." + k): v for k, v in sd.items()}
+    bad["module.hm.weight"] = torch.zeros(2, 32, 3, 1, 1)             # wrong shape -> skipped
+    del bad["module.conv1.weight"]                                     # missing -> kept
+    bad["module.extra.weight"] = torch.zeros(3)                        # unknown -> dropped
+    own_c1 = m.state_dict()["conv1.weight"].clone()
+    p = str(tmp_path / "c.pth")
+    torch.save({"epoch": 7, "state_dict": bad}, p)
+    m2 = load_model(m, p)
+    out = capsys.readouterr().out
+    assert "Skip loading parameter hm.weight" in out and "No param conv1.weight" in out and "Drop parameter extra.weight" in out
+    got = m2.state_dict()
+    assert torch.equal(got["hm.weight"], own_hm) and torch.equal(got["conv1.weight"], own_c1)
+    assert torch.equal(got["unet.down_convs.0.conv1.weight"], sd["unet.down_convs.0.conv1.weight"])
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    save_model(p, 450, m, opt)
+    m3, opt3, ep = load_model(m, p, optimizer=torch.optim.Adam(m.parameters(), lr=1.0), resume=True, lr=1e-3,
+                              lr_step=[200, 400, 600])
+    assert ep == 450 and abs(opt3.param_groups[0]["lr"] - 1e-5) < 1e-12
