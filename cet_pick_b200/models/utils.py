@@ -16,19 +16,15 @@ def _sigmoid(x: torch.Tensor) -> torch.Tensor:
 
 
 def _gather_feat(feat, ind, mask=None):
-    """models/utils.py:171-181 (index glue; plain tensor indexing, no arithmetic)."""
-    dim = feat.size(2)
-    ind = ind.unsqueeze(2).expand(ind.size(0), ind.size(1), dim)
-    feat = feat.gather(1, ind)
-    if mask is not None:
-        mask = mask.unsqueeze(2).expand_as(feat)
-        feat = feat[mask].view(-1, dim)
-    return feat
+    """models/utils.py:171-181: rows `ind` (N, K) of feat (N, M, C) -> (N, K, C); with a boolean `mask` (N, K)
+    only the selected rows, flattened to (n_selected, C)."""
+    picked = torch.take_along_dim(feat, ind.unsqueeze(-1), dim=1)
+    return picked if mask is None else picked[mask.bool()]
 
 
 def _transpose_and_gather_feat(feat, ind):
-    """models/utils.py:186-193.  tomo_decode does not use this (the CUDA pick writer gathers `reg`
-    directly at the linear index); kept for API parity."""
-    feat = feat.permute(0, 2, 3, 4, 1).contiguous()
-    feat = feat.view(feat.size(0), -1, feat.size(4))
-    return _gather_feat(feat, ind)
+    """models/utils.py:186-193: (N, C, D, H, W) feature map sampled at flat voxel indices `ind` (N, K) -> (N, K, C).
+    tomo_decode itself does not need this (the CUDA pick writer gathers `reg` at the linear index); kept for API
+    parity."""
+    n, c = feat.shape[:2]
+    return _gather_feat(feat.reshape(n, c, -1).transpose(1, 2), ind)

@@ -33,3 +33,19 @@ def test_parse_matches_reference(argv, tmp_path, monkeypatch):
     for k in ("save_dir", "debug_dir", "out_path"):          # same layout below the respective root
         if k in ref and k in ours:
             assert os.path.relpath(ref[k], ref["root_dir"]) == os.path.relpath(ours[k], ours["root_dir"])
+
+
+def test_gather_helpers_match_reference():
+    """models/utils.py:171-193 (`_gather_feat`, `_transpose_and_gather_feat`) on CPU tensors."""
+    import torch
+    u = refbridge.utils_module()
+    from cet_pick_b200.models import utils as ours
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(2, 3, 4, 5, 6, generator=g)
+    ind = torch.randint(0, 4 * 5 * 6, (2, 7), generator=g)
+    assert torch.equal(ours._transpose_and_gather_feat(feat, ind), u._transpose_and_gather_feat(feat, ind))
+    flat = torch.randn(2, 50, 3, generator=g)
+    idx = torch.randint(0, 50, (2, 9), generator=g)
+    mask = torch.rand(2, 9, generator=g) > 0.4
+    assert torch.equal(ours._gather_feat(flat, idx), u._gather_feat(flat, idx))
+    assert torch.equal(ours._gather_feat(flat, idx, mask), u._gather_feat(flat, idx, mask))
