@@ -64,3 +64,32 @@ def test_forward_against_live_reference(n_blocks, shape):
         out = uo.forward(x, sd)
     assert (out["hm"] - ref["hm"]).abs().max().item() <= 1e-5
     assert (out["proj"] - ref["proj"]).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("shape,sigma,tilt", [((9, 20, 22), 0.8, False), ((7, 16, 30), 0.0, False), ((12, 14, 14), 2.2, False),
+                                              ((5, 18, 20), 1.0, True), ((4, 24, 16), 0.0, True)])
+def test_preprocess_against_live_reference(shape, sigma, tilt):
+    """utils/loader.py:90-121 on arrays (no file involved): reconstruction and tilt branches."""
+    refbridge.install()
+    import cet_pick.utils.loader as rl
+    from oracle import preproc_oracle as po
+    rec = (synth.tomogram_np(*shape, 3).astype(np.float64) - 0.4) * 3.0
+    ref = rl.preprocess(rec.copy(), denoise=sigma, is_tilt=tilt)
+    if tilt:
+        out = po.preprocess_tilt(rec.copy(), sigma)
+        assert out.dtype == ref.dtype == np.float32 and np.abs(out - ref).max() <= 1.2e-7
+    else:
+        assert np.array_equal(po.preprocess(rec.copy(), sigma), ref)
+
+
+@pytest.mark.parametrize("shape,params", [((33, 70, 50), (16, 24, 8, 12)), ((10, 30, 31), (32, 96, 16, 24))])
+def test_patch_dataset_against_live_reference(shape, params):
+    refbridge.install()
+    from cet_pick.detectors.tomo_det_classify import PatchDataset
+    from oracle import classify_oracle as co
+    vol = synth.heatmap_tiefree_np(*shape, 2)
+    ds = PatchDataset(vol, *params)
+    for n in range(len(ds)):
+        idx, x = ds[n]
+        oi, ox, grid = co.patch(vol, n, *params)
+        assert np.array_equal(idx, oi) and np.array_equal(x, ox) and tuple(grid) == tuple(ds.shape)
