@@ -120,3 +120,37 @@ def test_pipeline_mrc_to_pick_file(tmp_path, monkeypatch):
     with torch.no_grad():
         hm_ref = uo.sigmoid_clamp(uo.forward(torch.from_numpy(ref_vol)[None], sd, want_proj=False)["hm"]).numpy()[0, 0]
     assert np.abs(np.swapaxes(hm_file, 1, 0) - hm_ref).max() <= 1e-2
+
+
+def test_command_line_entry(tmp_path, monkeypatch):
+    """`python -m cet_pick_b200.test semi ...` (the reference's test.py command line): image list -> MRC -> GPU
+    pre-processing -> detector -> pick files and opt.txt, for two tomograms."""
+    from cet_pick_b200 import synth
+    from cet_pick_b200 import test as cli
+    from cet_pick_b200.opts import opts
+    from cet_pick_b200.utils import mrcio
+    sd = synth.unet_state_dict_torch(317, 4)
+    ckpt = os.path.join(tmp_path, "model.pth")
+    torch.save({"epoch": 1, "state_dict": sd}, ckpt)
+    monkeypatch.chdir(tmp_path)
+    paths = []
+    for i in range(2):
+        raw = (synth.tomogram_np(64, 24, 96, 20 + i) * 900 - 300).astype(np.float32)      # stored as (x, z, y): order xzy
+        paths.append(os.path.join(tmp_path, f"t{i}.mrc"))
+        mrcio.write_mrc(paths[-1], raw)
+    lst = os.path.join(tmp_path, "test_images.txt")
+    with open(lst, "w") as f:
+        f.write("image_name\trec_path\n" + "".join(f"tomo{i}\t{p}\n" for i, p in enumerate(paths)))
+    K = 400
+    opt = opts().init(["semi", "--arch", "unet_4", "--load_model", ckpt, "--K", str(K), "--out_thresh", "0.0", "--cutoff_z", "0",
+                       "--with_score", "--compress", "--gauss", "0.8", "--test_img_txt", lst, "--out_id", "out",
+                       "--exp_id", "cli", "--gpus", "0"])
+    stats = cli.test(opt)
+    assert len(stats["tot_time"]) == 2 and os.path.exists(os.path.join(opt.save_dir, "opt.txt"))
+    n_lines = 0
+    for i in range(2):
+        lines = open(os.path.join(opt.out_path, f"tomo{i}.txt")).read().splitlines()
+        assert len(lines) <= K and all(len(ln.split("\t")) == 4 for ln in lines)      # the writer drops the 20-pixel border
+        n_lines += len(lines)
+        assert mrcio.read_mrc(os.path.join(opt.out_path, f"tomo{i}_hm.mrc")).shape == (32, 12, 48)     # (H', D, W')
+    assert n_lines > 0
