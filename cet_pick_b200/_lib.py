@@ -49,6 +49,7 @@ SIGNATURES = {
     "cetpick_unet_finalize": (_int, [_vp]),
     "cetpick_unet_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
+    "cetpick_unet_forward_u8": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_profile_enable": (_int, [_int]),
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "cetpick_conv_halo_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "cetpick_probe_mma_rate": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
+    "cetpick_probe_mma_rate2": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,
                                  _vp, _int, _int, _vp, _int, _int, _int, _int, _vp]),
 }
@@ -110,6 +112,11 @@ def require_cuda(t, what: str):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: tensor is on {t.device}; cet_pick_b200 runs on CUDA (sm_100a) only "
                            "and has no CPU fallback")
+    import torch
+    if t.device.index != torch.cuda.current_device():
+        # plans, workspaces and the launch stream belong to the current device (one process per GPU)
+        raise RuntimeError(f"{what}: tensor is on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device first")
 
 
 def stream_ptr():

@@ -49,15 +49,24 @@ constexpr int A_STAGE = MT * A_TILE;
 constexpr int A_STAGES = 4;
 constexpr int W_BYTES = 4 * COUT * 32;      // [4 slots][16 co][16 k] bf16
 constexpr int SMEM_BYTES = 1024 + 1024 * ((W_BYTES + 1023) / 1024) + A_STAGES * A_STAGE + RAW_STAGES * RAW_STAGE;
+// uint8 input (quantised tomogram, loader.py:16-25,117-120): a box row is 144 bytes (64 output pixels read
+// 2*63 + 8 = 134 columns; box widths are multiples of 16 bytes); the converters map level -> bf16 through a
+// per-lane copy of the 256-entry table (bank = lane: conflict-free), kept behind the raw stages.
+constexpr int U8_ROW_BYTES = 144;
+constexpr int U8_BOX_BYTES = 2 * U8_ROW_BYTES;
+constexpr int U8_BOX_STRIDE = 384;
+constexpr int LUT_BYTES = 256 * 32 * 4;
+constexpr int SMEM_BYTES_U8 = SMEM_BYTES + LUT_BYTES;
 
 struct alignas(64) StemParams {
-  CUtensorMap tmIn;     // fp32 (W,H,D), box (BOX_W, 2, 1), zero fill
+  CUtensorMap tmIn;     // fp32 (W,H,D), box (BOX_W, 2, 1), zero fill  |  uint8 (W,H,D), box (144, 2, 1), zero fill
   CUtensorMap tmW;      // bf16 (16, 64), SWIZZLE_32B
   int D, H, W, h, w;
   int R, nchunk, nxb;   // rows per strip, strips along y, 256-pixel blocks along x
   long long total_strips;
   float bias_c[16];
   __nv_bfloat16* out;
+  uint16_t lut[256];    // uint8 input: bf16 bits of level k (lut[0] == 0: the conv's zero padding is level 0)
 };
 
 struct Strip { int ma, mb, x0, z, j_lo, j_hi; };
@@ -82,7 +91,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemParams p) {
+  constexpr int BSTRIDE = U8 ? U8_BOX_STRIDE : BOX_STRIDE;
+  constexpr int BBYTES = U8 ? U8_BOX_BYTES : BOX_BYTES;
+  constexpr int RSTAGE = NBOX * BSTRIDE;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
   __shared__ __align__(8) uint64_t a_full[A_STAGES], a_empty[A_STAGES];
@@ -93,6 +106,9 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
   uint8_t* sW = smem;
   uint8_t* sA = smem + 1024 * ((W_BYTES + 1023) / 1024);
   uint8_t* sRaw = sA + A_STAGES * A_STAGE;
+  uint32_t* sLut = reinterpret_cast<uint32_t*>(sRaw + RAW_STAGES * RAW_STAGE);   // [256 levels][32 lanes]
+  if (U8)
+    for (int i = threadIdx.x; i < 256 * 32; i += STEM_THREADS) sLut[i] = p.lut[i >> 5];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -139,11 +155,11 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
         decode_strip(p, k, s);
         for (int j = s.j_lo; j <= s.j_hi; ++j) {
           ptx::mbar_wait(&raw_empty[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(NBOX * BOX_BYTES));
-          uint8_t* dst = sRaw + (size_t)stage * RAW_STAGE;
+          ptx::mbar_arrive_expect_tx(&raw_full[stage], (uint32_t)(NBOX * BBYTES));
+          uint8_t* dst = sRaw + (size_t)stage * RSTAGE;
 #pragma unroll
           for (int b = 0; b < NBOX; ++b)
-            ptx::tma_load_3d(dst + b * BOX_STRIDE, &p.tmIn, &raw_full[stage], 2 * (s.x0 + b * 64) - 4, 2 * j, s.z);
+            ptx::tma_load_3d(dst + b * BSTRIDE, &p.tmIn, &raw_full[stage], 2 * (s.x0 + b * 64) - 4, 2 * j, s.z);
           if (++stage == RAW_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -197,7 +213,9 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     // ================================ converters ==================================
     const int c = threadIdx.x - 128;
     const int t = c >> 7, px = c & 127, hb = px >> 6, pp = px & 63;
-    const uint32_t raw_off = (uint32_t)((t * 2 + hb) * BOX_STRIDE + pp * 8);
+    const uint32_t raw_off = U8 ? (uint32_t)((t * 2 + hb) * BSTRIDE + ((pp * 2) & ~3)) : (uint32_t)((t * 2 + hb) * BSTRIDE + pp * 8);
+    const uint32_t u8_shift = (uint32_t)((pp * 2) & 3) * 8u;     // the pixel's 8 bytes start 0 or 2 bytes into an aligned word
+    const uint32_t* lut = sLut + lane;
     const uint32_t a_row = (uint32_t)(px * 32);
     // SWIZZLE_32B: 16-byte chunk index (address bit 4) ^= address bit 7; tiles are 1024-byte aligned
     const uint32_t a_off0 = (uint32_t)(t * A_TILE) + (a_row ^ (((a_row >> 7) & 1u) << 4));
@@ -209,19 +227,40 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
       decode_strip(p, k, s);
       for (int j = s.j_lo; j <= s.j_hi; ++j) {
         ptx::mbar_wait(&raw_full[stage], phase);
-        const uint8_t* src = sRaw + (size_t)stage * RAW_STAGE + raw_off;
-        float2 f[2][4];
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) f[e][i] = *reinterpret_cast<const float2*>(src + e * ROW_BYTES + i * 8);
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&raw_empty[stage]);
+        const uint8_t* src = sRaw + (size_t)stage * RSTAGE + raw_off;
         uint4 c0, c1;
-        c0.x = pack2(f[0][0].x, f[0][0].y); c0.y = pack2(f[0][1].x, f[0][1].y);
-        c0.z = pack2(f[0][2].x, f[0][2].y); c0.w = pack2(f[0][3].x, f[0][3].y);
-        c1.x = pack2(f[1][0].x, f[1][0].y); c1.y = pack2(f[1][1].x, f[1][1].y);
-        c1.z = pack2(f[1][2].x, f[1][2].y); c1.w = pack2(f[1][3].x, f[1][3].y);
+        if (U8) {
+          uint32_t w[2][3];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) w[e][i] = *reinterpret_cast<const uint32_t*>(src + e * U8_ROW_BYTES + i * 4);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&raw_empty[stage]);
+          uint32_t o[2][4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const uint32_t lo = __funnelshift_r(w[e][0], w[e][1], u8_shift), hi = __funnelshift_r(w[e][1], w[e][2], u8_shift);
+            o[e][0] = lut[(lo & 0xffu) << 5] | (lut[((lo >> 8) & 0xffu) << 5] << 16);
+            o[e][1] = lut[((lo >> 16) & 0xffu) << 5] | (lut[(lo >> 24) << 5] << 16);
+            o[e][2] = lut[(hi & 0xffu) << 5] | (lut[((hi >> 8) & 0xffu) << 5] << 16);
+            o[e][3] = lut[((hi >> 16) & 0xffu) << 5] | (lut[(hi >> 24) << 5] << 16);
+          }
+          c0 = make_uint4(o[0][0], o[0][1], o[0][2], o[0][3]);
+          c1 = make_uint4(o[1][0], o[1][1], o[1][2], o[1][3]);
+        } else {
+          float2 f[2][4];
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[e][i] = *reinterpret_cast<const float2*>(src + e * ROW_BYTES + i * 8);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&raw_empty[stage]);
+          c0.x = pack2(f[0][0].x, f[0][0].y); c0.y = pack2(f[0][1].x, f[0][1].y);
+          c0.z = pack2(f[0][2].x, f[0][2].y); c0.w = pack2(f[0][3].x, f[0][3].y);
+          c1.x = pack2(f[1][0].x, f[1][0].y); c1.y = pack2(f[1][1].x, f[1][1].y);
+          c1.z = pack2(f[1][2].x, f[1][2].y); c1.w = pack2(f[1][3].x, f[1][3].y);
+        }
         ptx::mbar_wait(&a_empty[astage], aphase ^ 1u);
         uint8_t* dst = sA + (size_t)astage * A_STAGE;
         *reinterpret_cast<uint4*>(dst + a_off0) = c0;
@@ -283,6 +322,10 @@ bool stem_tc_supported(const float* in, int W) {
   return (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
 }
 
+bool stem_tc_supported_u8(const uint8_t* in, int W) {
+  return (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+}
+
 std::vector<uint16_t> stem_pack_weights(const float* w, const double* scale) {
   std::vector<uint16_t> out((size_t)4 * COUT * 16, 0);
   for (int d = 0; d < 4; ++d)
@@ -298,15 +341,19 @@ std::vector<uint16_t> stem_pack_weights(const float* w, const double* scale) {
 }
 
 int conv_stem_launch(const StemLaunch& L, cudaStream_t stream) {
-  if (!L.in || !L.wpk || !L.out || L.D <= 0 || L.H <= 0 || L.W <= 0) return CETPICK_ERR_BAD_ARG;
-  if (!stem_tc_supported(L.in, L.W)) return CETPICK_ERR_UNSUPPORTED;
+  const bool u8 = L.in_u8 != nullptr;
+  if ((!L.in && !u8) || (L.in && u8) || !L.wpk || !L.out || L.D <= 0 || L.H <= 0 || L.W <= 0) return CETPICK_ERR_BAD_ARG;
+  if (u8 ? !stem_tc_supported_u8(L.in_u8, L.W) : !stem_tc_supported(L.in, L.W)) return CETPICK_ERR_UNSUPPORTED;
+  if (u8 && L.lut[0] != 0) return CETPICK_ERR_BAD_ARG;     // level 0 doubles as the zero padding
   static bool attr_done = false;
   if (!attr_done) {
-    CETPICK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CETPICK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CETPICK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_U8));
     attr_done = true;
   }
   StemParams p;
   memset(&p, 0, sizeof(p));
+  if (u8) memcpy(p.lut, L.lut, sizeof(p.lut));
   p.D = L.D; p.H = L.H; p.W = L.W;
   p.h = (L.H - 1) / 2 + 1; p.w = (L.W - 1) / 2 + 1;
   p.out = static_cast<__nv_bfloat16*>(L.out);
@@ -329,7 +376,12 @@ int conv_stem_launch(const StemLaunch& L, cudaStream_t stream) {
   p.R = ceil_div(p.h, best_n);
   p.total_strips = base_strips * p.nchunk;
   int rc;
-  {
+  if (u8) {
+    const uint64_t dims[3] = {(uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.D};
+    const uint64_t strides[2] = {(uint64_t)L.W, (uint64_t)L.W * L.H};
+    const uint32_t box[3] = {(uint32_t)U8_ROW_BYTES, 2, 1};
+    if ((rc = tmap_encode_u8_zerofill(&p.tmIn, L.in_u8, 3, dims, strides, box))) return rc;
+  } else {
     const uint64_t dims[3] = {(uint64_t)L.W, (uint64_t)L.H, (uint64_t)L.D};
     const uint64_t strides[2] = {(uint64_t)L.W * 4, (uint64_t)L.W * L.H * 4};
     const uint32_t box[3] = {(uint32_t)BOX_W, 2, 1};
@@ -342,7 +394,8 @@ int conv_stem_launch(const StemLaunch& L, cudaStream_t stream) {
     if ((rc = tmap_encode_bf16(&p.tmW, L.wpk, 2, dims, strides, box, 16))) return rc;
   }
   const int grid = (int)std::min<long long>(p.total_strips, sms);
-  stem_tc_kernel<<<grid, STEM_THREADS, SMEM_BYTES, stream>>>(p);
+  if (u8) stem_tc_kernel<true><<<grid, STEM_THREADS, SMEM_BYTES_U8, stream>>>(p);
+  else stem_tc_kernel<false><<<grid, STEM_THREADS, SMEM_BYTES, stream>>>(p);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }

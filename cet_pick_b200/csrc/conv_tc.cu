@@ -326,6 +326,22 @@ int tmap_encode_f32_zerofill(CUtensorMap* tm, const void* base, int rank, const 
   return CETPICK_OK;
 }
 
+// uint8 tiled tensor map, no swizzle, out-of-bounds elements read as zero (quantised-input stem)
+int tmap_encode_u8_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(u8) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
+  return CETPICK_OK;
+}
+
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
   if (L.KC != 16 && L.KC != 32 && L.KC != 64) return CETPICK_ERR_BAD_ARG;
   if (L.Ntot <= 0 || (L.Ntot % 16) || L.ntaps < 1 || L.ntaps > 27 || L.nsrc < 1 || L.nsrc > 2) return CETPICK_ERR_BAD_ARG;

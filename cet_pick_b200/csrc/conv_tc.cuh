@@ -44,6 +44,8 @@ int tmap_encode_f32_nanfill(CUtensorMap* tm, const void* base, int rank, const u
                             const uint64_t* strides_bytes, const uint32_t* box);
 
 // fp32 tiled tensor map without swizzle whose out-of-bounds elements read as zero.
+int tmap_encode_u8_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box);
 int tmap_encode_f32_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box);
 

@@ -118,6 +118,70 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(const RateParams p) {
   if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
+// Same probe for a CTA pair: tcgen05.mma.cta_group::2 (M = 256 over two SMs; each CTA supplies its own 128 rows
+// of A and N/2 rows of B).  The leader CTA's elected thread issues; out[pair] = cycles per MMA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_rate2_kernel(const RateParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  for (int i = threadIdx.x; i < (96 * 1024) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar_done, 1); ptx::fence_barrier_init(); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(&s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  ptx::tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp == 0 && cta_rank == 0) {
+    const uint32_t a_hi = ptx::smem_desc_hi((uint32_t)p.sbo_a, (uint32_t)p.layout_type);
+    const uint32_t b_hi = ptx::smem_desc_hi((uint32_t)(16 * p.KC), (uint32_t)p.layout_type);
+    const uint32_t a_lo = ptx::smem_desc_lo(ptx::smem_u32(smem));
+    const uint32_t b_lo = ptx::smem_desc_lo(ptx::smem_u32(smem + 64 * 1024));
+    const uint32_t idesc = ptx::make_idesc_bf16(256, p.N);
+    const int k16 = p.KC / 16;
+    long long t0 = 0, t1 = 0;
+    if (ptx::elect_one()) {
+      t0 = clock64();
+      int tap = 0, dst = 0, kk = 0;
+      for (int i = 0; i < p.iters; ++i) {
+        const uint32_t al = a_lo + (uint32_t)((tap * p.a_step + kk * 32) >> 4);
+        const uint32_t bl = b_lo + (uint32_t)(((tap * (p.N / 2) * p.KC * 2) % (24 * 1024) + kk * 32) >> 4);
+        asm volatile(
+            "{\n\t"
+            ".reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n\t"
+            "}\n" ::"r"(tmem + (uint32_t)(dst * p.N)),
+            "r"(al), "r"(a_hi), "r"(bl), "r"(b_hi), "r"(idesc)
+            : "memory");
+        if (++kk == k16) { kk = 0; if (++tap == p.ntap) { tap = 0; if (++dst == p.ndst) dst = 0; } }
+      }
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                       ptx::smem_u32(&bar_done)), "h"((uint16_t)1)
+                   : "memory");
+    }
+    __syncwarp();
+    ptx::mbar_wait(&bar_done, 0);
+    t1 = clock64();
+    long long mx = t0;
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) p.out[blockIdx.x >> 1] = (float)((double)(t1 - mx) / p.iters);
+  }
+  ptx::tc_fence_before();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -179,6 +243,23 @@ extern "C" int cetpick_probe_mma_rate(int N, int KC, int sbo_a, int a_step, int 
   const size_t smem = 97 * 1024 + 1024;
   CETPICK_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mma_rate_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+// Tuning hook: the same measurement for a CTA pair (tcgen05.mma.cta_group::2, M = 256).  grid = number of pairs.
+extern "C" int cetpick_probe_mma_rate2(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
+                                       float* out_cycles, int pairs, void* stream) {
+  if (!out_cycles || N < 32 || N > 256 || (N % 32) || (KC != 16 && KC != 32 && KC != 64) || ntap < 1 || ndst < 1 ||
+      ndst * N > 512 || iters < 1 || pairs < 1)
+    return CETPICK_ERR_BAD_ARG;
+  RateParams p;
+  p.N = N; p.KC = KC; p.sbo_a = sbo_a; p.a_step = a_step; p.ntap = ntap; p.ndst = ndst; p.iters = iters;
+  p.layout_type = KC == 64 ? 2 : KC == 32 ? 4 : 6;
+  p.out = out_cycles;
+  const size_t smem = 97 * 1024 + 1024;
+  CETPICK_CUDA(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_rate2_kernel<<<2 * pairs, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }

@@ -593,11 +593,13 @@ extern "C" int cetpick_unet_workspace_bytes(const cetpick_unet* m, int64_t D, in
   return CETPICK_OK;
 }
 
-extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t D64, int64_t H64, int64_t W64,
-                                    float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes,
-                                    void* stream) {
+namespace {
+int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8, const float* lut_host, int64_t D64,
+                      int64_t H64, int64_t W64, float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes,
+                      void* stream) {
   g_launches = 0;
-  if (!m || !tomo || !hm || D64 <= 0 || H64 <= 0 || W64 <= 0) return CETPICK_ERR_BAD_ARG;
+  if (!m || (!tomo && !tomo_u8) || !hm || D64 <= 0 || H64 <= 0 || W64 <= 0) return CETPICK_ERR_BAD_ARG;
+  if (tomo_u8 && (!lut_host || lut_host[0] != 0.f)) return CETPICK_ERR_BAD_ARG;
   if (!m->finalized) return CETPICK_ERR_STATE;
   if (proj && m->proj_c == 0) return CETPICK_ERR_STATE;
   if (D64 > 32767 || H64 > (1 << 20) || W64 > (1 << 20)) return CETPICK_ERR_BAD_ARG;
@@ -616,7 +618,14 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   {
     g_prof.begin();
     g_prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
-    if (stem_tc_supported(tomo, W)) {          // tensor-core march (conv_stem.cu)
+    if (tomo_u8) {                              // quantised levels straight into the tensor-core march
+      if (!stem_tc_supported_u8(tomo_u8, W)) return CETPICK_ERR_UNSUPPORTED;   // rows must be 16-byte aligned
+      StemLaunch SL;
+      SL.in_u8 = tomo_u8; SL.D = D; SL.H = H; SL.W = W; SL.wpk = blob + m->stem_tc_w; SL.out = buf(0, 0);
+      for (int k = 0; k < 256; ++k) SL.lut[k] = f2bf_host(lut_host[k]);
+      memcpy(SL.bias, m->stem_shift, sizeof(SL.bias));
+      if ((rc = conv_stem_launch(SL, st))) return rc;
+    } else if (stem_tc_supported(tomo, W)) {   // tensor-core march (conv_stem.cu)
       StemLaunch SL;
       SL.in = tomo; SL.D = D; SL.H = H; SL.W = W; SL.wpk = blob + m->stem_tc_w; SL.out = buf(0, 0);
       memcpy(SL.bias, m->stem_shift, sizeof(SL.bias));
@@ -703,6 +712,21 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
   }
   g_prof.mark("end", 0.0, st);
   return CETPICK_OK;
+}
+}  // namespace
+
+extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t D, int64_t H, int64_t W,
+                                    float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  if (!tomo) return CETPICK_ERR_BAD_ARG;
+  return unet_forward_impl(m, tomo, nullptr, nullptr, D, H, W, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
+}
+
+extern "C" int cetpick_unet_forward_u8(cetpick_unet* m, const uint8_t* tomo_q, const float* level_values_host,
+                                       int64_t D, int64_t H, int64_t W, float* hm, int apply_sigmoid, float* proj,
+                                       void* ws, size_t ws_bytes, void* stream) {
+  if (!tomo_q || !level_values_host) return CETPICK_ERR_BAD_ARG;
+  return unet_forward_impl(m, nullptr, tomo_q, level_values_host, D, H, W, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
 }
 
 extern "C" int cetpick_profile_enable(int on) {

@@ -63,6 +63,8 @@ class BaseDetector(object):
         clock = _Laps()
         stats = {"load": clock.lap(), "pre": 0}
         volume = image_or_path_or_tensor.to(self.opt.device, non_blocking=True)
+        # a uint8 volume holds the quantised levels of utils/loader.py:preprocess_levels; meta carries their values
+        self.model.level_values = meta.get("level_values") if isinstance(meta, dict) else None
         clock.lap()                                      # the copy is not attributed to a stage in the reference either
         output, dets, hm, t_forward = self.process(volume, return_time=True)
         stats["net"] = clock.lap(t_forward)              # process() synchronises before taking t_forward

@@ -117,8 +117,10 @@ class TomoClassdetDetector(BaseDetector):
     def save_detection(self, hm, dets, path, meta, prefix="", name=""):
         """:173-214 (plain and --with_score lines; the fiber / spike graph post-processing of the
         reference is host-side Python outside this path)."""
-        if not os.path.exists(path):
-            os.mkdir(path)
+        os.makedirs(path, exist_ok=True)            # every rank of a torchrun job writes into the same directory
+        if self.opt.fiber or self.opt.spike:
+            raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
+                                      "(utils/post_process.py:31-106; DESIGN.md)")
         hm = hm.detach().cpu().numpy()[0][0]
         max_z, max_y, max_x = hm.shape
         if np.isnan(hm).any():

@@ -89,6 +89,14 @@ def _topk(scores, K=900):
 
 def tomo_decode(heat, kernel=3, reg=None, K=900, if_fiber=False):
     """decode.py:123-155: (B,1,D,H,W) -> (B,K,5) rows [x+0.25|x+reg0, y+0.25|y+reg1, z, score, score]."""
+    if if_fiber and int(kernel) != 3:
+        # decode.py:126-128 with a (1,k,k) then (k,1,1) window: the fused scan keeps 3 planes in flight, so wider
+        # fiber windows run as the two suppression passes (csrc/decode.cu nms_full_kernel) + a plain top-K
+        if int(kernel) < 1 or int(kernel) % 2 == 0:
+            raise ValueError("tomo_decode: the NMS kernel must be odd (the reference's hmax == heat breaks otherwise)")
+        heat = _nms_z(_nms_xy(heat, kernel), kernel)
+        dets, _ = _decode_call(heat, 1, K, _lib.NMS_NONE, reg, False, "tomo_decode")
+        return dets
     mode = _lib.NMS_FIBER if if_fiber else _lib.NMS_3D
     dets, _ = _decode_call(heat, kernel, K, mode, reg, False, "tomo_decode")
     return dets

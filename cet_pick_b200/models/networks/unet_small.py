@@ -94,6 +94,10 @@ class TomoConvUNet(nn.Module):
         # +-3 slices (feature_head.0, feature_head.2, hm/proj: one slice each), so every slab is
         # forwarded with a 3-slice recompute halo and only its core slices are kept: exact.
         self.slab_z = None
+        # Quantised input: a uint8 tensor is read as the 256 levels utils/loader.py's preprocess ends with; level k
+        # stands for the float32 value level_values[k] (default k/255, i.e. levels spanning 0..255).  Lossless
+        # and a quarter of the host->device bytes of the float32 volume the reference ships.
+        self.level_values = None
         self.compute_proj = "proj" in heads      # detectors switch this off (they never read 'proj')
         self.fuse_sigmoid = False                # TomodetDetector fuses _sigmoid into the hm epilogue
         self._plan = None
@@ -166,7 +170,20 @@ class TomoConvUNet(nn.Module):
         if x.dim() == 3:
             x = x.unsqueeze(0)
         b, d, h, w = x.shape
-        x = x.to(torch.float32).contiguous()
+        lut = None
+        if x.dtype == torch.uint8:
+            import numpy as np
+            lv = self.level_values
+            lut = np.ascontiguousarray((np.arange(256, dtype=np.float64) / 255.0).astype(np.float32) if lv is None
+                                       else np.asarray(lv, dtype=np.float32))
+            if lut.shape != (256,) or lut[0] != 0:
+                raise ValueError("TomoConvUNet: level_values must be 256 float32 values with level_values[0] == 0")
+            if w % 16:        # the TMA path needs 16-byte aligned rows: expand the levels on the device instead
+                x, lut = torch.from_numpy(lut).to(x.device)[x.long()], None
+            else:
+                x = x.contiguous()
+        if lut is None:
+            x = x.to(torch.float32).contiguous()
         plan = self.plan()
         L = _lib.lib()
         oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
@@ -187,10 +204,15 @@ class TomoConvUNet(nn.Module):
         sig = 1 if self.fuse_sigmoid else 0
 
         def run(src, depth, hm_dst, proj_dst):
-            _lib.check(L.cetpick_unet_forward(plan, src.data_ptr(), depth, h, w, hm_dst.data_ptr(), sig,
-                                              proj_dst.data_ptr() if proj_dst is not None else None,
-                                              self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
-                       "cetpick_unet_forward")
+            pj = proj_dst.data_ptr() if proj_dst is not None else None
+            if lut is not None:
+                _lib.check(L.cetpick_unet_forward_u8(plan, src.data_ptr(), lut.ctypes.data_as(C.c_void_p), depth, h, w,
+                                                     hm_dst.data_ptr(), sig, pj, self._ws.data_ptr(),
+                                                     self._ws.numel(), _lib.stream_ptr()), "cetpick_unet_forward_u8")
+            else:
+                _lib.check(L.cetpick_unet_forward(plan, src.data_ptr(), depth, h, w, hm_dst.data_ptr(), sig, pj,
+                                                  self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                           "cetpick_unet_forward")
             self.last_launches += L.cetpick_last_launch_count()
             self.last_slabs += 1
 

@@ -44,11 +44,18 @@ def write_opt_file(opt):
 
 def test(opt):
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
+    # Device selection: under torchrun LOCAL_RANK wins (one process per GPU); otherwise the first id of `--gpus`
+    # picks the device, like the reference's CUDA_VISIBLE_DEVICES = opt.gpus_str (cet_pick/test.py:66).
+    if world > 1 or "LOCAL_RANK" in os.environ:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    else:
+        first_gpu = int(str(getattr(opt, "gpus_str", "0")).split(",")[0] or 0)
+        if first_gpu >= 0:
+            torch.cuda.set_device(first_gpu)
     print(opt)
     if rank == 0:
         write_opt_file(opt)
+    os.makedirs(opt.out_path, exist_ok=True)      # every rank: no rank may reach save_detection before the directory exists
     detector = detector_factory[opt.task](opt)
     items = read_image_list(os.path.join(opt.data_dir, opt.test_img_txt))
     first, count = shard_range(len(items), rank, world)

@@ -170,6 +170,29 @@ def preprocess(mrc, denoise=0, is_tilt=False, dtype=torch.float64):
     return out
 
 
+def preprocess_levels(mrc, denoise=0):
+    """`preprocess` (reconstruction branch) stopped one step early: -> (levels, level_values) with `levels` a uint8
+    CUDA tensor (q - q.min(), loader.py:106,120) and `level_values[k]` the float32 value the reference's float32
+    input holds for level k, float32((q - min) / (max - min)).  `level_values[levels]` == preprocess(...) cast to
+    float32 (datasets cast with astype(np.float32)); the detector takes the pair as is (TomoConvUNet.level_values)."""
+    x, _ = _to_device(mrc)
+    x = x.to(torch.float64)
+    if x.dim() != 3:
+        raise ValueError(f"preprocess_levels: expected a 3-D volume, got {tuple(x.shape)}")
+    if denoise > 0:
+        im, mi, ma = gaussian_filter(x, denoise), -3.0, 3.0
+    else:
+        im, mi, ma = x.clone(), -2.5, 2.0
+    _zscore_(im)
+    q = quantize(im, mi=mi, ma=ma)
+    lo, hi = (int(v) for v in torch.aminmax(q))
+    if hi == lo:
+        raise ZeroDivisionError("preprocess_levels: constant volume (the reference divides by max - min = 0)")
+    lv = np.zeros(256, dtype=np.float32)
+    lv[:hi - lo + 1] = (np.arange(hi - lo + 1, dtype=np.float64) / np.float64(hi - lo)).astype(np.float32)
+    return q - lo, lv
+
+
 def load_tomos_from_list(names, paths, order="xzy", compress=False, denoise=0, tilt=False, dtype=torch.float64):
     """loader.py:165-173."""
     images = {}

@@ -185,6 +185,17 @@ int cetpick_unet_forward(cetpick_unet* plan, const float* tomo, int64_t D, int64
                          float* hm, int apply_sigmoid, float* proj,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* Same forward from the QUANTISED tomogram.  cet_pick/utils/loader.py:90-121 `preprocess` ends with a 256-level
+ * uint8 quantisation and a min-max normalisation, so the float32 volume the reference feeds the detector holds at
+ * most 256 distinct values; shipping the levels is lossless and a quarter of the bytes across PCIe.
+ * tomo_q: (D,H,W) uint8 device, rows 16-byte aligned (W % 16 == 0, else CETPICK_ERR_UNSUPPORTED);
+ * level_values_host: HOST float32[256], the value the reference's float32 input holds for each level
+ * (level_values_host[0] must be 0: level 0 doubles as the convolution's zero padding).  The stem converts
+ * level -> bf16 operand exactly as the float32 entry point converts value -> bf16, so both give identical results. */
+int cetpick_unet_forward_u8(cetpick_unet* plan, const uint8_t* tomo_q, const float* level_values_host,
+                            int64_t D, int64_t H, int64_t W, float* hm, int apply_sigmoid, float* proj,
+                            void* ws, size_t ws_bytes, void* stream);
+
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);
@@ -255,6 +266,10 @@ int cetpick_probe_umma(const void* A_big, int R, const void* B, int KC, int r0, 
  * regions.  out_cycles: `grid` floats (device). */
 int cetpick_probe_mma_rate(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
                            float* out_cycles, int grid, void* stream);
+
+/* Same measurement for a CTA pair: tcgen05.mma.cta_group::2 (M = 256 over two SMs).  out_cycles: `pairs` floats. */
+int cetpick_probe_mma_rate2(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
+                            float* out_cycles, int pairs, void* stream);
 
 #ifdef __cplusplus
 }

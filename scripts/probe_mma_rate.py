@@ -24,3 +24,15 @@ for grid in (1, 148):
             torch.cuda.synchronize()
         c = out[:grid]
         print(f"grid={grid:3d} {note:52s} cycles/MMA min {c.min().item():7.1f} mean {c.mean().item():7.1f}  floor {128 * N / 256:5.1f}")
+
+# CTA pair (tcgen05.mma.cta_group::2, M = 256): per-CTA operand traffic = own 128 rows of A + N/2 rows of B
+out2 = torch.zeros(74, device="cuda")
+for pairs in (1, 74):
+    for N, KC, sbo, step, ntap, ndst, note in cases:
+        if N % 32:
+            continue
+        for _ in range(2):
+            _lib.check(L.cetpick_probe_mma_rate2(N, KC, sbo, step, ntap, ndst, 4096, out2.data_ptr(), pairs, _lib.stream_ptr()), "probe2")
+            torch.cuda.synchronize()
+        c = out2[:pairs]
+        print(f"pairs={pairs:3d} cta_group::2 {note:44s} cycles/MMA min {c.min().item():7.1f} mean {c.mean().item():7.1f}  floor {128 * N / 256:5.1f}")

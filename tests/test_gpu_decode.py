@@ -34,7 +34,8 @@ def hm_of(g):
     return synth.heatmap_tiefree_np(D, H, W, int(g["seed"]))[None, None]
 
 
-@pytest.mark.parametrize("name", ["decode_tiefree_k3", "decode_tiefree_k5", "decode_tiefree_k1", "decode_fiber_k3"])
+@pytest.mark.parametrize("name", ["decode_tiefree_k3", "decode_tiefree_k5", "decode_tiefree_k1", "decode_fiber_k3",
+                                  "decode_fiber_k5", "decode_fiber_k7"])
 def test_golden_small(golden, dec, name):
     g = golden(name)
     out = dec.tomo_decode(cu(hm_of(g)), kernel=int(g["kernel"]), K=int(g["K"]), if_fiber=bool(g["fiber"]))
@@ -149,14 +150,15 @@ def test_oracle_medium_plateau_eq_path(dec, do):
 
 
 # ---- sieve_kernel (threshold-first COLLECT; aligned rows, volumes above the candidate capacity) ----
-@pytest.mark.parametrize("kernel,fiber,K", [(5, False, 800), (7, False, 300), (3, True, 1000), (1, False, 500)])
+@pytest.mark.parametrize("kernel,fiber,K", [(5, False, 800), (7, False, 300), (3, True, 1000), (1, False, 500),
+                                            (5, True, 400), (7, True, 200)])
 def test_sieve_window_modes(dec, do, kernel, fiber, K):
     D, H, W = 40, 256, 256
     hm = synth.heatmap_tiefree_np(D, H, W, 100 + kernel)[None, None]
     out = dec.tomo_decode(cu(hm), kernel=kernel, K=K, if_fiber=fiber).cpu().numpy()
     assert np.array_equal(bits(out), bits(do.tomo_decode(hm, kernel, None, K, fiber)))
     flags, _ = dec.decode_status()
-    assert flags == 0
+    assert flags & 1 == 0 and (flags == 0 or (fiber and kernel != 3))   # wide fiber windows: top-K of a mostly-zero map
 
 
 def test_sieve_plain_topk(dec, do):
@@ -228,8 +230,8 @@ def test_bad_arguments(dec):
         dec.tomo_decode(hm, kernel=4, K=10)           # even kernel: the reference fails too
     with pytest.raises(ValueError):
         dec.tomo_decode(hm, kernel=3, K=4 * 8 * 8 + 1)  # K > N: torch.topk raises
-    with pytest.raises(NotImplementedError):
-        dec.tomo_decode(hm, kernel=5, K=10, if_fiber=True)
+    with pytest.raises(ValueError):
+        dec.tomo_decode(hm, kernel=4, K=10, if_fiber=True)
     with pytest.raises(RuntimeError):
         dec.tomo_decode(hm.cpu(), kernel=3, K=10)     # no CPU fallback
 

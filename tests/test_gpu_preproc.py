@@ -91,3 +91,14 @@ def test_tilt_branch_reference_golden(golden, ld, name):
     assert im.dtype == torch.float32
     d = np.abs(im.cpu().numpy() - g["im"])
     assert (d > 1e-6).mean() <= 2e-3 and d.max() <= 1.0 / 100
+
+
+@pytest.mark.parametrize("sigma", [0, 0.8])
+def test_preprocess_levels_equals_preprocess(ld, sigma):
+    """preprocess_levels = preprocess stopped before the min-max division: level_values[levels] is the float32 volume."""
+    rng = np.random.default_rng(3)
+    vol = rng.normal(size=(6, 40, 48))
+    full = ld.preprocess(torch.from_numpy(vol), denoise=sigma, dtype=torch.float64).cpu().numpy().astype(np.float32)
+    q, lv = ld.preprocess_levels(torch.from_numpy(vol), denoise=sigma)
+    assert q.dtype == torch.uint8 and lv.dtype == np.float32 and lv[0] == 0
+    assert np.array_equal(lv[q.cpu().numpy()], full)

@@ -218,3 +218,28 @@ def test_unet5_medium_vs_oracle():
     perr = (out["proj"].cpu() - ref["proj"]).abs().max().item()
     print(f"unet_5 medium: raw hm err {err:.3e}, proj err {perr:.3e}")
     assert err <= HM_TOL_RAW and perr <= 5e-2
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 96), (3, 70, 112), (4, 50, 60)])
+def test_forward_uint8_levels_identical_to_float32(shape):
+    """Quantised input (cetpick_unet_forward_u8): the stem's converter warps map level -> bf16 operand exactly as
+    the float32 entry point maps value -> bf16, so the heat-maps are bit-identical; (4,50,60) has rows that are
+    not 16-byte aligned and takes the device-side expansion instead."""
+    D, H, W = shape
+    m = build_model(4, 317)
+    m.compute_proj, m.fuse_sigmoid = False, True
+    xf = synth.tomogram_np(D, H, W, 11)
+    q = np.rint(xf * 255.0).astype(np.uint8)
+    assert np.array_equal((q.astype(np.float64) / 255.0).astype(np.float32), xf)
+    a = m(torch.from_numpy(xf)[None].cuda())[-1]["hm"]
+    b = m(torch.from_numpy(q)[None].cuda())[-1]["hm"]
+    assert torch.equal(a, b)
+    # levels that do not span 0..255: value table from the loader
+    lv = np.zeros(256, np.float32)
+    lv[:201] = (np.arange(201, dtype=np.float64) / 200.0).astype(np.float32)
+    q2 = (q.astype(np.int32) * 200 // 255).astype(np.uint8)
+    m.level_values = lv
+    b2 = m(torch.from_numpy(q2)[None].cuda())[-1]["hm"]
+    m.level_values = None
+    a2 = m(torch.from_numpy(lv[q2])[None].cuda())[-1]["hm"]
+    assert torch.equal(a2, b2)
