@@ -50,6 +50,7 @@ SIGNATURES = {
     "cetpick_unet_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_unet_forward_u8": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
+    "cetpick_unet_forward_slab": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_profile_enable": (_int, [_int]),
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
@@ -59,6 +60,8 @@ SIGNATURES = {
                                        _vp, _vp]),
     "cetpick_conv_march_pool_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
                                             _vp, _vp, _vp]),
+    "cetpick_conv_block_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cetpick_block_debug_buffer": (_int, [_vp]),
     "cetpick_upconv_bf16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _vp, _int, _int, _vp]),
     "cetpick_conv_halo_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),

@@ -16,6 +16,13 @@
 // slot is complete when the row after it has been consumed; the epilogue warps drain it
 // (bias, ReLU, bf16, NHWC store), write zeros back and hand the slot to the MMA thread again, so
 // every UMMA accumulates and no instruction needs a per-column-block "first touch" flag.
+// The ring has SL logical slots and two more physical ones behind them: the window of a step starts at
+// logical slot w = q mod SL and always spans the physical columns [w, w+3), so it never wraps and a step is
+// ONE UMMA per (tap, k) -- an N <= 96 UMMA costs the same ~64 cycles whatever N is (operand-fetch bound), and
+// splitting the window at the ring end would add 25 % to the issue count.  Rows whose home slot is 0 or 1
+// collect part of their sum in the phantom slots SL / SL+1; the epilogue adds the two.  The home slot of a
+// row is (ABSOLUTE row index) mod SL, so the order in which a row's partial sums are added depends on nothing
+// but the row's position in the image / volume: strips, slabs and z-shards all give bit-identical results.
 //
 // Roles (384 threads, 1 CTA/SM, persistent over strips):
 //   warp 0: TMA producer   warp 1: UMMA issuer   warp 2: TMEM allocator   warps 4-11: epilogue
@@ -40,7 +47,8 @@ constexpr int DIL3D = 4;         // feature_head dilation (unet_small.py:39-46)
 struct alignas(64) MarchParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
-  int nsrc, chunks, S;
+  int nsrc, chunks, S, SL;   // S physical TMEM slots per M-tile, SL = S - 2 logical ring slots
+  int row_origin;            // 3-D: absolute z of plane 0 of this call (z-slab streaming), taken mod SL
   int NIMG, H, W;
   int L, R, nchunk;        // march extent, rows per strip, strips along the march axis
   int nxb;                 // tile columns (2-D: x blocks per row; 3-D: x tiles per plane)
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < p.S; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * MT); }
+    for (int s = 0; s < p.SL; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * MT); }
     ptx::mbar_init(&bar_w, 1);
     ptx::fence_barrier_init();
   }
@@ -157,8 +165,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
 
-  const uint32_t smask = (uint32_t)p.S - 1u;
-  const int sshift = 31 - __clz(p.S);
+  const uint32_t SL = (uint32_t)p.SL;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -197,26 +204,27 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     const uint32_t tile_cols = (uint32_t)(p.S * COUT);
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t q0 = 0, q_touched = 0;
+    uint32_t umask = 0;      // bit s: parity of the number of rows that have used logical slot s
+    const uint32_t org = (uint32_t)p.row_origin;
     ptx::mbar_wait(&bar_w, 0);
     for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
       Strip s;
       decode_strip<MODE, MT>(p, k, s);
       const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
+      int r_touched = s.ma;
       for (int i = i_lo; i <= i_hi; ++i) {
         const int r_lo = max(s.ma, i - 1), r_hi = min(s.mb - 1, i + 1);
-        const uint32_t q_lo = q0 + (uint32_t)(r_lo - s.ma);
         const int n = r_hi - r_lo + 1;
-        while (q_touched < q_lo + (uint32_t)n) {    // rows touched for the first time: slot must be drained
-          ptx::mbar_wait(&bar_aempty[q_touched & smask], ((q_touched >> sshift) & 1u) ^ 1u);
-          ++q_touched;
+        for (; r_touched <= r_hi; ++r_touched) {    // rows touched for the first time: slot must be drained
+          const uint32_t sl = ((uint32_t)r_touched + org) % SL;
+          ptx::mbar_wait(&bar_aempty[sl], ((umask >> sl) & 1u) ^ 1u);
+          umask ^= 1u << sl;
         }
-        const uint32_t s_lo = q_lo & smask;
-        const int n1 = min(n, p.S - (int)s_lo), n2 = n - n1;     // ring wrap splits the column range
-        const uint32_t id1 = IDESC0 | ((uint32_t)(n1 * COUT >> 3) << 17), id2 = IDESC0 | ((uint32_t)(n2 * COUT >> 3) << 17);
+        // the window starts at the home slot of row i-1 and runs on into the phantom slots: no wrap, and a
+        // row's partial sums land in the same places wherever the strip starts
+        const uint32_t id1 = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
         const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
-        const uint32_t boff2 = boff1 + (uint32_t)n1 * (G::SLOT_BYTES >> 4);
-        const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
+        const uint32_t d1 = tmem_base + (((uint32_t)i + org + SL - 1u) % SL + (uint32_t)(r_lo - (i - 1))) * COUT;
         for (int src = 0; src < p.nsrc; ++src)
           for (int c = 0; c < p.chunks; ++c) {
             ptx::mbar_wait(&bar_full[stage], phase);
@@ -224,28 +232,14 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
             const uint32_t a_lo = sA_lo + (uint32_t)(stage * (G::STAGE_BYTES >> 4));
             const uint32_t w_lo = sW_lo + (uint32_t)((src * p.chunks + c) * G::T * (G::WBLK >> 4));
             if (ptx::elect_one()) {
-              if (n2 == 0) {
 #pragma unroll
-                for (int t = 0; t < MT; ++t)
+              for (int t = 0; t < MT; ++t)
 #pragma unroll
-                  for (int j = 0; j < G::T; ++j)
+                for (int j = 0; j < G::T; ++j)
 #pragma unroll
-                    for (int kk = 0; kk < G::K16; ++kk)
-                      ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
-                                          w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
-              } else {
-#pragma unroll 1
-                for (int t = 0; t < MT; ++t)
-#pragma unroll
-                  for (int j = 0; j < G::T; ++j)
-#pragma unroll
-                    for (int kk = 0; kk < G::K16; ++kk) {
-                      ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
-                                          w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
-                      ptx::umma_bf16_lohi(d2 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
-                                          w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
-                    }
-              }
+                  for (int kk = 0; kk < G::K16; ++kk)
+                    ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
+                                        w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
               ptx::umma_commit(&bar_empty[stage]);
             }
             __syncwarp();
@@ -253,19 +247,19 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           }
         // rows that have now seen all three of their input rows
         if (ptx::elect_one()) {
-          if (i - 1 >= s.ma) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - 1 - s.ma)) & smask]);
-          if (i == p.L - 1 && i < s.mb) ptx::umma_commit(&bar_afull[(q0 + (uint32_t)(i - s.ma)) & smask]);
+          if (i - 1 >= s.ma) ptx::umma_commit(&bar_afull[((uint32_t)(i - 1) + org) % SL]);
+          if (i == p.L - 1 && i < s.mb) ptx::umma_commit(&bar_afull[((uint32_t)i + org) % SL]);
         }
         __syncwarp();
       }
-      q0 += (uint32_t)(s.mb - s.ma);
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     const int quad = warp & 3, eg = (warp - 4) >> 2;
     const int m = quad * 32 + lane;
     const bool fuse_hm = MODE == MARCH_3D_PLANES && p.hm_out != nullptr;
-    uint32_t q0 = 0;
+    uint32_t q0 = 0, emask = 0;
+    const uint32_t org = (uint32_t)p.row_origin;
     for (long long k = blockIdx.x; k < p.total_strips; k += gridDim.x) {
       Strip s;
       decode_strip<MODE, MT>(p, k, s);
@@ -273,14 +267,18 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
       const bool pool = MODE == MARCH_2D_ROWS && p.pool_out != nullptr;
       uint32_t prow[MODE == MARCH_2D_ROWS ? COUT / 2 : 1];   // fused pool: the even row of the pair (packed bf16)
       for (int r = s.ma; r < s.mb; ++r) {
-        const uint32_t q = q0 + (uint32_t)(r - s.ma);
-        const uint32_t slot = q & smask, par = (q >> sshift) & 1u;
+        const uint32_t q = q0 + (uint32_t)(r - s.ma);       // running row count: only spreads rows over the two groups
+        const uint32_t slot = ((uint32_t)r + org) % SL, par = (emask >> slot) & 1u;
+        emask ^= 1u << slot;
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
           // one epilogue group per (row, M-tile); with the fused pool a group keeps both rows of a pair
           // (MT = 2: group = M-tile; MT = 1: groups alternate row PAIRS; strips start on even rows)
-          if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) continue;
+          // (every group observes every phase of a slot's barrier, also for rows / tiles the other group drains:
+          // a parity wait only tells the current phase from the one before it, and a group that skipped a phase
+          // could run two phases ahead across a strip boundary and take the stale parity for "done")
           ptx::mbar_wait(&bar_afull[slot], par);
+          if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) continue;
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
           uint32_t v[COUT];
@@ -290,6 +288,18 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 16) ptx::tmem_st16_fill(taddr + c0, 0u);
+          if (slot < 2u) {   // home slots 0 / 1: the other part of the sum sits in the phantom slots SL / SL+1
+            const uint32_t paddr = taddr + SL * COUT;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 16) {
+              uint32_t u[16];
+              ptx::tmem_ld16(paddr + c0, u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[c0 + i] = __float_as_uint(__uint_as_float(v[c0 + i]) + __uint_as_float(u[i]));
+              ptx::tmem_st16_fill(paddr + c0, 0u);
+            }
+          }
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
@@ -439,6 +449,8 @@ int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
   }
   p.nblk = L.nsrc * p.chunks * G::T;
   p.S = std::min(MAX_SLOTS, TMEM_COLS / (MT * COUT));
+  p.SL = p.S - 2;
+  p.row_origin = MODE == MARCH_3D_PLANES ? (int)(((long long)L.z_origin % p.SL + p.SL) % p.SL) : 0;
   const size_t wtot = align_up((size_t)p.nblk * G::WBLK, 1024);
   const size_t avail = (size_t)smem_limit() - static_smem - 1024 - wtot;
   p.stages = (int)std::min<size_t>(MAX_STAGES, avail / G::STAGE_BYTES);

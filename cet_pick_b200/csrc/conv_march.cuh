@@ -19,6 +19,7 @@ struct MarchLaunch {
   const void* src[2] = {nullptr, nullptr};   // bf16 [NIMG][H][W][C]
   int C = 0;                // channels per source: 16 / 32 / 64
   int NIMG = 0, H = 0, W = 0;
+  int z_origin = 0;         // 3-D mode: absolute z of plane 0 (z-slab streaming / z-sharding keep results bit-identical)
   const void* wpk = nullptr;    // device, layout of march_pack_weights()
   int Cout = 0;             // 32 or 64
   const float* bias = nullptr;  // [Cout] fp32 or null (device)

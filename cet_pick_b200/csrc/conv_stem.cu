@@ -49,10 +49,12 @@ constexpr int A_STAGE = MT * A_TILE;
 constexpr int A_STAGES = 4;
 constexpr int W_BYTES = 4 * COUT * 32;      // [4 slots][16 co][16 k] bf16
 constexpr int SMEM_BYTES = 1024 + 1024 * ((W_BYTES + 1023) / 1024) + A_STAGES * A_STAGE + RAW_STAGES * RAW_STAGE;
-// uint8 input (quantised tomogram, loader.py:16-25,117-120): a box row is 144 bytes (64 output pixels read
-// 2*63 + 8 = 134 columns; box widths are multiples of 16 bytes); the converters map level -> bf16 through a
-// per-lane copy of the 256-entry table (bank = lane: conflict-free), kept behind the raw stages.
-constexpr int U8_ROW_BYTES = 144;
+// uint8 input (quantised tomogram, loader.py:16-25,117-120): a box row is 160 bytes starting 16 bytes left of the
+// block's first pixel pair (a TMA box must start on a 16-byte boundary of the innermost dimension; 64 output pixels
+// read bytes 12 .. 12 + 2*63 + 8); the converters map level -> bf16 through a per-lane copy of the 256-entry table
+// (bank = lane: conflict-free), kept behind the raw stages.
+constexpr int U8_ROW_BYTES = 160;
+constexpr int U8_LEAD = 12;                 // bytes between the box start and column 2*ox - 4 of its first pixel
 constexpr int U8_BOX_BYTES = 2 * U8_ROW_BYTES;
 constexpr int U8_BOX_STRIDE = 384;
 constexpr int LUT_BYTES = 256 * 32 * 4;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
           uint8_t* dst = sRaw + (size_t)stage * RSTAGE;
 #pragma unroll
           for (int b = 0; b < NBOX; ++b)
-            ptx::tma_load_3d(dst + b * BSTRIDE, &p.tmIn, &raw_full[stage], 2 * (s.x0 + b * 64) - 4, 2 * j, s.z);
+            ptx::tma_load_3d(dst + b * BSTRIDE, &p.tmIn, &raw_full[stage], 2 * (s.x0 + b * 64) - (U8 ? 16 : 4), 2 * j, s.z);
           if (++stage == RAW_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 1) stem_tc_kernel(const __grid_c
     // ================================ converters ==================================
     const int c = threadIdx.x - 128;
     const int t = c >> 7, px = c & 127, hb = px >> 6, pp = px & 63;
-    const uint32_t raw_off = U8 ? (uint32_t)((t * 2 + hb) * BSTRIDE + ((pp * 2) & ~3)) : (uint32_t)((t * 2 + hb) * BSTRIDE + pp * 8);
+    const uint32_t raw_off = U8 ? (uint32_t)((t * 2 + hb) * BSTRIDE + ((pp * 2 + U8_LEAD) & ~3)) : (uint32_t)((t * 2 + hb) * BSTRIDE + pp * 8);
     const uint32_t u8_shift = (uint32_t)((pp * 2) & 3) * 8u;     // the pixel's 8 bytes start 0 or 2 bytes into an aligned word
     const uint32_t* lut = sLut + lane;
     const uint32_t a_row = (uint32_t)(px * 32);

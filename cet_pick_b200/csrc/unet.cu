@@ -13,6 +13,7 @@
 #include "conv_stem.cuh"
 #include "conv_up.cuh"
 #include "conv_halo.cuh"
+#include "conv_block.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -374,6 +375,7 @@ struct HeadExtras {
   const float* hm_w_host = nullptr;
   float* hm_out = nullptr;
   int hm_sigmoid = 0;
+  int z_origin = 0;
 };
 
 int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
@@ -393,6 +395,7 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
     if (ex) {
       M.bias_tab = ex->bias_tab; M.bias_tab_host = ex->bias_tab_host;
       M.hm_w = ex->hm_w; M.hm_w_host = ex->hm_w_host; M.hm_out = ex->hm_out; M.hm_sigmoid = ex->hm_sigmoid;
+      M.z_origin = ex->z_origin;
     }
     return conv_march_launch(M, st);
   }
@@ -415,6 +418,28 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
   L.relu = pc.relu; L.epi = epi; L.out = out; L.out_cstride = pc.Ntot;
   L.Ho = Ho; L.Wo = Wo; L.Cout = Cout;
   return conv_tc_launch(L, st);
+}
+
+// conv1 + conv2 (+ pool) of a 32-channel full-resolution block as ONE kernel (conv_block.cu) when both layers were
+// packed for the marching kernel and a thread-block cluster can span the row.  CETPICK_NO_BLOCK=1 keeps the two
+// separate kernels (A/B measurements).
+bool use_block(const PackedConv& c1, const PackedConv& c2, int W) {
+  static const bool off = [] { const char* e = getenv("CETPICK_NO_BLOCK"); return e && e[0] == '1'; }();
+  return !off && c1.march == MARCH_2D_ROWS && c2.march == MARCH_2D_ROWS && c1.Ntot == 32 && c2.Ntot == 32 && c2.nsrc == 1 &&
+         c2.C[0] == 32 && c1.relu && c2.relu && c1.has_bias && c2.has_bias && W > 128 && block_supported(c1.C[0], c1.nsrc, W);
+}
+
+int run_block(const cetpick_unet* m, const std::string& name, const PackedConv& c1, const PackedConv& c2, const void* s0,
+              const void* s1, int NIMG, int H, int W, void* out, void* pool_out, cudaStream_t st) {
+  g_prof.mark((std::string("conv:") + name + ".c1+c2:block").c_str(), (c1.flops_per_pixel + c2.flops_per_pixel) * (double)NIMG * H * W, st);
+  BlockLaunch B;
+  B.nsrc = c1.nsrc; B.src[0] = s0; B.src[1] = s1; B.C1 = c1.C[0]; B.NIMG = NIMG; B.H = H; B.W = W;
+  B.w1pk = static_cast<const uint8_t*>(m->d_blob) + c1.w_off;
+  B.w2pk = static_cast<const uint8_t*>(m->d_blob) + c2.w_off;
+  B.bias1_host = reinterpret_cast<const float*>(m->blob.data() + c1.b_off);
+  B.bias2_host = reinterpret_cast<const float*>(m->blob.data() + c2.b_off);
+  B.out = out; B.pool_out = pool_out;
+  return conv_block_launch(B, st);
 }
 
 }  // namespace
@@ -595,8 +620,8 @@ extern "C" int cetpick_unet_workspace_bytes(const cetpick_unet* m, int64_t D, in
 
 namespace {
 int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8, const float* lut_host, int64_t D64,
-                      int64_t H64, int64_t W64, float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes,
-                      void* stream) {
+                      int64_t H64, int64_t W64, int64_t z_origin, float* hm, int apply_sigmoid, float* proj, void* ws,
+                      size_t ws_bytes, void* stream) {
   g_launches = 0;
   if (!m || (!tomo && !tomo_u8) || !hm || D64 <= 0 || H64 <= 0 || W64 <= 0) return CETPICK_ERR_BAD_ARG;
   if (tomo_u8 && (!lut_host || lut_host[0] != 0.f)) return CETPICK_ERR_BAD_ARG;
@@ -642,6 +667,11 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
   // encoder: level i: in Y0 -> conv1 -> Y1 -> conv2 -> Y2 (skip) -> pool -> next level's Y0
   for (int i = 0; i < nb; ++i) {
     const int h = dims[i].h, w = dims[i].w;
+    if (use_block(m->down1[i], m->down2[i], w)) {
+      if ((rc = run_block(m, "down" + std::to_string(i), m->down1[i], m->down2[i], buf(i, 0), nullptr, D, h, w, buf(i, 2),
+                          i < nb - 1 ? buf(i + 1, 0) : nullptr, st))) return rc;
+      continue;
+    }
     if ((rc = run_conv(m, "down" + std::to_string(i) + ".c1", m->down1[i], buf(i, 0), nullptr, D, h, w, EPI_BF16_NHWC, buf(i, 1), 0, 0, 0, st))) return rc;
     // MaxPool2d(2, ceil) (unet.py:225) comes out of the marching kernel's epilogue where that kernel runs
     const bool fuse_pool = (i < nb - 1) && m->down2[i].march == MARCH_2D_ROWS && m->down2[i].relu;
@@ -670,6 +700,11 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
       U.Cout = Cout; U.out = buf(j, 0); U.Ho = h; U.Wo = w;
       if ((rc = conv_up_launch(U, st))) return rc;
     } else if ((rc = run_conv(m, "up" + std::to_string(i) + ".upconv", m->upc[i], below, nullptr, D, dims[j + 1].h, dims[j + 1].w, EPI_UPCONV_2X2, buf(j, 0), h, w, Cout, st))) return rc;
+    if (use_block(m->up1[i], m->up2[i], w)) {
+      if ((rc = run_block(m, "up" + std::to_string(i), m->up1[i], m->up2[i], buf(j, 0), buf(j, 2), D, h, w, buf(j, 1), nullptr, st))) return rc;
+      below = buf(j, 1);
+      continue;
+    }
     if ((rc = run_conv(m, "up" + std::to_string(i) + ".c1", m->up1[i], buf(j, 0), buf(j, 2), D, h, w, EPI_BF16_NHWC, buf(j, 1), 0, 0, 0, st))) return rc;
     if ((rc = run_conv(m, "up" + std::to_string(i) + ".c2", m->up2[i], buf(j, 1), nullptr, D, h, w, EPI_BF16_NHWC, buf(j, 0), 0, 0, 0, st))) return rc;
     below = buf(j, 0);
@@ -680,26 +715,35 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
   // 32-channel feature map is never written.
   {
     const float* hmw = reinterpret_cast<const float*>(blob + m->hm_w);
-    const __nv_bfloat16* f_in = buf(0, 0);
+    // trunk output X (buffer 0 or 1 of level 0, depending on the fused block) and the other buffer Y
+    __nv_bfloat16* X = const_cast<__nv_bfloat16*>(below);
+    __nv_bfloat16* Y = (X == buf(0, 0)) ? buf(0, 1) : buf(0, 0);
+    const __nv_bfloat16* f_in = X;
+    __nv_bfloat16* f_out = Y;
     if (!m->fold_cf) {
-      if ((rc = run_conv(m, "conv_final", m->conv_final, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st))) return rc;
-      if ((rc = run_conv(m, "fhead0", m->fh0, buf(0, 1), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 0), 0, 0, 0, st))) return rc;
-      f_in = buf(0, 0);
+      if ((rc = run_conv(m, "conv_final", m->conv_final, X, nullptr, D, h0, w0, EPI_BF16_NHWC, Y, 0, 0, 0, st))) return rc;
+      HeadExtras ex0;
+      ex0.z_origin = (int)(z_origin % 840);
+      if ((rc = run_conv(m, "fhead0", m->fh0, Y, nullptr, D, h0, w0, EPI_BF16_NHWC, X, 0, 0, 0, st, &ex0))) return rc;
+      f_in = X; f_out = Y;
     } else {
       HeadExtras ex;
+      ex.z_origin = (int)(z_origin % 840);     // 840 = lcm(1..8): every ring length divides it
       ex.bias_tab = reinterpret_cast<const float*>(blob + m->fh0_btab);
       ex.bias_tab_host = reinterpret_cast<const float*>(m->blob.data() + m->fh0_btab);
-      if ((rc = run_conv(m, "fhead0+conv_final", m->fh0, buf(0, 0), nullptr, D, h0, w0, EPI_BF16_NHWC, buf(0, 1), 0, 0, 0, st, &ex))) return rc;
-      f_in = buf(0, 1);
+      if ((rc = run_conv(m, "fhead0+conv_final", m->fh0, X, nullptr, D, h0, w0, EPI_BF16_NHWC, Y, 0, 0, 0, st, &ex))) return rc;
+      f_in = Y; f_out = X;
     }
-    __nv_bfloat16* f_out = (f_in == buf(0, 1)) ? buf(0, 0) : buf(0, 1);
     if (!proj && m->fh2.march >= 0) {
       HeadExtras ex;
+      ex.z_origin = (int)(z_origin % 840);
       ex.hm_w = hmw; ex.hm_w_host = reinterpret_cast<const float*>(m->blob.data() + m->hm_w);
       ex.hm_out = hm; ex.hm_sigmoid = apply_sigmoid;
       if ((rc = run_conv(m, "fhead2+hm", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, nullptr, 0, 0, 0, st, &ex))) return rc;
     } else {
-      if ((rc = run_conv(m, "fhead2", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, f_out, 0, 0, 0, st))) return rc;
+      HeadExtras ex2;
+      ex2.z_origin = (int)(z_origin % 840);
+      if ((rc = run_conv(m, "fhead2", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, f_out, 0, 0, 0, st, &ex2))) return rc;
       const size_t plane = (size_t)h0 * w0, total = plane * D;
       g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
@@ -719,14 +763,24 @@ extern "C" int cetpick_unet_forward(cetpick_unet* m, const float* tomo, int64_t 
                                     float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes,
                                     void* stream) {
   if (!tomo) return CETPICK_ERR_BAD_ARG;
-  return unet_forward_impl(m, tomo, nullptr, nullptr, D, H, W, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
+  return unet_forward_impl(m, tomo, nullptr, nullptr, D, H, W, 0, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
 }
 
 extern "C" int cetpick_unet_forward_u8(cetpick_unet* m, const uint8_t* tomo_q, const float* level_values_host,
                                        int64_t D, int64_t H, int64_t W, float* hm, int apply_sigmoid, float* proj,
                                        void* ws, size_t ws_bytes, void* stream) {
   if (!tomo_q || !level_values_host) return CETPICK_ERR_BAD_ARG;
-  return unet_forward_impl(m, nullptr, tomo_q, level_values_host, D, H, W, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
+  return unet_forward_impl(m, nullptr, tomo_q, level_values_host, D, H, W, 0, hm, apply_sigmoid, proj, ws, ws_bytes, stream);
+}
+
+extern "C" int cetpick_unet_forward_slab(cetpick_unet* m, const float* tomo, const uint8_t* tomo_q,
+                                         const float* level_values_host, int64_t D, int64_t H, int64_t W,
+                                         int64_t z_origin, float* hm, int apply_sigmoid, float* proj, void* ws,
+                                         size_t ws_bytes, void* stream) {
+  if ((tomo == nullptr) == (tomo_q == nullptr) || z_origin < 0) return CETPICK_ERR_BAD_ARG;
+  if (tomo_q && !level_values_host) return CETPICK_ERR_BAD_ARG;
+  return unet_forward_impl(m, tomo, tomo_q, level_values_host, D, H, W, z_origin, hm, apply_sigmoid, proj, ws, ws_bytes,
+                           stream);
 }
 
 extern "C" int cetpick_profile_enable(int on) {

@@ -118,7 +118,7 @@ class TomoClassdetDetector(BaseDetector):
         """:173-214 (plain and --with_score lines; the fiber / spike graph post-processing of the
         reference is host-side Python outside this path)."""
         os.makedirs(path, exist_ok=True)            # every rank of a torchrun job writes into the same directory
-        if self.opt.fiber or self.opt.spike:
+        if getattr(self.opt, "fiber", False) or getattr(self.opt, "spike", False):
             raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
                                       "(utils/post_process.py:31-106; DESIGN.md)")
         hm = hm.detach().cpu().numpy()[0][0]

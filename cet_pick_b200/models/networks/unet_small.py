@@ -98,6 +98,8 @@ class TomoConvUNet(nn.Module):
         # stands for the float32 value level_values[k] (default k/255, i.e. levels spanning 0..255).  Lossless
         # and a quarter of the host->device bytes of the float32 volume the reference ships.
         self.level_values = None
+        # absolute z of plane 0 of the tensors passed to forward() (a z-shard of a larger volume, shard.py)
+        self.z_origin = 0
         self.compute_proj = "proj" in heads      # detectors switch this off (they never read 'proj')
         self.fuse_sigmoid = False                # TomodetDetector fuses _sigmoid into the hm epilogue
         self._plan = None
@@ -203,16 +205,15 @@ class TomoConvUNet(nn.Module):
         self.last_slabs = 0
         sig = 1 if self.fuse_sigmoid else 0
 
-        def run(src, depth, hm_dst, proj_dst):
+        def run(src, depth, hm_dst, proj_dst, z_origin=0):
             pj = proj_dst.data_ptr() if proj_dst is not None else None
-            if lut is not None:
-                _lib.check(L.cetpick_unet_forward_u8(plan, src.data_ptr(), lut.ctypes.data_as(C.c_void_p), depth, h, w,
-                                                     hm_dst.data_ptr(), sig, pj, self._ws.data_ptr(),
-                                                     self._ws.numel(), _lib.stream_ptr()), "cetpick_unet_forward_u8")
-            else:
-                _lib.check(L.cetpick_unet_forward(plan, src.data_ptr(), depth, h, w, hm_dst.data_ptr(), sig, pj,
-                                                  self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
-                           "cetpick_unet_forward")
+            z_origin += int(self.z_origin)
+            _lib.check(L.cetpick_unet_forward_slab(plan, None if lut is not None else src.data_ptr(),
+                                                   src.data_ptr() if lut is not None else None,
+                                                   lut.ctypes.data_as(C.c_void_p) if lut is not None else None,
+                                                   depth, h, w, z_origin, hm_dst.data_ptr(), sig, pj,
+                                                   self._ws.data_ptr(), self._ws.numel(), _lib.stream_ptr()),
+                       "cetpick_unet_forward_slab")
             self.last_launches += L.cetpick_last_launch_count()
             self.last_slabs += 1
 
@@ -227,7 +228,7 @@ class TomoConvUNet(nn.Module):
                 lo, hi = max(0, z0 - halo), min(d, z1 + halo)
                 # (pc, depth, oh, ow) output of a slab is contiguous only for the slab's own depth
                 pj_v = pj_s.view(-1)[:pc * (hi - lo) * oh * ow].view(pc, hi - lo, oh, ow) if pj_s is not None else None
-                run(x[i, lo:hi], hi - lo, hm_s, pj_v)
+                run(x[i, lo:hi], hi - lo, hm_s, pj_v, z_origin=lo)
                 hm[i, 0, z0:z1].copy_(hm_s[z0 - lo:z0 - lo + (z1 - z0)])
                 if pj_v is not None:
                     proj[i, :, z0:z1].copy_(pj_v[:, z0 - lo:z0 - lo + (z1 - z0)])

@@ -54,14 +54,18 @@ def forward_z_sharded(forward_fn, volume_slab_fn, depth: int, group=None, halo: 
     per-slice, the head needs +-3 slices, so each rank recomputes a 3-slice halo instead of exchanging features).
 
     volume_slab_fn(lo, hi) -> this rank's input slices (hi-lo, H, W) (only those are ever loaded);
-    forward_fn(slab)       -> heat-map slices (hi-lo, h, w) of that slab.
+    forward_fn(slab[, lo]) -> heat-map slices (hi-lo, h, w) of that slab; a two-argument function also receives the
+                              absolute z of the slab's first slice (TomoConvUNet.z_origin: the head then adds its
+                              partial sums in the whole-volume order and the slab result is bit-identical).
     Every rank returns the full (depth, h, w) heat-map: ONE all_gather of the core slabs (padded to the
     largest share), after which decode runs on identical data everywhere (picks bit-identical to 1 GPU)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     z0, z1, lo, hi = slab_range(depth, rank, world, halo)
     if z1 > z0:
-        hm_slab = forward_fn(volume_slab_fn(lo, hi))
+        import inspect
+        two = len(inspect.signature(forward_fn).parameters) >= 2
+        hm_slab = forward_fn(volume_slab_fn(lo, hi), lo) if two else forward_fn(volume_slab_fn(lo, hi))
         core = hm_slab[z0 - lo:z0 - lo + (z1 - z0)].contiguous()
     else:
         core = None

@@ -196,6 +196,15 @@ int cetpick_unet_forward_u8(cetpick_unet* plan, const uint8_t* tomo_q, const flo
                             int64_t D, int64_t H, int64_t W, float* hm, int apply_sigmoid, float* proj,
                             void* ws, size_t ws_bytes, void* stream);
 
+/* One z-slab of a larger volume (the sliding-slab scheduler and the z-sharded multi-GPU forward): planes
+ * [z_origin, z_origin + D) of the tomogram, given as float32 (tomo) OR as levels (tomo_q + level_values_host), the
+ * other pointer NULL.  The 2-D trunk is per slice and the 3-D head reaches +-3 planes, so a slab forwarded with a
+ * 3-plane recompute halo reproduces the whole-volume heat-map on its core planes; z_origin makes the accumulation
+ * order of the head depend on the ABSOLUTE plane index only, so the reproduction is bit-identical. */
+int cetpick_unet_forward_slab(cetpick_unet* plan, const float* tomo, const uint8_t* tomo_q,
+                              const float* level_values_host, int64_t D, int64_t H, int64_t W, int64_t z_origin,
+                              float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes, void* stream);
+
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);
@@ -233,6 +242,19 @@ int cetpick_conv_march_bf16(int mode, int dil, int nsrc, const void* src0, const
 int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
                                  int NIMG, int H, int W, const float* w_host, int Cout,
                                  const float* bias, int relu, void* out, void* pool_out, void* stream);
+
+/* Test hook: the fused full-resolution block of csrc/conv_block.cu: conv3x3 + bias + ReLU -> conv3x3 + bias + ReLU
+ * (-> MaxPool2d(2, ceil)) with the intermediate map kept in shared memory (cet_pick/models/networks/unet.py:198-249,
+ * 375-399).  src*: bf16 device [NIMG][H][W][C1] (C1 = 16, or 32 with nsrc 1 / 2); w1_host (32, nsrc*C1, 3, 3),
+ * w2_host (32, 32, 3, 3), bias*_host [32]: fp32 HOST; out: bf16 device [NIMG][H][W][32]; pool_out: bf16 device
+ * [NIMG][(H+1)/2][(W+1)/2][32] or null.  W <= 1024 (one cluster of <= 8 CTAs spans a row).  Packs, uploads, launches and synchronises. */
+int cetpick_conv_block_bf16(int nsrc, const void* src0, const void* src1, int C1, int NIMG, int H, int W,
+                            const float* w1_host, const float* bias1_host, const float* w2_host,
+                            const float* bias2_host, void* out, void* pool_out, void* stream);
+
+/* Bring-up aid for csrc/conv_block.cu: registers (first call) and returns a 256-word HOST buffer the kernel can write;
+ * word 0 = number of mbarrier waits that timed out, 4-word records from word 4: (cta << 8 | warp, wait site, a, b). */
+int cetpick_block_debug_buffer(uint32_t** host_buf);
 
 /* Test hook: ConvTranspose2d(Cin,Cout,2,stride 2)+bias+ReLU through csrc/conv_up.cu.  src: bf16 device
  * [NIMG][h][w][Cin]; w_host: fp32 HOST weight in PyTorch layout (Cin,Cout,2,2); bias_host: fp32 HOST

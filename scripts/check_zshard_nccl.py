@@ -31,7 +31,7 @@ def main():
         loaded.append((lo, hi))
         return vol[lo:hi]
 
-    hm = forward_z_sharded(lambda s: m(s[None])[-1]["hm"][0, 0], slab_fn, D)
+    hm = forward_z_sharded(lambda s, lo: (setattr(m, "z_origin", lo), m(s[None])[-1]["hm"][0, 0], setattr(m, "z_origin", 0))[1], slab_fn, D)
     dets = tomo_decode(hm[None, None].contiguous(), kernel=3, K=K)
     whole = m(vol[None])[-1]["hm"][0, 0]
     ref = tomo_decode(whole[None, None].contiguous(), kernel=3, K=K)

@@ -77,7 +77,7 @@ def test_config2_decode_index_quirk_bit_exact_vs_torch_cuda(c2_map):
     from cet_pick_b200.models import decode as dec
     K, H, W = 10000, 1024, 1024
     hm = c2_map.clone()
-    planes = [17, 100, 300, 301, 400, 511]
+    planes = [17, 100, 300, 302, 400, 511]          # no two adjacent in z: every planted maximum survives the NMS
     vals = []
     for i, z in enumerate(planes):
         for j, x in enumerate(range(W - 16, W, 3)):
@@ -91,7 +91,6 @@ def test_config2_decode_index_quirk_bit_exact_vs_torch_cuda(c2_map):
     top = out[0, :len(vals)]
     assert bool((top[:, 3] > 1.0).all())                                  # the planted maxima lead the list
     assert bool((top[:, 1] == -0.75).any())                               # y = -1 + 0.25: the quirk is reproduced
-    assert (300, -0.75, 1023.25) != tuple(top[0, :3].tolist())
 
 
 def test_config2_decode_properties_plateau_map():

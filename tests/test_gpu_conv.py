@@ -300,3 +300,45 @@ def test_march_fused_maxpool(L, n, h, w, cin, cout):
     # the pooled tensor is EXACTLY the ceil-mode max-pool of the bf16 output the kernel wrote
     pref = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, ceil_mode=True).permute(0, 2, 3, 1)
     assert torch.equal(pool.float(), pref)
+
+
+# ---- fused full-resolution block (csrc/conv_block.cu): conv+ReLU -> conv+ReLU (-> pool), intermediate map in smem ----
+@pytest.mark.parametrize("n,h,w,c1,nsrc,pool", [
+    (2, 20, 130, 16, 1, True),       # cluster of 2 CTAs, second one holds 2 valid pixels
+    (3, 33, 256, 16, 1, True),       # exactly two M-tiles, odd height (ceil-mode pool)
+    (2, 41, 300, 32, 2, False),      # concat of two sources (UpConv), cluster of 3
+    (1, 64, 512, 32, 2, False),      # cluster of 4: the configs[1] row width at level 0
+    (1, 17, 700, 32, 1, False),      # cluster of 6
+    (40, 96, 384, 16, 1, True),      # more strips than resident clusters: ring / slot state carries across strips
+])
+def test_fused_block_equals_two_march_convs(L, n, h, w, c1, nsrc, pool):
+    """The fused kernel must reproduce, bit for bit, conv1 -> bf16 -> conv2 run as two marching kernels (same MMA
+    shapes, same accumulation order), and agree with torch fp32 on the same bf16-rounded operands."""
+    g = torch.Generator(device="cuda").manual_seed(n * 3 + h + w + c1)
+    srcs = [torch.randn(n, h, w, c1, device="cuda", generator=g).bfloat16() for _ in range(nsrc)]
+    w1 = (torch.randn(32, nsrc * c1, 3, 3, device="cuda", generator=g) / (3 * (nsrc * c1) ** 0.5)).bfloat16()
+    w2 = (torch.randn(32, 32, 3, 3, device="cuda", generator=g) / (3 * 32 ** 0.5)).bfloat16()
+    b1 = torch.randn(32, device="cuda", generator=g) * 0.2
+    b2 = torch.randn(32, device="cuda", generator=g) * 0.2
+    out = torch.full((n, h, w, 32), float("nan"), device="cuda", dtype=torch.bfloat16)
+    hp, wp = (h + 1) // 2, (w + 1) // 2
+    pl = torch.full((n, hp, wp, 32), float("nan"), device="cuda", dtype=torch.bfloat16) if pool else None
+    w1h, w2h = w1.float().cpu().contiguous(), w2.float().cpu().contiguous()
+    b1h, b2h = b1.cpu().contiguous(), b2.cpu().contiguous()
+    rc = L.lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
+                                         w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(), b2h.data_ptr(),
+                                         out.data_ptr(), pl.data_ptr() if pool else None, L.stream_ptr())
+    L.check(rc, "cetpick_conv_block_bf16")
+    torch.cuda.synchronize()
+    mid = run_march(L, L.MARCH_2D_ROWS, 1, srcs, w1, 32, b1, True)
+    two = run_march(L, L.MARCH_2D_ROWS, 1, [mid], w2, 32, b2, True)
+    assert not torch.isnan(out.float()).any()
+    ndiff = int((out.view(torch.int16) != two.view(torch.int16)).sum())
+    assert ndiff == 0, f"{ndiff} of {out.numel()} values differ from the two-kernel result (max {float((out.float() - two.float()).abs().max()):.3e})"
+    xin = torch.cat(srcs, 3).float().permute(0, 3, 1, 2)
+    r1 = F.relu(F.conv2d(xin, w1.float(), b1, padding=1)).bfloat16().float()
+    ref = F.relu(F.conv2d(r1, w2.float(), b2, padding=1)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 4e-2
+    if pool:
+        pref = F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, ceil_mode=True).permute(0, 2, 3, 1)
+        assert torch.equal(pl.float(), pref)

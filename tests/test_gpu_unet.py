@@ -120,7 +120,7 @@ def test_z_sharded_forward_single_process():
     m.compute_proj = False
     D, H, W = 6, 32, 48
     x = torch.from_numpy(synth.tomogram_np(D, H, W, 4)).cuda()
-    hm = forward_z_sharded(lambda s: m(s[None])[-1]["hm"][0, 0], lambda lo, hi: x[lo:hi], D)
+    hm = forward_z_sharded(lambda s, lo: (setattr(m, "z_origin", lo), m(s[None])[-1]["hm"][0, 0], setattr(m, "z_origin", 0))[1], lambda lo, hi: x[lo:hi], D)
     assert torch.equal(hm, m(x[None])[-1]["hm"][0, 0])
 
 
