@@ -51,6 +51,14 @@ SIGNATURES = {
     "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_unet_forward_u8": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_unet_forward_slab": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
+    "cetpick_simsiam_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _int]),
+    "cetpick_simsiam_destroy": (None, [_vp]),
+    "cetpick_simsiam_set_param": (_int, [_vp, C.c_char_p, _vp, _i64]),
+    "cetpick_simsiam_finalize": (_int, [_vp]),
+    "cetpick_simsiam_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_sz)]),
+    "cetpick_simsiam_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cetpick_conv_small_bf16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _int, _int, _vp, _vp,
+                                       _vp, _int, _int, _vp, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_profile_enable": (_int, [_int]),
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),

@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcetpick_sm100a.so")
 STAMP = LIB + ".stamp"
-SOURCES = ["abi.cu", "decode.cu", "greedy_nms.cu", "preproc.cu", "explore.cu", "conv_tc.cu", "conv_march.cu", "conv_up.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "unet.cu", "probe.cu"]
+SOURCES = ["abi.cu", "decode.cu", "greedy_nms.cu", "preproc.cu", "explore.cu", "conv_tc.cu", "conv_march.cu", "conv_up.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "conv_small.cu", "simsiam.cu", "unet.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"]
 

@@ -38,8 +38,8 @@ constexpr int BLK_THREADS = 512;
 constexpr int COUT = 32;
 constexpr int SP = 8, SLOTS = 6;            // physical / logical TMEM slots per convolution (phantom ring, conv_march.cu)
 constexpr int TMEM_C1 = 0, TMEM_C2 = SP * COUT;
-constexpr int LAG = 3;                      // conv2 consumes ring row j while conv1 is fed input row j + LAG
-constexpr int MAX_STAGES = 10, MAX_RS = 8;
+constexpr int MAX_LAG = 12;                 // conv2 consumes ring row j while conv1 is fed input row j + lag
+constexpr int MAX_STAGES = 10, MAX_RS = 16;
 constexpr int RING_PIX = 130;               // x0-1 .. x0+128
 constexpr int RING_ROW = 9216;              // 130 * 64 bytes, 1024-aligned
 constexpr int W2BLK = 3 * COUT * 64;        // one dx block of conv2's weights (KC = 32)
@@ -51,6 +51,7 @@ struct alignas(64) BlockParams {
   int R, nchunk;                // rows per strip, strips per image
   long long total_strips;       // per cluster
   int stages, RS, NC;
+  int lag, flags;               // tuning: bit0 no consumer-side proxy fence, bit1 CTA-scope proxy fence for the local ring stores
   float bias1[COUT], bias2[COUT];
   __nv_bfloat16* out;
   __nv_bfloat16* pool_out;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
       Strip s;
       decode_strip(p, k, s);
       int r1_touched = s.c1a, r2_touched = s.ma;
-      for (int tck = s.i_lo; tck <= s.i_hi + LAG; ++tck) {
+      for (int tck = s.i_lo; tck <= s.i_hi + p.lag; ++tck) {
         if (tck <= s.i_hi) {
           // ---- conv1: input row i feeds conv1 rows i-1, i, i+1 (inside [c1a, c1b))
           const int i = tck;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
           }
           __syncwarp();
         }
-        const int j = tck - LAG;
+        const int j = tck - p.lag;
         if (j >= s.c1a && j < s.c1b) {
           // ---- conv2: ring row j (= conv1 output row j) feeds conv2 rows j-1, j, j+1 (inside [ma, mb))
           const int r_lo = max(s.ma, j - 1), r_hi = min(s.mb - 1, j + 1);
@@ -314,8 +315,9 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
             wait_t<false>(&c2_empty[sl], ((umask2 >> sl) & 1u) ^ 1u, 5, (uint32_t)r2_touched, (uint32_t)tck);
             umask2 ^= 1u << sl;
           }
-          wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
-          fence_proxy_async_all();
+          if (p.flags & 4) wait_t<false>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+          else wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+          if (!(p.flags & 1)) fence_proxy_async_all();
           ptx::tc_fence_after();
           const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
           const uint32_t boff = (uint32_t)(r_lo - (j - 1)) * ((COUT * 64) >> 4);
@@ -430,9 +432,10 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
           fence_proxy_async_all();
           mbar_arrive_remote(rem_full + rslot * 8u);
         }
-        fence_proxy_async_all();
+        if (p.flags & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        else fence_proxy_async_all();
         __syncwarp();
-        if (lane == 0) mbar_arrive_release_cluster(&ring_full[rslot]);
+        if (lane == 0) { if (p.flags & 8) ptx::mbar_arrive(&ring_full[rslot]); else mbar_arrive_release_cluster(&ring_full[rslot]); }
         if (++rslot == (uint32_t)p.RS) { rslot = 0; rpar ^= 1u; }
       }
     }
@@ -542,7 +545,11 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.nsrc = L.nsrc; p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.NC = ceil_div(L.W, 128);
-  p.RS = 6;
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
+  p.lag = std::min(MAX_LAG, std::max(2, env_int("CETPICK_BLOCK_LAG", 3)));
+  p.RS = std::min(MAX_RS, std::max(p.lag + 2, env_int("CETPICK_BLOCK_RS", p.lag + 3)));
+  p.flags = env_int("CETPICK_BLOCK_FLAGS", 0);
+  const int max_stages = std::min(MAX_STAGES, std::max(3, env_int("CETPICK_BLOCK_STAGES", MAX_STAGES)));
   static int static_smem = -1;
   if (static_smem < 0) {
     cudaFuncAttributes fa;
@@ -552,7 +559,7 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
     static_smem = (int)fa.sharedSizeBytes;
   }
   const size_t avail = (size_t)227 * 1024 - static_smem;
-  p.stages = MAX_STAGES;
+  p.stages = max_stages;
   while (p.stages > 3 && block_smem(KC1, L.nsrc, p.stages, p.RS) > avail) --p.stages;
   if (block_smem(KC1, L.nsrc, p.stages, p.RS) > avail) return CETPICK_ERR_UNSUPPORTED;
   const size_t smem = block_smem(KC1, L.nsrc, p.stages, p.RS);
@@ -580,7 +587,7 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
     const int nn = ceil_div(L.H, R);
     const long long strips = (long long)L.NIMG * nn;
     const double waves = (double)ceil_div<long long>(strips, max_clusters);
-    const double eff = ((double)strips / (waves * max_clusters)) * ((double)R / (R + 4 + LAG));
+    const double eff = ((double)strips / (waves * max_clusters)) * ((double)R / (R + 4 + p.lag));
     if (eff > best_eff + 1e-9) { best_eff = eff; best_n = nn; best_R = R; }
   }
   p.nchunk = best_n; p.R = best_R;

@@ -122,6 +122,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int COUT, int KC, int MODE, int MT>
 __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __grid_constant__ MarchParams p) {
   using G = Geo<COUT, KC, MODE, MT>;
+  // COUT = 32: N = 96 UMMAs are operand-fetch bound, a window split at the ring end would double the issue count of
+  // that step -> phantom slots (SL = S - 2).  COUT = 64: N = 192 UMMAs run at the tensor rate, a split costs nothing
+  // in time (two UMMAs of N = 64 + 128) -> plain ring (SL = S) with the window split where it wraps.
+  constexpr bool PHANTOM = COUT == 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
@@ -222,9 +226,12 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         }
         // the window starts at the home slot of row i-1 and runs on into the phantom slots: no wrap, and a
         // row's partial sums land in the same places wherever the strip starts
-        const uint32_t id1 = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
+        const uint32_t s_lo = (((uint32_t)i + org + SL - 1u) % SL + (uint32_t)(r_lo - (i - 1))) % (PHANTOM ? 0xffffffffu : SL);
+        const int n1 = PHANTOM ? n : min(n, (int)(SL - s_lo)), n2 = n - n1;     // plain ring: the wrap splits the columns
+        const uint32_t id1 = IDESC0 | ((uint32_t)(n1 * COUT >> 3) << 17), id2 = IDESC0 | ((uint32_t)(n2 * COUT >> 3) << 17);
         const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
-        const uint32_t d1 = tmem_base + (((uint32_t)i + org + SL - 1u) % SL + (uint32_t)(r_lo - (i - 1))) * COUT;
+        const uint32_t boff2 = boff1 + (uint32_t)n1 * (G::SLOT_BYTES >> 4);
+        const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
         for (int src = 0; src < p.nsrc; ++src)
           for (int c = 0; c < p.chunks; ++c) {
             ptx::mbar_wait(&bar_full[stage], phase);
@@ -238,8 +245,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
                 for (int j = 0; j < G::T; ++j)
 #pragma unroll
                   for (int kk = 0; kk < G::K16; ++kk)
+                  {
                     ptx::umma_bf16_lohi(d1 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
                                         w_lo + boff1 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id1);
+                    if (!PHANTOM && n2)
+                      ptx::umma_bf16_lohi(d2 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
+                                          w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
+                  }
               ptx::umma_commit(&bar_empty[stage]);
             }
             __syncwarp();
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int c0 = 0; c0 < COUT; c0 += 16) ptx::tmem_st16_fill(taddr + c0, 0u);
-          if (slot < 2u) {   // home slots 0 / 1: the other part of the sum sits in the phantom slots SL / SL+1
+          if (PHANTOM && slot < 2u) {   // home slots 0 / 1: the other part of the sum sits in the phantom slots SL / SL+1
             const uint32_t paddr = taddr + SL * COUT;
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -449,7 +461,7 @@ int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
   }
   p.nblk = L.nsrc * p.chunks * G::T;
   p.S = std::min(MAX_SLOTS, TMEM_COLS / (MT * COUT));
-  p.SL = p.S - 2;
+  p.SL = COUT == 32 ? p.S - 2 : p.S;
   p.row_origin = MODE == MARCH_3D_PLANES ? (int)(((long long)L.z_origin % p.SL + p.SL) % p.SL) : 0;
   const size_t wtot = align_up((size_t)p.nblk * G::WBLK, 1024);
   const size_t avail = (size_t)smem_limit() - static_smem - 1024 - wtot;

@@ -1,0 +1,334 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) for BATCHES OF SMALL MAPS: the layers of the
+// exploration-step embedding network TomoResClassifier (cet_pick/models/networks/simsiam_model.py:44-73 BasicBlock,
+// :181-215 3-D feature layer and MLP heads, :325-366 forward_test), whose per-slice maps are 8x8, 4x4 and 2x2 pixels.
+//
+// GEMM view: M = 128 output pixels = TZ whole maps of TH x TW pixels (TW*TH*TZ = 128; the 3-D layer takes one
+// 2x2x32 sub-volume per tile, a Linear layer 128 rows), N = output channels (<= 256), K = taps x input channels.
+// The activation tensor is a rank-5 TMA tensor (C, W, H, Z, B); for every (tap, 64-channel chunk) ONE box load shifted
+// by the tap offset brings the [128][64] K-major A tile, TMA's out-of-bounds zero fill is the zero padding (in x, y
+// and, for the 3-D layer, z), and the traversal stride of the tensor map (elementStrides) is the convolution stride
+// (2 for the first conv and the 1x1 shortcut of a down-sampling BasicBlock).  fp32 accumulators in TMEM, double
+// buffered; epilogue = bias (folded BatchNorm) + optional residual add + optional ReLU, bf16 or fp32 out.
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: epilogue
+#include "conv_small.cuh"
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+#include <cuda_bf16.h>
+#include <algorithm>
+
+namespace cetpick {
+
+namespace {
+
+constexpr int SM_THREADS = 256;
+constexpr int MAX_STAGES = 8;
+
+struct alignas(64) SmallParams {
+  CUtensorMap tmA, tmB;
+  int chunks, ntaps, KC, nkb;
+  int N;                         // GEMM N = output channels (one tile of N columns)
+  int Wo, Ho, Z, NBATCH;         // output map size, maps per batch element, batch elements
+  int TW, TH, TZ, tiles_z;
+  long long total_tiles;
+  int stages, a_sub, b_sub, layout_type;
+  int relu, out_f32;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+  signed char tdz[27], tdy[27], tdx[27];
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void tma_load_5d(void* smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(ptx::smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const __grid_constant__ SmallParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * p.a_sub;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = p.N <= 128 ? 256u : 512u;       // two accumulators of N columns, power of two
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tmA);
+    ptx::prefetch_tensormap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&bar_tfull[a], 1); ptx::mbar_init(&bar_tempty[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&s_tmem_base, tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t acc_stride = tmem_cols / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int z0 = (int)(t % p.tiles_z) * p.TZ, nb = (int)(t / p.tiles_z);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int tap = kb / p.chunks, chunk = kb - tap * p.chunks;
+          ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(p.a_sub + p.b_sub));
+          tma_load_5d(sA + (size_t)stage * p.a_sub, &p.tmA, &bar_full[stage], chunk * p.KC, p.tdx[tap], p.tdy[tap],
+                      z0 + p.tdz[tap], nb);
+          ptx::tma_load_2d(sB + (size_t)stage * p.b_sub, &p.tmB, &bar_full[stage], 0, kb * p.N);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.N);
+      const uint32_t sbo = 16u * (uint32_t)p.KC;
+      const int k16s = p.KC / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          ptx::mbar_wait(&bar_full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a0 = ptx::smem_u32(sA + (size_t)stage * p.a_sub);
+          const uint32_t b0 = ptx::smem_u32(sB + (size_t)stage * p.b_sub);
+          for (int k = 0; k < k16s; ++k) {
+            const uint64_t da = ptx::make_smem_desc(a0 + k * 32, sbo, p.layout_type);
+            const uint64_t db = ptx::make_smem_desc(b0 + k * 32, sbo, p.layout_type);
+            ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
+          }
+          ptx::umma_commit(&bar_empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&bar_tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int px = m % p.TW, py = (m / p.TW) % p.TH, pz = m / (p.TW * p.TH);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int z0 = (int)(t % p.tiles_z) * p.TZ, nb = (int)(t / p.tiles_z);
+      const int z = z0 + pz;
+      const bool valid = z < p.Z;
+      const size_t pix = (((size_t)nb * p.Z + z) * p.Ho + py) * p.Wo + px;
+      ptx::mbar_wait(&bar_tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride;
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        ptx::tmem_ld16(t_row + c0, v);
+        ptx::tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + i));
+            f[i] += b.x; f[i + 1] += b.y; f[i + 2] += b.z; f[i + 3] += b.w;
+          }
+        }
+        if (p.residual && valid) {       // BasicBlock: out += identity | shortcut (simsiam_model.py:66-71)
+          const uint4* r = reinterpret_cast<const uint4*>(p.residual + pix * p.N + c0);
+          const uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+            f[2 * i] += a.x; f[2 * i + 1] += a.y; f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.out) + pix * p.N + c0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.N + c0;
+            uint4 w0, w1;
+            w0.x = pack_bf16x2(f[0], f[1]);   w0.y = pack_bf16x2(f[2], f[3]);
+            w0.z = pack_bf16x2(f[4], f[5]);   w0.w = pack_bf16x2(f[6], f[7]);
+            w1.x = pack_bf16x2(f[8], f[9]);   w1.y = pack_bf16x2(f[10], f[11]);
+            w1.z = pack_bf16x2(f[12], f[13]); w1.w = pack_bf16x2(f[14], f[15]);
+            ptx::st_global_256(dst, w0, w1);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar_tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+std::vector<uint16_t> small_pack_weights(const float* w, int Cout, int Cin, int ntaps, const double* scale) {
+  const int KC = 64, chunks = Cin / KC;
+  std::vector<uint16_t> out((size_t)ntaps * chunks * Cout * KC);
+  for (int t = 0; t < ntaps; ++t)
+    for (int ch = 0; ch < chunks; ++ch)
+      for (int n = 0; n < Cout; ++n)
+        for (int k = 0; k < KC; ++k) {
+          const double v = (double)w[((size_t)n * Cin + ch * KC + k) * ntaps + t] * (scale ? scale[n] : 1.0);
+          out[(((size_t)t * chunks + ch) * Cout + n) * KC + k] = f2bf_host((float)v);
+        }
+  return out;
+}
+
+int conv_small_launch(const SmallLaunch& L, cudaStream_t stream) {
+  if (!L.src || !L.wpk || !L.out || L.C <= 0 || (L.C % 64) || L.N < 16 || L.N > 256 || (L.N % 16)) return CETPICK_ERR_BAD_ARG;
+  if (L.ntaps < 1 || L.ntaps > 27 || (L.stride != 1 && L.stride != 2) || L.Wo < 1 || L.Ho < 1 || L.Z < 1 || L.B < 1)
+    return CETPICK_ERR_BAD_ARG;
+  const int pix = L.Wo * L.Ho;
+  if (pix > 128 || (128 % pix)) return CETPICK_ERR_UNSUPPORTED;     // whole maps per tile: Wo*Ho must divide 128
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
+
+  SmallParams p;
+  memset(&p, 0, sizeof(p));
+  p.KC = 64; p.chunks = L.C / 64; p.ntaps = L.ntaps; p.nkb = L.ntaps * p.chunks; p.N = L.N;
+  p.Wo = L.Wo; p.Ho = L.Ho; p.Z = L.Z; p.NBATCH = L.B;
+  p.TW = L.Wo; p.TH = L.Ho; p.TZ = 128 / pix;
+  p.tiles_z = ceil_div(L.Z, p.TZ);
+  p.total_tiles = (long long)p.tiles_z * L.B;
+  p.a_sub = 128 * 64 * 2;
+  p.b_sub = L.N * 64 * 2;
+  p.layout_type = 2;
+  p.relu = L.relu; p.out_f32 = L.out_f32; p.bias = L.bias; p.residual = static_cast<const __nv_bfloat16*>(L.residual);
+  p.out = L.out;
+  for (int t = 0; t < L.ntaps; ++t) {
+    p.tdz[t] = (signed char)L.tap[t][0]; p.tdy[t] = (signed char)L.tap[t][1]; p.tdx[t] = (signed char)L.tap[t][2];
+  }
+  static int static_smem = -1;
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_small_kernel));
+    CETPICK_CUDA(cudaFuncSetAttribute(conv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)fa.sharedSizeBytes));
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int stage_bytes = p.a_sub + p.b_sub;
+  p.stages = std::max(2, std::min(MAX_STAGES, (int)((227 * 1024 - static_smem - 1024) / stage_bytes)));
+  {
+    // input tensor (C, Win, Hin, Z, B); the box spans stride * (TW, TH) input positions, traversed with the conv stride
+    const cuuint64_t C = (cuuint64_t)L.C;
+    cuuint64_t dims[5] = {C, (cuuint64_t)L.Win, (cuuint64_t)L.Hin, (cuuint64_t)L.Z, (cuuint64_t)L.B};
+    cuuint64_t strides[4] = {C * 2, C * 2 * L.Win, C * 2 * (cuuint64_t)L.Win * L.Hin, C * 2 * (cuuint64_t)L.Win * L.Hin * L.Z};
+    cuuint32_t box[5] = {64, (cuuint32_t)(p.TW * L.stride), (cuuint32_t)(p.TH * L.stride), (cuuint32_t)p.TZ, 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1, 1};
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(L.src), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(small A) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {64, (cuuint64_t)p.nkb * L.N};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)L.N};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(L.wpk), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(small B) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const int grid = (int)std::min<long long>(p.total_tiles, num_sms());
+  conv_small_kernel<<<grid, SM_THREADS, smem, stream>>>(p);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+}  // namespace cetpick
+
+using namespace cetpick;
+
+// Test hook: one convolution through conv_small_kernel from a PyTorch-layout fp32 host weight (Cout, Cin, taps...).
+// src: bf16 device [B][Z][Hin][Win][C]; taps: ntaps x (dz, dy, dx) input offsets of tap t (before the stride);
+// out: bf16 (or fp32) device [B][Z][Ho][Wo][Cout].  Packs, uploads, launches, synchronises.
+extern "C" int cetpick_conv_small_bf16(const void* src, int C, int B, int Z, int Hin, int Win, int stride, int Ho, int Wo,
+                                       const float* w_host, int Cout, int ntaps, const int* taps, const float* bias,
+                                       const void* residual, int relu, int out_f32, void* out, void* stream) {
+  g_launches = 0;
+  if (!w_host || !taps || ntaps < 1 || ntaps > 27) return CETPICK_ERR_BAD_ARG;
+  if (C <= 0 || (C % 64)) return CETPICK_ERR_UNSUPPORTED;
+  std::vector<uint16_t> pk = small_pack_weights(w_host, Cout, C, ntaps, nullptr);
+  void* d = nullptr;
+  CETPICK_CUDA(cudaMalloc(&d, pk.size() * 2));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = CETPICK_OK;
+  if (cudaMemcpyAsync(d, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = CETPICK_ERR_CUDA;
+  if (rc == CETPICK_OK) {
+    SmallLaunch L;
+    L.src = src; L.C = C; L.B = B; L.Z = Z; L.Hin = Hin; L.Win = Win; L.stride = stride; L.Ho = Ho; L.Wo = Wo;
+    L.wpk = d; L.N = Cout; L.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) for (int k = 0; k < 3; ++k) L.tap[t][k] = taps[t * 3 + k];
+    L.bias = bias; L.residual = residual; L.relu = relu; L.out_f32 = out_f32; L.out = out;
+    rc = conv_small_launch(L, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_small");
+  return rc;
+}

@@ -1,0 +1,391 @@
+// Exploration-step embedding network on the device: TomoResClassifier.forward_test of
+// cet_pick/models/networks/simsiam_model.py:325-366 (arch `simsiam3d_18` / `simsiam_18`; BasicBlock :44-73, stages
+// :256-271, 3-D feature layer + heads :181-215), the network simsiam_test_hm_3d.py:136-195 runs over every candidate
+// sub-volume (BASELINE.json configs[3]: 8192 sub-volumes of 32^3).
+//
+// finalize(): every eval-mode BatchNorm (2d / 3d / 1d, affine or not) is folded into the preceding conv / Linear in
+//   double precision, weights rounded to bf16 once and packed for conv_small.cu.
+// forward(): all slices of all sub-volumes go through the 2-D trunk as one batch of small maps (the reference reshapes
+//   (B,D,H,W) -> (B*D,1,H,W), :333-337), bf16 NHWC activations:
+//     stem_pool_kernel  conv 7x7 s2 p3 (1 -> 64) + BN + ReLU + MaxPool2d(3, 2, 1)   (CUDA cores: one input channel)
+//     conv_small_kernel every 3x3 / 1x1 conv of the BasicBlocks (stride 1 / 2, residual add + ReLU in the epilogue),
+//                       the Conv3d(256,256,3) feature layer (one 2x2xD sub-volume per M-tile) and the Linear layers
+//     avgpool_kernel    AdaptiveAvgPool3d((1,1,1))
+#include "common.cuh"
+#include "conv_small.cuh"
+
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace cetpick {
+namespace {
+
+constexpr double BN_EPS = 1e-5;
+
+// conv1 7x7 s2 p3 (1->64) + BN + ReLU + MaxPool2d(3,2,1): one CTA per slice.  H = W = 32 (conv map 16x16, pooled 8x8)
+// or 16 (8x8 -> 4x4).  Thread = one conv-map row segment of 16 (or 8) pixels x 4 channels; the ReLU'd conv map goes to
+// shared memory as fp32 and is pooled from there (every window holds at least one in-map pixel and values are >= 0).
+template <int HW>
+__global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict__ in, long long nslices,
+                                                        const float* __restrict__ wgt /*[49][64], BN scale folded*/,
+                                                        const float* __restrict__ shift /*[64]*/,
+                                                        __nv_bfloat16* __restrict__ out /*[nslices][HW/4][HW/4][64]*/) {
+  constexpr int CW = HW / 2, PW = HW / 4, IP = HW + 6;
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  float* s_w = reinterpret_cast<float*>(stem_smem);                                   // [49][64]
+  float (*s_in)[IP + 1] = reinterpret_cast<float (*)[IP + 1]>(stem_smem + 49 * 64 * 4);   // [IP][IP+1]
+  // ReLU'd conv map as bf16 (max-pooling commutes with the monotone rounding); 66-element rows: odd word stride
+  __nv_bfloat16 (*s_map)[66] = reinterpret_cast<__nv_bfloat16 (*)[66]>(stem_smem + 49 * 64 * 4 + ((IP * (IP + 1) * 4 + 15) & ~15));
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 49 * 64; i += 256) s_w[i] = wgt[i];
+  const int cg = tid & 15, rowseg = tid >> 4;           // 16 channel groups x 16 row segments
+  float sh[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sh[c] = shift[cg * 4 + c];
+  for (long long s = blockIdx.x; s < nslices; s += gridDim.x) {
+    __syncthreads();
+    const float* src = in + (size_t)s * HW * HW;
+    for (int i = tid; i < IP * IP; i += 256) {
+      const int r = i / IP, c = i - r * IP;
+      const int y = r - 3, x = c - 3;
+      s_in[r][c] = (y >= 0 && y < HW && x >= 0 && x < HW) ? __ldg(src + y * HW + x) : 0.f;
+    }
+    __syncthreads();
+    // conv rows: CW rows of CW pixels; a thread takes SEG pixels of one row
+    constexpr int SEG = CW * CW / 16;                   // pixels per thread: 16 (HW 32) or 4 (HW 16)
+    const int p0 = rowseg * SEG, oy = p0 / CW, ox0 = p0 % CW;
+    float acc[SEG][4];
+#pragma unroll
+    for (int i = 0; i < SEG; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = sh[c];
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[(ky * 7 + kx) * 64 + cg * 4]);
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+          const float v = s_in[2 * oy + ky][2 * (ox0 + i) + kx];
+          acc[i][0] = fmaf(v, w4.x, acc[i][0]); acc[i][1] = fmaf(v, w4.y, acc[i][1]);
+          acc[i][2] = fmaf(v, w4.z, acc[i][2]); acc[i][3] = fmaf(v, w4.w, acc[i][3]);
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < SEG; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s_map[p0 + i][cg * 4 + c] = __float2bfloat16_rn(fmaxf(acc[i][c], 0.f));
+    __syncthreads();
+    // MaxPool2d(3, stride 2, pad 1) on the CW x CW map -> PW x PW
+    for (int o = tid; o < PW * PW * 32; o += 256) {
+      const int c2 = o & 31, pp = o >> 5, py = pp / PW, px = pp % PW;
+      float m0 = 0.f, m1 = 0.f;                         // post-ReLU values: 0 is a safe identity
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = 2 * py + dy;
+        if (y < 0 || y >= CW) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = 2 * px + dx;
+          if (x < 0 || x >= CW) continue;
+          m0 = fmaxf(m0, __bfloat162float(s_map[y * CW + x][2 * c2]));
+          m1 = fmaxf(m1, __bfloat162float(s_map[y * CW + x][2 * c2 + 1]));
+        }
+      }
+      reinterpret_cast<__nv_bfloat162*>(out + ((size_t)s * PW * PW + pp) * 64)[c2] = __floats2bfloat162_rn(m0, m1);
+    }
+  }
+}
+
+// AdaptiveAvgPool3d((1,1,1)): bf16 [B][P][C] -> bf16 [B][C] (fp32 sum); one CTA per batch element, C = 256 threads
+__global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int P, int C,
+                                                      __nv_bfloat16* __restrict__ out) {
+  for (int b = blockIdx.x; b < B; b += gridDim.x)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.f;
+      const __nv_bfloat16* src = in + (size_t)b * P * C + c;
+      for (int i = 0; i < P; ++i) a += __bfloat162float(src[(size_t)i * C]);
+      out[(size_t)b * C + c] = __float2bfloat16_rn(a / (float)P);
+    }
+}
+
+struct Fold { std::vector<double> scale, shift; };
+
+}  // namespace
+}  // namespace cetpick
+
+using namespace cetpick;
+
+struct cetpick_simsiam {
+  int layers[3];
+  bool has_proj, has_pred;
+  std::map<std::string, std::vector<float>> params;
+  bool finalized = false;
+  std::vector<uint8_t> blob;
+  void* d_blob = nullptr;
+  struct Conv { size_t w_off = 0, b_off = 0; int Cin = 0, Cout = 0, ntaps = 0, stride = 1; bool has_bias = false; };
+  struct Block { Conv c1, c2, ds; bool has_ds = false; };
+  size_t stem_w = 0, stem_b = 0;
+  std::vector<Block> blocks;
+  Conv f3d, fc, proj0, proj3, proj6, pred0, pred3;
+
+  const std::vector<float>* get(const std::string& k, size_t numel) const {
+    auto it = params.find(k);
+    if (it == params.end() || it->second.size() != numel) return nullptr;
+    return &it->second;
+  }
+};
+
+namespace {
+
+size_t balloc(cetpick_simsiam* m, size_t bytes) {
+  const size_t off = align_up(m->blob.size(), 256);
+  m->blob.resize(off + bytes, 0);
+  return off;
+}
+
+bool bn_fold(const cetpick_simsiam* m, const std::string& p, int C, bool affine, Fold& f) {
+  auto mu = m->get(p + ".running_mean", C), var = m->get(p + ".running_var", C);
+  auto w = affine ? m->get(p + ".weight", C) : nullptr, b = affine ? m->get(p + ".bias", C) : nullptr;
+  if (!mu || !var || (affine && (!w || !b))) return false;
+  f.scale.resize(C); f.shift.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const double s = (affine ? (double)(*w)[c] : 1.0) / std::sqrt((double)(*var)[c] + BN_EPS);
+    f.scale[c] = s;
+    f.shift[c] = (affine ? (double)(*b)[c] : 0.0) - (double)(*mu)[c] * s;
+  }
+  return true;
+}
+
+// conv / Linear weight (Cout, Cin, taps) with an optional BatchNorm behind it and an optional bias of its own
+bool pack(cetpick_simsiam* m, const std::string& wkey, int Cout, int Cin, int ntaps, int stride, const Fold* fold,
+          const std::vector<float>* own_bias, cetpick_simsiam::Conv& c) {
+  auto w = m->get(wkey, (size_t)Cout * Cin * ntaps);
+  if (!w || (Cin % 64)) return false;
+  const std::vector<uint16_t> pk = small_pack_weights(w->data(), Cout, Cin, ntaps, fold ? fold->scale.data() : nullptr);
+  c.w_off = balloc(m, pk.size() * 2);
+  memcpy(m->blob.data() + c.w_off, pk.data(), pk.size() * 2);
+  c.Cin = Cin; c.Cout = Cout; c.ntaps = ntaps; c.stride = stride;
+  c.has_bias = fold || own_bias;
+  if (c.has_bias) {
+    c.b_off = balloc(m, (size_t)Cout * 4);
+    float* b = reinterpret_cast<float*>(m->blob.data() + c.b_off);
+    for (int n = 0; n < Cout; ++n) {
+      double v = own_bias ? (double)(*own_bias)[n] : 0.0;
+      if (fold) v = v * fold->scale[n] + fold->shift[n];
+      b[n] = (float)v;
+    }
+  }
+  return true;
+}
+
+struct Geo { int h0, h1, h2, h3; };   // conv map, after pool (layer1), layer2, layer3
+
+bool geometry(int64_t H, int64_t W, Geo& g) {
+  if (H != W || (H != 32 && H != 16)) return false;     // small maps whose pixel count divides the 128-row M-tile
+  g.h0 = (int)H / 2; g.h1 = g.h0 / 2; g.h2 = g.h1 / 2; g.h3 = std::max(1, g.h2 / 2);
+  return g.h2 >= 2;
+}
+
+size_t ws_bytes_for(const cetpick_simsiam* m, int64_t B, int64_t D, const Geo& g) {
+  (void)m;
+  const size_t n = (size_t)B * D;
+  const size_t a1 = align_up(n * g.h1 * g.h1 * 64 * 2, 1024);       // layer1 maps (three rotating buffers)
+  return 3 * a1 + 1024 + align_up((size_t)B * 256 * 2, 1024) * 4;
+}
+
+int run(const cetpick_simsiam* m, const cetpick_simsiam::Conv& c, const void* src, int B, int Z, int Hin, int Win, int Ho,
+        int Wo, bool is3d, const void* residual, int relu, int out_f32, void* out, cudaStream_t st) {
+  SmallLaunch L;
+  L.src = src; L.C = c.Cin; L.B = B; L.Z = Z; L.Hin = Hin; L.Win = Win; L.stride = c.stride; L.Ho = Ho; L.Wo = Wo;
+  L.wpk = static_cast<const uint8_t*>(m->d_blob) + c.w_off; L.N = c.Cout; L.ntaps = c.ntaps;
+  int t = 0;
+  if (c.ntaps == 1) { L.tap[0][0] = L.tap[0][1] = L.tap[0][2] = 0; }
+  else if (c.ntaps == 9) {
+    for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) { L.tap[t][0] = 0; L.tap[t][1] = ky - 1; L.tap[t][2] = kx - 1; ++t; }
+  } else {
+    for (int kz = 0; kz < 3; ++kz) for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) {
+      L.tap[t][0] = kz - 1; L.tap[t][1] = ky - 1; L.tap[t][2] = kx - 1; ++t;
+    }
+  }
+  (void)is3d;
+  L.bias = c.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + c.b_off) : nullptr;
+  L.residual = residual; L.relu = relu; L.out_f32 = out_f32; L.out = out;
+  return conv_small_launch(L, st);
+}
+
+}  // namespace
+
+extern "C" int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int has_proj,
+                                      int has_pred) {
+  if (!plan || blocks1 < 1 || blocks2 < 1 || blocks3 < 1 || blocks1 > 8 || blocks2 > 8 || blocks3 > 8) return CETPICK_ERR_BAD_ARG;
+  if (has_pred && !has_proj) return CETPICK_ERR_BAD_ARG;     // 'pred' is applied to the 'proj' output (:360-363)
+  cetpick_simsiam* m = new cetpick_simsiam();
+  m->layers[0] = blocks1; m->layers[1] = blocks2; m->layers[2] = blocks3;
+  m->has_proj = has_proj != 0; m->has_pred = has_pred != 0;
+  *plan = m;
+  return CETPICK_OK;
+}
+
+extern "C" void cetpick_simsiam_destroy(cetpick_simsiam* m) {
+  if (!m) return;
+  if (m->d_blob) cudaFree(m->d_blob);
+  delete m;
+}
+
+extern "C" int cetpick_simsiam_set_param(cetpick_simsiam* m, const char* key, const float* data, int64_t numel) {
+  if (!m || !key || (!data && numel > 0) || numel < 0) return CETPICK_ERR_BAD_ARG;
+  const std::string k(key);
+  if (k.size() >= 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return CETPICK_OK;
+  m->params[k].assign(data, data + numel);
+  m->finalized = false;
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_simsiam_finalize(cetpick_simsiam* m) {
+  if (!m) return CETPICK_ERR_BAD_ARG;
+  m->blob.clear();
+  m->blocks.clear();
+  Fold f;
+  {
+    auto w = m->get("conv1.weight", 64 * 49);
+    if (!w || !bn_fold(m, "bn1", 64, true, f)) return CETPICK_ERR_STATE;
+    m->stem_w = balloc(m, 49 * 64 * 4);
+    m->stem_b = balloc(m, 64 * 4);
+    float* sw = reinterpret_cast<float*>(m->blob.data() + m->stem_w);
+    float* sb = reinterpret_cast<float*>(m->blob.data() + m->stem_b);
+    for (int c = 0; c < 64; ++c) {
+      for (int t = 0; t < 49; ++t) sw[t * 64 + c] = (float)((double)(*w)[c * 49 + t] * f.scale[c]);
+      sb[c] = (float)f.shift[c];
+    }
+  }
+  int inpl = 64;
+  const int planes[3] = {64, 128, 256};
+  for (int li = 0; li < 3; ++li)
+    for (int b = 0; b < m->layers[li]; ++b) {
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+      const int pl = planes[li], cin = b == 0 ? inpl : pl, stride = (li > 0 && b == 0) ? 2 : 1;
+      cetpick_simsiam::Block blk;
+      if (!bn_fold(m, p + ".bn1", pl, true, f) || !pack(m, p + ".conv1.weight", pl, cin, 9, stride, &f, nullptr, blk.c1)) return CETPICK_ERR_STATE;
+      if (!bn_fold(m, p + ".bn2", pl, true, f) || !pack(m, p + ".conv2.weight", pl, pl, 9, 1, &f, nullptr, blk.c2)) return CETPICK_ERR_STATE;
+      blk.has_ds = m->params.count(p + ".downsample.0.weight") != 0;
+      if (blk.has_ds && !pack(m, p + ".downsample.0.weight", pl, cin, 1, stride, nullptr, nullptr, blk.ds)) return CETPICK_ERR_STATE;
+      if (!blk.has_ds && (stride != 1 || cin != pl)) return CETPICK_ERR_STATE;
+      m->blocks.push_back(blk);
+      inpl = pl;
+    }
+  if (!bn_fold(m, "feature_3d.1", 256, true, f) || !pack(m, "feature_3d.0.weight", 256, 256, 27, 1, &f, nullptr, m->f3d)) return CETPICK_ERR_STATE;
+  {
+    auto b = m->get("fc.bias", 256);
+    if (!b || !pack(m, "fc.weight", 256, 256, 1, 1, nullptr, b, m->fc)) return CETPICK_ERR_STATE;
+  }
+  if (m->has_proj) {
+    if (!bn_fold(m, "proj.1", 256, true, f) || !pack(m, "proj.0.weight", 256, 256, 1, 1, &f, nullptr, m->proj0)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.4", 256, true, f) || !pack(m, "proj.3.weight", 256, 256, 1, 1, &f, nullptr, m->proj3)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.7", 256, false, f) || !pack(m, "proj.6.weight", 256, 256, 1, 1, &f, nullptr, m->proj6)) return CETPICK_ERR_STATE;
+  }
+  if (m->has_pred) {
+    auto b = m->get("pred.3.bias", 256);
+    if (!bn_fold(m, "pred.1", 256, true, f) || !pack(m, "pred.0.weight", 256, 256, 1, 1, &f, nullptr, m->pred0)) return CETPICK_ERR_STATE;
+    if (!b || !pack(m, "pred.3.weight", 256, 256, 1, 1, nullptr, b, m->pred3)) return CETPICK_ERR_STATE;
+  }
+  if (m->d_blob) { cudaFree(m->d_blob); m->d_blob = nullptr; }
+  CETPICK_CUDA(cudaMalloc(&m->d_blob, m->blob.size()));
+  CETPICK_CUDA(cudaMemcpy(m->d_blob, m->blob.data(), m->blob.size(), cudaMemcpyHostToDevice));
+  m->finalized = true;
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* m, int64_t B, int64_t D, int64_t H, int64_t W,
+                                               size_t* bytes) {
+  Geo g;
+  if (!m || !bytes || B <= 0 || D <= 0) return CETPICK_ERR_BAD_ARG;
+  if (!geometry(H, W, g)) return CETPICK_ERR_UNSUPPORTED;
+  *bytes = ws_bytes_for(m, B, D, g);
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64_t B64, int64_t D64, int64_t H, int64_t W,
+                                       float* proj, float* pred, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  if (!m || !x || B64 <= 0 || D64 <= 0 || B64 > (1 << 24) || D64 > 4096) return CETPICK_ERR_BAD_ARG;
+  if (!m->finalized) return CETPICK_ERR_STATE;
+  if ((proj && !m->has_proj) || (pred && !m->has_pred) || (!proj && !pred)) return CETPICK_ERR_BAD_ARG;
+  Geo g;
+  if (!geometry(H, W, g)) return CETPICK_ERR_UNSUPPORTED;
+  const int B = (int)B64, D = (int)D64;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  if (!ws || ws_bytes < ws_bytes_for(m, B, D, g)) return CETPICK_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * D;
+  const size_t a1 = align_up((size_t)n * g.h1 * g.h1 * 64 * 2, 1024);
+  __nv_bfloat16* buf[3] = {reinterpret_cast<__nv_bfloat16*>(base), reinterpret_cast<__nv_bfloat16*>(base + a1),
+                           reinterpret_cast<__nv_bfloat16*>(base + 2 * a1)};
+  const size_t v1 = align_up((size_t)B * 256 * 2, 1024);
+  __nv_bfloat16* vec[4];
+  for (int i = 0; i < 4; ++i) vec[i] = reinterpret_cast<__nv_bfloat16*>(base + 3 * a1 + (size_t)i * v1);
+  const uint8_t* blob = static_cast<const uint8_t*>(m->d_blob);
+  int rc;
+
+  {  // conv1 + bn1 + relu + maxpool -> buf[0]: (n, h1, h1, 64)
+    const int grid = (int)std::min<long long>(n, (long long)num_sms() * 8);
+    const float* sw = reinterpret_cast<const float*>(blob + m->stem_w);
+    const float* sb = reinterpret_cast<const float*>(blob + m->stem_b);
+    auto smem_of = [](int hw) { const int ip = hw + 6, cw = hw / 2; return 49 * 64 * 4 + ((ip * (ip + 1) * 4 + 15) & ~15) + cw * cw * 66 * 2; };
+    static bool attr_done = false;
+    if (!attr_done) {
+      CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32)));
+      CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(16)));
+      attr_done = true;
+    }
+    if (H == 32) stem_pool_kernel<32><<<grid, 256, smem_of(32), st>>>(x, n, sw, sb, buf[0]);
+    else stem_pool_kernel<16><<<grid, 256, smem_of(16), st>>>(x, n, sw, sb, buf[0]);
+    CETPICK_LAUNCH_CHECK();
+  }
+  // BasicBlocks: x -> relu(bn1(conv1(x))) -> bn2(conv2(.)) + (x | downsample(x)) -> relu
+  int cur = 0, hin = g.h1, bi = 0;
+  for (int li = 0; li < 3; ++li)
+    for (int b = 0; b < m->layers[li]; ++b, ++bi) {
+      const cetpick_simsiam::Block& blk = m->blocks[bi];
+      const int hout = blk.c1.stride == 2 ? hin / 2 : hin;
+      if (hout < 1) return CETPICK_ERR_UNSUPPORTED;
+      const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+      if ((rc = run(m, blk.c1, buf[cur], 1, (int)n, hin, hin, hout, hout, false, nullptr, 1, 0, buf[t1], st))) return rc;
+      const void* res = buf[cur];
+      if (blk.has_ds) {
+        if ((rc = run(m, blk.ds, buf[cur], 1, (int)n, hin, hin, hout, hout, false, nullptr, 0, 0, buf[t2], st))) return rc;
+        res = buf[t2];
+      }
+      // conv2 + bn2 + residual + relu; the output may overwrite the block input unless that IS the residual
+      __nv_bfloat16* dst = blk.has_ds ? buf[cur] : buf[t2];
+      if ((rc = run(m, blk.c2, buf[t1], 1, (int)n, hout, hout, hout, hout, false, res, 1, 0, dst, st))) return rc;
+      cur = blk.has_ds ? cur : t2;
+      hin = hout;
+    }
+  // (B, D, h, w, 256) -> Conv3d 3x3x3 pad 1 + BN3d + ReLU (:348-354); one sub-volume (D*h*w positions) per M-tile
+  const int P = D * hin * hin;
+  if (P != 128) return CETPICK_ERR_UNSUPPORTED;            // 32 slices of 2x2 (or 16x... ) must fill one 128-row tile
+  const int t1 = (cur + 1) % 3;
+  if ((rc = run(m, m->f3d, buf[cur], B, D, hin, hin, hin, hin, true, nullptr, 1, 0, buf[t1], st))) return rc;
+  avgpool_kernel<<<std::min(B, num_sms() * 8), 256, 0, st>>>(buf[t1], B, P, 256, vec[0]);
+  CETPICK_LAUNCH_CHECK();
+  // fc, then the heads: Linear (+ folded BatchNorm1d) (+ ReLU) as 1x1 "convolutions" over the batch axis
+  if ((rc = run(m, m->fc, vec[0], 1, B, 1, 1, 1, 1, false, nullptr, 0, 0, vec[1], st))) return rc;
+  if (m->has_proj) {
+    if ((rc = run(m, m->proj0, vec[1], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[2], st))) return rc;
+    if ((rc = run(m, m->proj3, vec[2], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[3], st))) return rc;
+    // proj.6 + BN(affine=False): fp32 out for the caller, bf16 copy as the input of 'pred'
+    if (proj && (rc = run(m, m->proj6, vec[3], 1, B, 1, 1, 1, 1, false, nullptr, 0, 1, proj, st))) return rc;
+    if (pred) {
+      if ((rc = run(m, m->proj6, vec[3], 1, B, 1, 1, 1, 1, false, nullptr, 0, 0, vec[2], st))) return rc;
+      if ((rc = run(m, m->pred0, vec[2], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[0], st))) return rc;
+      if ((rc = run(m, m->pred3, vec[0], 1, B, 1, 1, 1, 1, false, nullptr, 0, 1, pred, st))) return rc;
+    }
+  }
+  return CETPICK_OK;
+}

@@ -421,11 +421,14 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
 }
 
 // conv1 + conv2 (+ pool) of a 32-channel full-resolution block as ONE kernel (conv_block.cu) when both layers were
-// packed for the marching kernel and a thread-block cluster can span the row.  CETPICK_NO_BLOCK=1 keeps the two
-// separate kernels (A/B measurements).
+// packed for the marching kernel and a thread-block cluster can span the row.  CETPICK_BLOCK=1 selects it (A/B measurements).
 bool use_block(const PackedConv& c1, const PackedConv& c2, int W) {
-  static const bool off = [] { const char* e = getenv("CETPICK_NO_BLOCK"); return e && e[0] == '1'; }();
-  return !off && c1.march == MARCH_2D_ROWS && c2.march == MARCH_2D_ROWS && c1.Ntot == 32 && c2.Ntot == 32 && c2.nsrc == 1 &&
+  // Off unless CETPICK_BLOCK=1: the fused kernel is exact but, with one 128-pixel M-tile per CTA and a single group of
+  // conv1 epilogue warps on the critical path of every row, it is slower than the two marching kernels it replaces
+  // (profiles/r3o_block_*: tensor pipe 10 % active, latency-bound); see DESIGN.md.
+  const char* e = getenv("CETPICK_BLOCK");
+  const bool on = e && e[0] == '1';
+  return on && c1.march == MARCH_2D_ROWS && c2.march == MARCH_2D_ROWS && c1.Ntot == 32 && c2.Ntot == 32 && c2.nsrc == 1 &&
          c2.C[0] == 32 && c1.relu && c2.relu && c1.has_bias && c2.has_bias && W > 128 && block_supported(c1.C[0], c1.nsrc, W);
 }
 

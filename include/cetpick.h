@@ -205,6 +205,35 @@ int cetpick_unet_forward_slab(cetpick_unet* plan, const float* tomo, const uint8
                               const float* level_values_host, int64_t D, int64_t H, int64_t W, int64_t z_origin,
                               float* hm, int apply_sigmoid, float* proj, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exploration-step embedding network.  Replaces TomoResClassifier.forward_test
+ * (cet_pick/models/networks/simsiam_model.py:325-366; arch simsiam_18 / simsiam3d_18), called per batch of candidate
+ * sub-volumes by simsiam_test_hm_3d.py:169.  Same arithmetic conventions as the detector: BF16 operands on tcgen05
+ * tensor cores, FP32 accumulation, every eval-mode BatchNorm folded, residual adds / ReLU in the epilogues.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cetpick_simsiam cetpick_simsiam;
+
+/* blocks1..3: BasicBlocks per stage (2,2,2 for *_18; 3,4,6 for *_34).  has_proj / has_pred: which heads exist. */
+int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int has_proj, int has_pred);
+void cetpick_simsiam_destroy(cetpick_simsiam* plan);
+/* one tensor of the reference state_dict by its key, host float32, PyTorch layout */
+int cetpick_simsiam_set_param(cetpick_simsiam* plan, const char* key, const float* data_host, int64_t numel);
+int cetpick_simsiam_finalize(cetpick_simsiam* plan);
+int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* plan, int64_t B, int64_t D, int64_t H, int64_t W, size_t* bytes);
+/* x: (B,D,H,W) float32 device sub-volumes (H = W = 32 with D = 32, or H = W = 16 with D = 128: the trunk's final
+ * 2x2xD (1x1xD) map fills one 128-row tile; other sizes return CETPICK_ERR_UNSUPPORTED).
+ * proj / pred: (B,256) float32 device out, either may be NULL. */
+int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, int64_t D, int64_t H, int64_t W,
+                            float* proj, float* pred, void* ws, size_t ws_bytes, void* stream);
+
+/* Test hook: ONE convolution through the small-map implicit-GEMM kernel (csrc/conv_small.cu).  src: bf16 device
+ * [B][Z][Hin][Win][C] (C a multiple of 64); w_host: fp32 HOST weight (Cout, C, ntaps); taps: ntaps x (dz,dy,dx) input
+ * offsets relative to stride * output position; bias: fp32 device [Cout] or null; residual: bf16 device
+ * [B][Z][Ho][Wo][Cout] or null; out: bf16 (out_f32 = 0) or fp32 device [B][Z][Ho][Wo][Cout].  Wo*Ho must divide 128. */
+int cetpick_conv_small_bf16(const void* src, int C, int B, int Z, int Hin, int Win, int stride, int Ho, int Wo,
+                            const float* w_host, int Cout, int ntaps, const int* taps, const float* bias,
+                            const void* residual, int relu, int out_f32, void* out, void* stream);
+
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);

@@ -34,7 +34,22 @@ if rc != 0:
     for k in range(min(n_to, 60)):
         e = [dbg[4 + 4 * k + i] for i in range(4)]
         print("   cta %3d warp %2d waits %-18s a=%d b=%d" % (e[0] >> 8, e[0] & 255, names.get(e[1], e[1]), e[2], e[3]))
-if rc == 0:
+if rc == 0 and os.environ.get("TIME"):
+    import ctypes as C
+    # time the kernel alone: pre-packed weights through the product path are not exposed, so time the hook minus its
+    # fixed host work by differencing two sizes is overkill: use CUDA events around 5 calls (the hook synchronises)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(5):
+        ev0.record()
+        L.lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
+                                        w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(), b2h.data_ptr(),
+                                        out.data_ptr(), pl.data_ptr() if pool else None, L.stream_ptr())
+        ev1.record(); torch.cuda.synchronize()
+        ts.append(ev0.elapsed_time(ev1))
+    print("  ms per call (incl. weight upload): min %.3f median %.3f" % (min(ts), sorted(ts)[2]),
+          {k: v for k, v in os.environ.items() if k.startswith("CETPICK_BLOCK")})
+if rc == 0 and not os.environ.get("TIME"):
     xin = torch.cat(srcs, 3).float().permute(0, 3, 1, 2)
     r1 = F.relu(F.conv2d(xin, w1.float(), b1, padding=1)).bfloat16().float()
     ref = F.relu(F.conv2d(r1, w2.float(), b2, padding=1)).permute(0, 2, 3, 1)
