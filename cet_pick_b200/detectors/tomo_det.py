@@ -22,6 +22,25 @@ class TomodetDetector(BaseDetector):
         # `_sigmoid(hm)` mutates output['hm'] in place in the reference (:33); fusing it into the hm
         # epilogue leaves the same tensor in both places
         self.model.fuse_sigmoid = True
+        # opt.async_write (or set_async_write): finished heat-maps go to <name>_hm.mrc from writer threads while the GPU
+        # works on the next tomogram; run() then returns before the files exist and flush() waits for them
+        self._writer = None
+        self._pool = None
+        if getattr(opt, "async_write", False):
+            self.set_async_write(True)
+
+    def set_async_write(self, on=True, threads=3):
+        from ..utils.async_io import AsyncWriter, PinnedPool
+        self.flush()
+        if self._writer is not None:
+            self._writer.close()
+        self._writer = AsyncWriter(threads, max_pending=threads + 1) if on else None
+        self._pool = PinnedPool(threads + 2) if on else None
+
+    def flush(self):
+        """wait until every pick file / heat-map of the tomograms run() has returned for is on disk"""
+        if getattr(self, "_writer", None) is not None:
+            self._writer.flush()
 
     def process(self, images, return_time=False):
         with torch.no_grad():
@@ -63,12 +82,43 @@ class TomodetDetector(BaseDetector):
             sw = vol.permute(1, 0, 2).contiguous()             # np.swapaxes(hm, 1, 0): (H', D, W')
             sd, mean = torch.std_mean(vol.double(), correction=0)
             mn, mx = torch.aminmax(vol)
+            max_y, max_z, max_x = sw.shape
+            if getattr(self, "_writer", None) is not None:
+                # asynchronous path: D2H into a pooled page-locked buffer, the file write happens on a writer thread
+                host = self._pool.get(sw.shape, sw.dtype)
+                st_dev = torch.stack([mn.double(), mx.double(), mean, sd])
+                st_host = torch.empty(4, dtype=torch.float64, pin_memory=True)
+                if getattr(self, "_copy_stream", None) is None:
+                    self._copy_stream = torch.cuda.Stream(hm.device)
+                cs = self._copy_stream                          # the copy engine works under the next tomogram's kernels
+                cs.wait_stream(torch.cuda.current_stream(hm.device))
+                with torch.cuda.stream(cs):
+                    host.copy_(sw, non_blocking=True)
+                    st_host.copy_(st_dev, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cs)
+                sw.record_stream(cs)
+                st_dev.record_stream(cs)
+                lines = self._pick_lines(dets, max_z, max_x * 2, max_y * 2)
+                mrc_path, txt_path = os.path.join(path, "{}_hm.mrc".format(name)), os.path.join(path, "{}.txt".format(name))
+                pool = self._pool
+
+                def job():
+                    done.synchronize()
+                    try:
+                        write_mrc(mrc_path, host.numpy(), tuple(float(v) for v in st_host))
+                    finally:
+                        pool.put(host)
+                    with open(txt_path, "w+") as f:
+                        f.write("".join(ln + "\n" for ln in lines))
+
+                self._writer.submit(job)
+                return
             host = self._pinned_like(sw)
             host.copy_(sw, non_blocking=True)
             st = torch.stack([mn.double(), mx.double(), mean, sd]).cpu()   # synchronises: `host` is complete
             stats = tuple(float(v) for v in st)
             hm = host.numpy()
-            max_y, max_z, max_x = hm.shape
         else:
             hm = hm.numpy()[0][0]
             max_z, max_y, max_x = hm.shape
@@ -77,6 +127,13 @@ class TomodetDetector(BaseDetector):
                 raise ValueError("Output contains NaN values")
         max_x, max_y = max_x * 2, max_y * 2
         write_mrc(os.path.join(path, "{}_hm.mrc".format(name)), hm, stats)
+        lines = self._pick_lines(dets, max_z, max_x, max_y)
+        with open(os.path.join(path, "{}.txt".format(name)), "w+") as f:
+            for ln in lines:
+                print(ln, file=f)
+
+    def _pick_lines(self, dets, max_z, max_x, max_y):
+        """tomo_det.py:69-83: one `x\tz\ty[\tscore]` line per pick that passes the score / z-cutoff / 20-px border filter"""
         o = self.opt
         if o.fiber or o.spike:
             raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
@@ -93,9 +150,7 @@ class TomodetDetector(BaseDetector):
                         lines.append(str(x) + "\t" + str(z) + "\t" + str(y))
                     else:
                         lines.append(str(x) + "\t" + str(z) + "\t" + str(y) + "\t" + str(score))
-        with open(os.path.join(path, "{}.txt".format(name)), "w+") as f:
-            for ln in lines:
-                print(ln, file=f)
+        return lines
 
     def _pinned_like(self, t):
         """page-locked staging buffer for the heat-map copy, kept across tomograms"""

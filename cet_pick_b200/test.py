@@ -21,6 +21,7 @@ from .detectors.detector_factory import detector_factory
 from .opts import opts
 from .shard import shard_range
 from .utils import loader
+from .utils.async_io import Prefetcher
 
 
 def read_image_list(path):
@@ -60,16 +61,27 @@ def test(opt):
     items = read_image_list(os.path.join(opt.data_dir, opt.test_img_txt))
     first, count = shard_range(len(items), rank, world)
     stats = {}
-    for name, path in items[first:first + count]:
+    # Overlap around the detector (the reference overlaps only the read, test.py:77): a reader thread prepares the next
+    # tomogram (MRC read + GPU pre-processing on its own stream, shipped as uint8 levels) while the current one is in the
+    # detector, and writer threads put finished heat-maps on disk while the GPU moves on.
+    if hasattr(detector, "set_async_write"):
+        detector.set_async_write(True)
+
+    def prepare(item):
+        name, path = item
+        rec = loader.load_rec(path, order=opt.order, compress=opt.compress)
+        return loader.preprocess_levels(rec, denoise=opt.gauss)
+
+    t0 = time.time()
+    for (name, path), (levels, level_values) in Prefetcher(items[first:first + count], prepare):
+        ret = detector.run(levels[None], {"name": [name], "zdim": levels.shape[0], "level_values": level_values})
+        ret["load"] = max(0.0, time.time() - t0 - ret["tot_time"])     # wait for the reader (read + pre-processing not hidden)
         t0 = time.time()
-        vol = loader.load_tomos_from_list([name], [path], order=opt.order, compress=opt.compress, denoise=opt.gauss,
-                                          dtype=torch.float32)[name]
-        torch.cuda.synchronize()
-        ret = detector.run(vol[None], {"name": [name], "zdim": vol.shape[0]})
-        ret["load"] = time.time() - t0 - ret["tot_time"]           # file read + GPU pre-processing
         print(f"{opt.exp_id} {name}: " + " |".join(f"{k} {v:.3f}s" for k, v in ret.items()))
         for k, v in ret.items():
             stats.setdefault(k, []).append(v)
+    if hasattr(detector, "flush"):
+        detector.flush()                                   # every <name>.txt / <name>_hm.mrc is on disk when test() returns
     return stats
 
 

@@ -154,3 +154,35 @@ def test_command_line_entry(tmp_path, monkeypatch):
         n_lines += len(lines)
         assert mrcio.read_mrc(os.path.join(opt.out_path, f"tomo{i}_hm.mrc")).shape == (32, 12, 48)     # (H', D, W')
     assert n_lines > 0
+
+
+def test_async_write_and_uint8_levels_give_identical_files(tmp_path, monkeypatch):
+    """run() with the writer threads (set_async_write) and with the tomogram shipped as uint8 levels must leave the
+    same `<name>.txt` and the same heat-map bytes on disk as the blocking float32 path."""
+    from cet_pick_b200 import synth
+    from cet_pick_b200.detectors.detector_factory import detector_factory
+    from cet_pick_b200.opts import opts
+    sd = synth.unet_state_dict_torch(317, 4)
+    ckpt = os.path.join(tmp_path, "model.pth")
+    torch.save({"epoch": 1, "state_dict": sd}, ckpt)
+    monkeypatch.chdir(tmp_path)
+    opt = opts().init(["semi", "--arch", "unet_4", "--load_model", ckpt, "--K", "60", "--out_thresh", "0.0",
+                       "--cutoff_z", "0", "--with_score", "--out_id", "out", "--exp_id", "aw", "--gpus", "0"])
+    det = detector_factory[opt.task](opt)
+    D, H, W = 10, 96, 128
+    vols = [synth.tomogram_np(D, H, W, 20 + i) for i in range(3)]
+    opt.out_path = os.path.join(tmp_path, "sync")
+    for i, v in enumerate(vols):
+        det.run(torch.from_numpy(v)[None], {"name": [f"t{i}"]})
+    opt.out_path = os.path.join(tmp_path, "async")
+    det.set_async_write(True, threads=2)
+    for i, v in enumerate(vols):
+        q = torch.from_numpy(np.rint(v * 255.0).astype(np.uint8))
+        det.run(q[None], {"name": [f"t{i}"], "level_values": None})
+    det.flush()
+    det.set_async_write(False)
+    for i in range(3):
+        for suffix in (".txt", "_hm.mrc"):
+            a = open(os.path.join(tmp_path, "sync", f"t{i}{suffix}"), "rb").read()
+            b = open(os.path.join(tmp_path, "async", f"t{i}{suffix}"), "rb").read()
+            assert a == b, f"t{i}{suffix} differs between the blocking and the asynchronous path"

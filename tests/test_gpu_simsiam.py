@@ -108,7 +108,7 @@ def test_forward_test_vs_reference_golden(golden):
         e_abs, e_rel = float(np.abs(got - ref).max()), rel_err(got, ref)
         print(f"simsiam3d {k}: max-abs err {e_abs:.3e} (|ref| max {np.abs(ref).max():.3f}), relative L2 err {e_rel:.3e}")
         assert got.shape == ref.shape
-        assert e_rel <= 3e-2 and e_abs <= 5e-2 * max(1.0, float(np.abs(ref).max()))      # BF16 operands through 20 layers
+        assert e_rel <= 1e-2 and e_abs <= 1e-2      # BF16 operands through 20 layers (measured 3e-3 / 2.6e-3)
 
 
 def test_forward_test_vs_oracle_batch():
@@ -124,8 +124,8 @@ def test_forward_test_vs_oracle_batch():
     for k in ("proj", "pred"):
         got, r = out[k].cpu().numpy(), ref[k].numpy()
         print(f"simsiam3d batch {k}: max-abs {np.abs(got - r).max():.3e}, relative L2 {rel_err(got, r):.3e}")
-        assert rel_err(got, r) <= 3e-2
+        assert rel_err(got, r) <= 1e-2
     # embeddings are what the exploration step clusters: nearest neighbours by cosine similarity must agree
     a, b = out["proj"].cpu().numpy(), ref["proj"].numpy()
     cos = lambda v: (v / np.linalg.norm(v, axis=1, keepdims=True)) @ (v / np.linalg.norm(v, axis=1, keepdims=True)).T
-    assert np.abs(cos(a) - cos(b)).max() <= 5e-2
+    assert np.abs(cos(a) - cos(b)).max() <= 2e-2
