@@ -26,6 +26,7 @@ SIGNATURES = {
     "cetpick_decode_f32": (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "cetpick_decode_status": (_int, [_vp, _vp, C.POINTER(_int), C.POINTER(_i64)]),
     "cetpick_decode_debug_state": (_int, [_vp, _vp, _vp]),
+    "cetpick_rows_from_indices_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "cetpick_nms_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _vp]),
     "cetpick_greedy_nms_workspace_bytes": (_int, [_i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_greedy_nms_f32": (_int, [_vp, _i64, _i64, _i64, C.c_double, C.c_double, C.c_double, _i64, _vp, _vp, _i64,

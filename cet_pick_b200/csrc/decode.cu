@@ -1579,6 +1579,34 @@ extern "C" int cetpick_nms_f32(const float* heat, float* out, int64_t B, int64_t
   return CETPICK_OK;
 }
 
+// rows [x+0.25, y+0.25, z, score, score] of given (score, linear index) pairs: decode.py:35-41 + :141-154
+__global__ void __launch_bounds__(256) rows_from_inds_kernel(const float* __restrict__ scores, const long long* __restrict__ inds,
+                                                             long long n, int hw, int W, float* __restrict__ dets) {
+  const long long i = blockIdx.x * 256ll + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t idx = (uint32_t)inds[i];
+  const float fhw = (float)hw, fw = (float)W;
+  const float zf = floorf((float)idx / fhw);
+  const int z = (int)zf;
+  const int t = (int)idx - z * hw;
+  const float yf = floorf((float)t / fw);
+  int x = t % W;
+  if (x < 0) x += W;
+  float* d = dets + i * 5;
+  d[0] = (float)x + 0.25f; d[1] = yf + 0.25f; d[2] = (float)z; d[3] = scores[i]; d[4] = scores[i];
+}
+
+extern "C" int cetpick_rows_from_indices_f32(const float* scores, const int64_t* inds, int64_t n, int64_t D, int64_t H,
+                                             int64_t W, float* dets, void* stream) {
+  g_launches = 0;
+  if (!scores || !inds || !dets || n < 0 || D <= 0 || H <= 0 || W <= 0 || (uint64_t)D * H * W > 0x7fffffffull) return CETPICK_ERR_BAD_ARG;
+  if (n == 0) return CETPICK_OK;
+  rows_from_inds_kernel<<<(unsigned)ceil_div<long long>(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const long long*>(inds), n, (int)(H * W), (int)W, dets);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
 extern "C" int cetpick_sigmoid_clamp_f32(float* x, int64_t n, void* stream) {
   g_launches = 0;
   if (!x || n < 0) return CETPICK_ERR_BAD_ARG;

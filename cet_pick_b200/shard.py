@@ -93,3 +93,76 @@ def forward_z_sharded(forward_fn, volume_slab_fn, depth: int, group=None, halo: 
 
 def _default_device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+NMS_HALO = 1       # the (3,k,k) NMS window reaches one more slice in z (decode.py:27-33)
+
+
+def merge_topk(scores: torch.Tensor, inds: torch.Tensor, K: int):
+    """K best of the gathered candidates in the canonical order (score descending, linear index ascending) -- the
+    order csrc/decode.cu uses.  scores / inds: 1-D tensors (CPU or CUDA).  Returns (scores[K], inds[K])."""
+    o = torch.argsort(inds, stable=True)
+    o = o[torch.argsort(scores[o], descending=True, stable=True)]
+    o = o[:K]
+    return scores[o], inds[o]
+
+
+def local_candidates(forward_fn, volume_slab_fn, depth: int, K: int, kernel: int, rank: int, world: int):
+    """This rank's K best NMS survivors among its own core slices of the volume: (scores[K], global linear indices[K]).
+    The slab is forwarded with a (3 + 1)-slice recompute halo: 3 for the head, 1 more so that the 3x3x3 NMS of the
+    core slices sees real neighbours (of the forwarded range core +- 4, the slices core +- 1 are exact)."""
+    from .models.decode import _nms, _topk
+    z0, z1, lo, hi = slab_range(depth, rank, world, HEAD_HALO + NMS_HALO)
+    hm = forward_fn(volume_slab_fn(lo, hi), lo)                     # heat-map slices [lo, hi)
+    h, w = int(hm.shape[1]), int(hm.shape[2])
+    n_lo, n_hi = max(0, z0 - NMS_HALO), min(depth, z1 + NMS_HALO)
+    sub = hm[n_lo - lo:n_hi - lo].contiguous()[None, None]
+    nm = _nms(sub, kernel)
+    nm[0, 0, :z0 - n_lo] = 0                                        # halo slices only lend their values to the windows
+    nm[0, 0, z1 - n_lo:] = 0
+    kk = min(K, sub.numel())
+    sc, _, _, _, li = _topk(nm, kk)
+    sc, li = sc.reshape(-1), li.reshape(-1) + n_lo * h * w          # local linear index -> global linear index
+    if kk < K:
+        sc = torch.cat([sc, sc.new_zeros(K - kk)])
+        li = torch.cat([li, li.new_zeros(K - kk)])
+    return sc.contiguous(), li.contiguous(), h, w
+
+
+def gather_merge_candidates(sc: torch.Tensor, li: torch.Tensor, K: int, group=None):
+    """the one exchange of the z-sharded decode: all_gather of every rank's (K scores, K global indices), then the
+    merge-select in the canonical order.  Works over NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1:
+        gs = torch.empty(world * K, dtype=sc.dtype, device=sc.device)
+        gi = torch.empty(world * K, dtype=li.dtype, device=li.device)
+        dist.all_gather_into_tensor(gs, sc.contiguous(), group=group)
+        dist.all_gather_into_tensor(gi, li.contiguous(), group=group)
+    else:
+        gs, gi = sc, li
+    return merge_topk(gs, gi, K)
+
+
+def rows_from_indices(scores: torch.Tensor, inds: torch.Tensor, depth: int, h: int, w: int) -> torch.Tensor:
+    """(1, K, 5) pick rows of (score, global linear index) pairs with the reference's fp32 index arithmetic"""
+    from . import _lib
+    K = scores.numel()
+    dets = torch.empty((1, K, 5), dtype=torch.float32, device=scores.device)
+    _lib.check(_lib.lib().cetpick_rows_from_indices_f32(scores.contiguous().data_ptr(), inds.contiguous().data_ptr(), K,
+                                                        depth, h, w, dets.data_ptr(), _lib.stream_ptr()), "rows_from_indices")
+    return dets
+
+
+def decode_z_sharded(forward_fn, volume_slab_fn, depth: int, K: int, kernel: int = 3, group=None):
+    """SURVEY.md section 8e for ONE oversized volume: every rank forwards its z-slab with a recompute halo, decodes its
+    OWN core slices (local top-K of the NMS map), and only K candidates per rank travel: one all_gather of (K scores,
+    K global indices), then the merge-select.  No heat-map leaves its GPU.  -> (1, K, 5) picks, identical on every
+    rank and bit-identical to the single-GPU tomo_decode of the whole volume (rows whose score is 0 excepted: filler
+    when fewer than K peaks exist, whose indices torch.topk leaves unspecified).
+
+    forward_fn(slab, lo) -> (hi-lo, h, w) float32 heat-map slices (sigmoid applied); volume_slab_fn(lo, hi) -> input."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    sc, li, h, w = local_candidates(forward_fn, volume_slab_fn, depth, K, kernel, rank, world)
+    ms, mi = gather_merge_candidates(sc, li, K, group)
+    return rows_from_indices(ms, mi, depth, h, w)

@@ -81,6 +81,12 @@ int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_c
  * left, flags, candidate count, n_gt, need_fallback, eq_need, eq_zc, ...).  Synchronises. */
 int cetpick_decode_debug_state(const void* ws, void* stream, uint32_t* out24);
 
+/* Pick rows of given (score, linear index) pairs with the reference's index arithmetic (decode.py:35-41 in fp32,
+ * :141-154): dets[i] = [x + 0.25, y + 0.25, z, score, score].  Used to assemble the merged pick list of a z-sharded
+ * volume (per-rank top-K -> all_gather -> merge-select), where the indices are global. */
+int cetpick_rows_from_indices_f32(const float* scores, const int64_t* inds, int64_t n, int64_t D, int64_t H, int64_t W,
+                                  float* dets, void* stream);
+
 /* Full NMS map (decode.py:11-33): out = heat * (maxpool(heat) == heat).  mode: CETPICK_NMS_3D
  * ((3,k,k)), 3 = xy only ((1,k,k), `_nms_xy`), 4 = z only ((k,1,1), `_nms_z`). */
 #define CETPICK_NMS_XY 3

@@ -1,5 +1,6 @@
 """torchrun --nproc-per-node N scripts/check_zshard_nccl.py : one oversized volume, z-slabs over N GPUs (NCCL).
-Every rank forwards only its slab (+3-slice recompute halo); one all_gather of heat-map slabs; decode everywhere.
+Every rank forwards only its slab (+ recompute halo).  Two exchanges are checked: all_gather of heat-map slabs with the
+decode everywhere, and local decode + all_gather of K candidates per rank + merge-select.
 Checks against the single-GPU whole-volume result on rank 0's device: heat-map and picks must be identical."""
 import os
 import sys
@@ -11,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cet_pick_b200 import synth                                   # noqa: E402
 from cet_pick_b200.models.decode import tomo_decode               # noqa: E402
 from cet_pick_b200.models.model import create_model               # noqa: E402
-from cet_pick_b200.shard import forward_z_sharded, slab_range     # noqa: E402
+from cet_pick_b200.shard import decode_z_sharded, forward_z_sharded, slab_range     # noqa: E402
 
 
 def main():
@@ -37,11 +38,15 @@ def main():
     ref = tomo_decode(whole[None, None].contiguous(), kernel=3, K=K)
     z0, z1, lo, hi = slab_range(D, rank, world)
     ok = bool((hm - whole).abs().max().item() <= 2e-7) and torch.equal(dets, ref) and loaded == [(lo, hi)]
+    # SURVEY 8e proper: local decode of the own core slices, all_gather of K candidates per rank, merge-select
+    fwd = lambda s, lo: (setattr(m, "z_origin", lo), m(s[None])[-1]["hm"][0, 0], setattr(m, "z_origin", 0))[1]
+    dets2 = decode_z_sharded(fwd, lambda a, b: vol[a:b], D, K, 3)
+    ok = ok and torch.equal(dets2.view(torch.int32), ref.view(torch.int32))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"z-sharded forward over {world} GPUs: slab of rank 0 = [{lo},{hi}) of {D}; "
-              f"max |hm - whole| = {(hm - whole).abs().max().item():.2e}; picks identical = {torch.equal(dets, ref)}; "
+              f"max |hm - whole| = {(hm - whole).abs().max().item():.2e}; picks identical = {torch.equal(dets, ref)}; candidate-merge picks identical = {torch.equal(dets2.view(torch.int32), ref.view(torch.int32))}; "
               f"{'OK' if flag.item() == 1 else 'MISMATCH'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)

@@ -243,3 +243,46 @@ def test_forward_uint8_levels_identical_to_float32(shape):
     m.level_values = None
     a2 = m(torch.from_numpy(lv[q2])[None].cuda())[-1]["hm"]
     assert torch.equal(a2, b2)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_z_sharded_decode_candidate_merge_equals_whole_volume(world):
+    """per-rank local top-K of the own core slices (4-slice recompute halo) -> merge-select gives the
+    single-GPU pick list bit for bit; the ranks are played one after the other in this process."""
+    from cet_pick_b200.models.decode import tomo_decode
+    from cet_pick_b200.shard import local_candidates, merge_topk, rows_from_indices
+    m = build_model(4, 317)
+    m.compute_proj, m.fuse_sigmoid = False, True
+    D, H, W, K = 23, 64, 96, 120
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, 8)).cuda()
+    whole = tomo_decode(m(x[None])[-1]["hm"], kernel=3, K=K)
+
+    def fwd(slab, lo):
+        m.z_origin = lo
+        try:
+            return m(slab[None])[-1]["hm"][0, 0]
+        finally:
+            m.z_origin = 0
+
+    cs, ci = [], []
+    for rank in range(world):
+        sc, li, h, w = local_candidates(fwd, lambda lo, hi: x[lo:hi], D, K, 3, rank, world)
+        cs.append(sc); ci.append(li)
+    ms, mi = merge_topk(torch.cat(cs), torch.cat(ci), K)
+    dets = rows_from_indices(ms, mi, D, h, w)
+    assert torch.equal(dets.view(torch.int32), whole.view(torch.int32))
+
+
+def test_fused_block_path_equals_two_kernel_path(monkeypatch):
+    """CETPICK_BLOCK=1 routes conv1+conv2 of the 32-channel full-resolution blocks through the fused cluster kernel
+    (csrc/conv_block.cu); the heat-map must not change by a single bit."""
+    m = build_model(4, 317)
+    m.compute_proj, m.fuse_sigmoid = False, True
+    x = torch.from_numpy(synth.tomogram_np(3, 120, 520, 6))[None].cuda()      # level-0 maps are 60 x 260: a 3-CTA cluster
+    monkeypatch.delenv("CETPICK_BLOCK", raising=False)
+    a = m(x)[-1]["hm"].clone()
+    n_plain = m.last_launches
+    monkeypatch.setenv("CETPICK_BLOCK", "1")
+    b = m(x)[-1]["hm"]
+    assert m.last_launches == n_plain - 2            # two blocks: four convolutions became two launches
+    assert torch.equal(a, b)

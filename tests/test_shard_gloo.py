@@ -116,3 +116,56 @@ def test_forward_z_sharded_world2_gloo(depth):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+# ---- z-sharded decode: per-rank top-K candidates -> all_gather -> merge-select ----
+def _cand_worker(rank, world, port, depth, K, q):
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from cet_pick_b200 import synth
+    from cet_pick_b200.shard import gather_merge_candidates, shard_range
+    from oracle import decode_oracle as do
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W = 14, 18
+        hm = synth.heatmap_tiefree_np(depth, H, W, 31)
+        nm = do.nms(hm[None, None], 3)[0, 0]                     # oracle NMS of the whole map (CPU stand-in for the
+        z0, cnt = shard_range(depth, rank, world)                 # GPU part, which the -m gpu tests cover)
+        own = np.zeros_like(nm)
+        own[z0:z0 + cnt] = nm[z0:z0 + cnt]
+        sc, li = do.topk_canonical(own.ravel(), K)
+        ms, mi = gather_merge_candidates(torch.from_numpy(sc.copy()), torch.from_numpy(li.copy()), K)
+        rs, ri = do.topk_canonical(nm.ravel(), K)
+        pos = rs > 0
+        ok = np.array_equal(ms.numpy()[pos], rs[pos]) and np.array_equal(mi.numpy()[pos], ri[pos])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("depth,K", [(12, 40), (7, 25), (2, 10)])
+def test_candidate_merge_world2_gloo(depth, K):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cand_worker, args=(r, 2, port, depth, K, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+def test_merge_topk_canonical_order():
+    from cet_pick_b200.shard import merge_topk
+    sc = torch.tensor([0.5, 0.9, 0.5, 0.1, 0.9, 0.5])
+    ix = torch.tensor([40, 7, 3, 99, 2, 11])
+    s, i = merge_topk(sc, ix, 4)
+    assert torch.equal(s, torch.tensor([0.9, 0.9, 0.5, 0.5])) and i.tolist() == [2, 7, 3, 11]
