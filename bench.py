@@ -74,7 +74,7 @@ def cpu_sample(shape, K, nms, slices, threads=None):
     decode are O(voxels), so cost scales linearly in slices; value = 1 / (t * D / slices)."""
     import numpy as np
     import torch
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from oracle import decode_oracle as do
     from oracle import unet_oracle as uo
     D, H, W = shape
@@ -179,7 +179,8 @@ def leg_roofline_decode(dev, pk, iters=10):
     (every kernel of one cetpick_decode_f32 call; CUDA events on the launching stream, a 2 GiB map > L2 between
     iterations).  Self-check: all five columns bit-identical to the reference's op sequence run by PyTorch on the GPU."""
     import torch
-    from cet_pick_b200 import _lib, synth
+    from cet_pick_b200 import _lib
+    import synthdata as synth
     from cet_pick_b200.models.decode import decode_status, tomo_decode
     D, H, W, K = 512, 1024, 1024, 10000
     hm = synth.heatmap_tiefree_torch(D, H, W, 2, device=dev)[None, None]
@@ -235,7 +236,7 @@ def leg_torch_cuda_baseline(dev, shape, our_forward_ms, our_hm):
     oracle/unet_oracle.py: conv2d / batch_norm / relu / max_pool2d / conv_transpose2d / cat / conv3d, then _sigmoid)
     executed by PyTorch -> cuDNN's sm_100 kernels on this GPU, one 1024x1024x256 tomogram in z-slabs of 32 (+3 halo)."""
     import torch
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from oracle import unet_oracle as uo
     D, H, W = shape
     sd0 = synth.unet_state_dict_torch(317, 4)
@@ -300,7 +301,7 @@ def leg_simsiam(dev, pk, B=8192):
     reference) = 17.9 TFLOP per batch; the torch-CUDA arm runs the reference's op sequence (oracle restatement) on
     1/8 of the batch."""
     import torch
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.models.model import create_model
     from oracle import simsiam_oracle as so
     sd = synth.simsiam3d_state_dict_torch(5)
@@ -406,7 +407,8 @@ def leg_e2e_run(dev, a, shape, n_tomo, host_q):
 def run_b200(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from cet_pick_b200 import _lib, synth
+    from cet_pick_b200 import _lib
+    import synthdata as synth
     from cet_pick_b200.shard import gather_picks, shard_range
     from cet_pick_b200.models.decode import tomo_decode
     from cet_pick_b200.models.model import create_model

@@ -8,6 +8,7 @@ import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CETPICK_LIB") or os.path.join(_PKG, "libcetpick_sm100a.so")   # explicit override for A/B builds
+TEST_LIB_PATH = os.environ.get("CETPICK_TEST_LIB") or os.path.join(_PKG, "libcetpick_test_sm100a.so")
 
 OK = 0
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_STATE, ERR_SHAPE = -1, -2, -3, -4, -5, -6
@@ -58,11 +59,15 @@ SIGNATURES = {
     "cetpick_simsiam_finalize": (_int, [_vp]),
     "cetpick_simsiam_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_simsiam_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
-    "cetpick_conv_small_bf16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _int, _int, _vp, _vp,
-                                       _vp, _int, _int, _vp, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_profile_enable": (_int, [_int]),
     "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
+}
+
+# test / tuning hooks of include/cetpick_test.h (libcetpick_test_sm100a.so only)
+TEST_SIGNATURES = {
+    "cetpick_conv_small_bf16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _int, _int, _vp, _vp,
+                                       _vp, _int, _int, _vp, _vp]),
     "cetpick_selftest_gemm_bf16": (_int, [_vp, _vp, _vp, _int, _int, _int, _vp]),
     "cetpick_probe_umma": (_int, [_vp, _int, _vp, _int, _int, _int, _int, _vp, _vp]),
     "cetpick_conv_march_bf16": (_int, [_int, _int, _int, _vp, _vp, _int, _int, _int, _int, _vp, _int, _vp, _int,
@@ -106,6 +111,26 @@ def lib() -> C.CDLL:
                     fn.restype, fn.argtypes = res, args
                 _lib = h
     return _lib
+
+
+_test_lib = None
+
+
+def test_lib() -> C.CDLL:
+    """The test twin of the product library: the same objects plus the per-kernel hooks and hardware probes of
+    include/cetpick_test.h.  Used by tests/ and scripts/ only; nothing in the product package calls it."""
+    global _test_lib
+    if _test_lib is None:
+        with _lock:
+            if _test_lib is None:
+                if not os.path.exists(TEST_LIB_PATH):
+                    raise ImportError(f"{TEST_LIB_PATH} is missing: build it with `python -m cet_pick_b200.build`")
+                h = C.CDLL(TEST_LIB_PATH)
+                for name, (res, args) in {**SIGNATURES, **TEST_SIGNATURES}.items():
+                    fn = getattr(h, name)
+                    fn.restype, fn.argtypes = res, args
+                _test_lib = h
+    return _test_lib
 
 
 def check(code: int, where: str):

@@ -51,7 +51,7 @@ struct alignas(64) BlockParams {
   int R, nchunk;                // rows per strip, strips per image
   long long total_strips;       // per cluster
   int stages, RS, NC;
-  int lag, flags;               // tuning: bit0 no consumer-side proxy fence, bit1 CTA-scope proxy fence for the local ring stores
+  int lag, flags;               // tuning: bit0 = acquire.cluster polls on ring_full (A/B only)
   float bias1[COUT], bias2[COUT];
   __nv_bfloat16* out;
   __nv_bfloat16* pool_out;
@@ -315,9 +315,12 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
             wait_t<false>(&c2_empty[sl], ((umask2 >> sl) & 1u) ^ 1u, 5, (uint32_t)r2_touched, (uint32_t)tck);
             umask2 ^= 1u << sl;
           }
-          if (p.flags & 4) wait_t<false>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
-          else wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
-          if (!(p.flags & 1)) fence_proxy_async_all();
+          // The ring row lives in THIS SM's shared memory (a neighbour's edge pixel arrives through DSMEM before its
+          // release.cluster arrive is counted), so a CTA-scope wait plus a consumer-side proxy fence orders it before
+          // the UMMA reads; an acquire.cluster poll would invalidate L1 (CCTL.IVALL, ~500 cycles) on every try.
+          if (p.flags & 1) wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+          else wait_t<false>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           ptx::tc_fence_after();
           const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
           const uint32_t boff = (uint32_t)(r_lo - (j - 1)) * ((COUT * 64) >> 4);
@@ -419,8 +422,8 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
         }
         // the ring row must have been consumed by conv2 (here, and in the neighbour the edge pixel goes to)
         wait_t<false>(&ring_empty[rslot], rpar ^ 1u, 9, (uint32_t)r, rslot);
-        if (quad == 0 && has_left) wait_t<true>(&nb_empty[0][rslot], rpar ^ 1u, 10, (uint32_t)r, rslot);
-        if (quad == 3 && has_right) wait_t<true>(&nb_empty[1][rslot], rpar ^ 1u, 11, (uint32_t)r, rslot);
+        if (quad == 0 && has_left) wait_t<false>(&nb_empty[0][rslot], rpar ^ 1u, 10, (uint32_t)r, rslot);
+        if (quad == 3 && has_right) wait_t<false>(&nb_empty[1][rslot], rpar ^ 1u, 11, (uint32_t)r, rslot);
         uint8_t* row = sRing + (size_t)rslot * RING_ROW;
 #pragma unroll
         for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + sw(own_off + c * 16u)) = w4[c];
@@ -429,13 +432,11 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
           const uint32_t poff = edge_l ? 129u * 64u : 0u;    // swizzle is a function of the offset inside the (1024-aligned) row
 #pragma unroll
           for (int c = 0; c < 4; ++c) st_cluster_v4(rb - poff + sw(poff + c * 16u), w4[c]);
-          fence_proxy_async_all();
-          mbar_arrive_remote(rem_full + rslot * 8u);
+          mbar_arrive_remote(rem_full + rslot * 8u);      // release.cluster: the four stores above are visible first
         }
-        if (p.flags & 2) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        else fence_proxy_async_all();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) { if (p.flags & 8) ptx::mbar_arrive(&ring_full[rslot]); else mbar_arrive_release_cluster(&ring_full[rslot]); }
+        if (lane == 0) ptx::mbar_arrive(&ring_full[rslot]);
         if (++rslot == (uint32_t)p.RS) { rslot = 0; rpar ^= 1u; }
       }
     }
@@ -639,6 +640,7 @@ int conv_block_launch(const BlockLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: one fused block from PyTorch-layout fp32 host weights (packs, uploads, launches, synchronises, frees).
 extern "C" int cetpick_conv_block_bf16(int nsrc, const void* src0, const void* src1, int C1, int NIMG, int H, int W,
                                        const float* w1_host, const float* bias1_host, const float* w2_host,
@@ -683,3 +685,5 @@ extern "C" int cetpick_block_debug_buffer(uint32_t** host_buf) {
   if (host_buf) *host_buf = h;
   return CETPICK_OK;
 }
+
+#endif  // CETPICK_TEST_HOOKS

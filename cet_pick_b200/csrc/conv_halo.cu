@@ -299,6 +299,7 @@ int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: one 3x3 conv through conv_halo.cu from a PyTorch-layout fp32 HOST weight (Cout, nsrc*C, 3, 3)
 // and a HOST bias [Cout] (packs, uploads, launches, synchronises) -- tests/test_gpu_conv.py.
 extern "C" int cetpick_conv_halo_bf16(int nsrc, const void* src0, const void* src1, int C, int NIMG, int H, int W,
@@ -328,3 +329,5 @@ extern "C" int cetpick_conv_halo_bf16(int nsrc, const void* src0, const void* sr
   if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_halo");
   return rc;
 }
+
+#endif  // CETPICK_TEST_HOOKS

@@ -563,6 +563,7 @@ int conv_march_launch(const MarchLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: one marching convolution from a PyTorch-layout fp32 host weight (packs, uploads,
 // launches, synchronises, frees) -- tests/test_gpu_conv.py.
 extern "C" int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const void* src0, const void* src1, int C,
@@ -606,3 +607,5 @@ extern "C" int cetpick_conv_march_pool_bf16(int mode, int dil, int nsrc, const v
   if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_march");
   return rc;
 }
+
+#endif  // CETPICK_TEST_HOOKS

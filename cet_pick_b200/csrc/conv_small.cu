@@ -304,6 +304,7 @@ int conv_small_launch(const SmallLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: one convolution through conv_small_kernel from a PyTorch-layout fp32 host weight (Cout, Cin, taps...).
 // src: bf16 device [B][Z][Hin][Win][C]; taps: ntaps x (dz, dy, dx) input offsets of tap t (before the stride);
 // out: bf16 (or fp32) device [B][Z][Ho][Wo][Cout].  Packs, uploads, launches, synchronises.
@@ -332,3 +333,5 @@ extern "C" int cetpick_conv_small_bf16(const void* src, int C, int B, int Z, int
   if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_small");
   return rc;
 }
+
+#endif  // CETPICK_TEST_HOOKS

@@ -406,6 +406,7 @@ int conv_stem_launch(const StemLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: the stem from a PyTorch-layout fp32 host weight (16,1,7,7), BN scale/shift on the host
 // (packs, uploads, launches, synchronises, frees) -- tests/test_gpu_conv.py.
 extern "C" int cetpick_conv_stem_bf16(const float* in, int D, int H, int W, const float* w_host,
@@ -432,3 +433,5 @@ extern "C" int cetpick_conv_stem_bf16(const float* in, int D, int H, int W, cons
   if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_stem");
   return rc;
 }
+
+#endif  // CETPICK_TEST_HOOKS

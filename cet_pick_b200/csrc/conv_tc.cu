@@ -424,6 +424,7 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // C[M,N] = A[M,K] * B[N,K]^T as a 1x1 "convolution" over an (M/16) x 16 image -- validates the
 // TMA / UMMA descriptor plumbing in isolation (tests/test_gpu_conv.py).
 extern "C" int cetpick_selftest_gemm_bf16(const void* A, const void* B, float* C, int M, int N, int K,
@@ -443,3 +444,5 @@ extern "C" int cetpick_selftest_gemm_bf16(const void* A, const void* B, float* C
   L.out = C;
   return conv_tc_launch(L, static_cast<cudaStream_t>(stream));
 }
+
+#endif  // CETPICK_TEST_HOOKS

@@ -256,6 +256,7 @@ int conv_up_launch(const UpLaunch& L, cudaStream_t stream) {
 
 using namespace cetpick;
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: ConvTranspose2d(k2,s2)+bias+ReLU from a PyTorch-layout fp32 HOST weight (Cin,Cout,2,2)
 // (packs, uploads, launches, synchronises) -- tests/test_gpu_conv.py.
 extern "C" int cetpick_upconv_bf16(const void* src, int Cin, int NIMG, int h, int w, const float* w_host,
@@ -287,3 +288,5 @@ extern "C" int cetpick_upconv_bf16(const void* src, int Cin, int NIMG, int h, in
   if (rc == CETPICK_OK && e != cudaSuccess) return cuda_fail(e, "conv_up");
   return rc;
 }
+
+#endif  // CETPICK_TEST_HOOKS

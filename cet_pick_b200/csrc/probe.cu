@@ -1,3 +1,4 @@
+#ifdef CETPICK_TEST_HOOKS   // hardware probes: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Hardware probe (test hook, not on the product path): which shifted / strided shared-memory
 // descriptors does tcgen05.mma accept for a TMA-written, hardware-swizzled K-major tile?
 // One CTA: TMA-load A_big[R][KC] and B[32][KC], then D[128][32] = A_big[rows(m)] * B^T with the A
@@ -263,3 +264,5 @@ extern "C" int cetpick_probe_mma_rate2(int N, int KC, int sbo_a, int a_step, int
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }
+
+#endif  // CETPICK_TEST_HOOKS

@@ -808,6 +808,7 @@ extern "C" int cetpick_profile_read(int max_entries, int* n, float* ms, double* 
   return CETPICK_OK;
 }
 
+#ifdef CETPICK_TEST_HOOKS   // test / tuning hooks: built into libcetpick_test_sm100a.so only (include/cetpick_test.h)
 // Test hook: one convolution through conv_tc.cu with caller-packed weights (tests/test_gpu_conv.py).
 extern "C" int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void* src1, int C1, int NIMG,
                                  int H, int W, const void* wpk, int KC, int ntaps, const int* taps,
@@ -823,3 +824,5 @@ extern "C" int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void*
   L.Ho = Ho; L.Wo = Wo; L.Cout = Cout;
   return conv_tc_launch(L, static_cast<cudaStream_t>(stream));
 }
+
+#endif  // CETPICK_TEST_HOOKS

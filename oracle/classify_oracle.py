@@ -25,7 +25,7 @@ def patch(tomo: np.ndarray, n: int, psz: int, psxy: int, pdz: int, pdxy: int):
 
 
 def stub_model(x: np.ndarray) -> np.ndarray:
-    """numpy twin of cet_pick_b200.synth.fullres_stub_model (separately rounded fp32 operations)."""
+    """numpy twin of synthdata.fullres_stub_model (separately rounded fp32 operations)."""
     xp = np.pad(x, 1)
     y = (x * np.float32(6.0) - np.float32(3.0)).astype(np.float32)
     y = (y + np.float32(0.5) * xp[:-2, 1:-1, 1:-1]).astype(np.float32)

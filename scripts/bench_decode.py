@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--kind", default="tiefree", choices=["tiefree", "peaks"])
     a = ap.parse_args()
     import torch
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.models import decode as dec
 
     D, H, W = (int(v) for v in a.shape.split(","))

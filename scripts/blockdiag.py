@@ -20,9 +20,9 @@ pl = torch.full((n, (h + 1) // 2, (w + 1) // 2, 32), float("nan"), device="cuda"
 w1h, w2h, b1h, b2h = w1.float().cpu().contiguous(), w2.float().cpu().contiguous(), b1.cpu().contiguous(), b2.cpu().contiguous()
 import ctypes
 dbg = ctypes.POINTER(ctypes.c_uint32)()
-L.lib().cetpick_block_debug_buffer(ctypes.byref(dbg))
+L.test_lib().cetpick_block_debug_buffer(ctypes.byref(dbg))
 t0 = time.time()
-rc = L.lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
+rc = L.test_lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
                                      w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(), b2h.data_ptr(),
                                      out.data_ptr(), pl.data_ptr() if pool else None, L.stream_ptr())
 print(sys.argv[1:7], "rc", rc, L.lib().cetpick_last_cuda_error().decode(), "t=%.2fs" % (time.time() - t0))
@@ -42,7 +42,7 @@ if rc == 0 and os.environ.get("TIME"):
     ts = []
     for _ in range(5):
         ev0.record()
-        L.lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
+        L.test_lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
                                         w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(), b2h.data_ptr(),
                                         out.data_ptr(), pl.data_ptr() if pool else None, L.stream_ptr())
         ev1.record(); torch.cuda.synchronize()

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from cet_pick_b200 import synth                                   # noqa: E402
+import synthdata as synth                                   # noqa: E402
 from cet_pick_b200.models.decode import tomo_decode               # noqa: E402
 from cet_pick_b200.models.model import create_model               # noqa: E402
 from cet_pick_b200.shard import decode_z_sharded, forward_z_sharded, slab_range     # noqa: E402

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cet_pick_b200 import _lib
 
-L = _lib.lib()
+L = _lib.test_lib()
 out = torch.zeros(148, device="cuda")
 cases = [  # N, KC, sbo_a, a_step, ntap, ndst, note
     (32, 32, 512, 0, 1, 1, "N=32 dense"),

@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from cet_pick_b200 import _lib
-L = _lib.lib()
+L = _lib.test_lib()
 R = 384
 for KC in (64, 32, 16):
     g = torch.Generator(device="cuda").manual_seed(KC)

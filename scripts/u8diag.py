@@ -1,7 +1,7 @@
 import sys, time, os
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
-from cet_pick_b200 import synth
+import synthdata as synth
 from cet_pick_b200.models.model import create_model
 m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
 m.load_state_dict(synth.unet_state_dict_torch(317, 4)); m = m.cuda().eval(); m.compute_proj=False; m.fuse_sigmoid=True

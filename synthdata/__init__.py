@@ -1,4 +1,5 @@
-"""Seeded synthetic inputs for the localisation hot path (tomograms, heat-maps, checkpoints).
+"""TEST / BENCH INFRASTRUCTURE (not part of the product package): seeded synthetic inputs for the localisation hot
+path (tomograms, heat-maps, checkpoints).
 
 Everything is a pure function of (seed, element index) through one 64-bit counter hash
 (splitmix64 finaliser), written once for numpy (host, tests, oracle) and once for torch

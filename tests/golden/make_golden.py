@@ -4,7 +4,7 @@ these files are the parity pin for oracle/ (and through it for the CUDA path).
 
     python tests/golden/make_golden.py            # needs /root/reference (or $CET_PICK_REF)
 
-Inputs are never stored when they can be regenerated from a seed (cet_pick_b200.synth);
+Inputs are never stored when they can be regenerated from a seed (synthdata);
 only reference OUTPUTS are.  Reference environment: torch CPU fp32 (version recorded below).
 """
 import io
@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from cet_pick_b200 import synth          # noqa: E402
+import synthdata as synth          # noqa: E402
 from oracle import refbridge             # noqa: E402
 
 torch.set_num_threads(max(1, os.cpu_count() or 1))

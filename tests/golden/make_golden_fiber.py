@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from cet_pick_b200 import synth          # noqa: E402
+import synthdata as synth          # noqa: E402
 from oracle import refbridge             # noqa: E402
 
 d = refbridge.decode_module()

@@ -27,6 +27,30 @@ def test_header_symbols_all_exported(L):
         assert getattr(lib, name) is not None
 
 
+def test_test_hooks_live_in_the_test_library_only(L):
+    """include/cetpick_test.h declares the per-kernel hooks and probes; libcetpick_test_sm100a.so exports them (and the
+    whole product ABI), the product library exports none of them."""
+    hdr = open(os.path.join(ROOT, "include", "cetpick_test.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cetpick_[a-z0-9_]+)\s*\(", hdr))
+    assert declared and declared == set(L.TEST_SIGNATURES), declared ^ set(L.TEST_SIGNATURES)
+    assert not (declared & set(L.SIGNATURES))
+    tl, pl = L.test_lib(), L.lib()
+    for name in declared:
+        assert getattr(tl, name) is not None
+        assert not hasattr(pl, name), f"{name} leaked into the product library"
+    for name in L.SIGNATURES:
+        assert getattr(tl, name) is not None
+
+
+def test_synthetic_data_helpers_are_outside_the_product_package():
+    assert not os.path.exists(os.path.join(ROOT, "cet_pick_b200", "synth.py"))
+    for dp, _, fs in os.walk(os.path.join(ROOT, "cet_pick_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                assert "synthdata" not in open(os.path.join(dp, f)).read(), os.path.join(dp, f)
+
+
 def test_version_and_strerror(L):
     lib = L.lib()
     assert lib.cetpick_version() == 1

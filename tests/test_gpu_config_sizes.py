@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from cet_pick_b200 import synth
+import synthdata as synth
 
 pytestmark = pytest.mark.gpu
 

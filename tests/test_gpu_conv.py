@@ -32,7 +32,7 @@ def pack(w, nsrc, csrc, kc):
 def run_conv(L, srcs, wpk, kc, taps, ntot, bias, relu, epi, out, cstride=0, Ho=0, Wo=0, Cout=0):
     n, h, w, _ = srcs[0].shape
     tp = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
-    rc = L.lib().cetpick_conv_bf16(len(srcs), srcs[0].data_ptr(), srcs[0].shape[3],
+    rc = L.test_lib().cetpick_conv_bf16(len(srcs), srcs[0].data_ptr(), srcs[0].shape[3],
                                    srcs[1].data_ptr() if len(srcs) > 1 else None,
                                    srcs[1].shape[3] if len(srcs) > 1 else 0, n, h, w, wpk.data_ptr(), kc,
                                    len(taps), tp, ntot, bias.data_ptr() if bias is not None else None,
@@ -50,7 +50,7 @@ def test_gemm_selftest(L, M, N, K):
     kc = 64 if K % 64 == 0 else 32 if K % 32 == 0 else 16
     Bp = pack(B.view(N, K, 1), 1, K, kc)
     Cm = torch.full((M, N), float("nan"), device="cuda")
-    L.check(L.lib().cetpick_selftest_gemm_bf16(A.data_ptr(), Bp.data_ptr(), Cm.data_ptr(), M, N, K,
+    L.check(L.test_lib().cetpick_selftest_gemm_bf16(A.data_ptr(), Bp.data_ptr(), Cm.data_ptr(), M, N, K,
                                                L.stream_ptr()), "selftest")
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
@@ -143,7 +143,7 @@ def run_march(L, mode, dil, srcs, wt, cout, bias, relu):
     n, h, w, c = srcs[0].shape
     out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     wh = wt.float().cpu().contiguous()
-    rc = L.lib().cetpick_conv_march_bf16(mode, dil, len(srcs), srcs[0].data_ptr(),
+    rc = L.test_lib().cetpick_conv_march_bf16(mode, dil, len(srcs), srcs[0].data_ptr(),
                                          srcs[1].data_ptr() if len(srcs) > 1 else None, c, n, h, w,
                                          wh.data_ptr(), cout, bias.data_ptr() if bias is not None else None,
                                          int(relu), out.data_ptr(), L.stream_ptr())
@@ -220,7 +220,7 @@ def test_conv_up_kernel(L, cin, cout, n, h, w, Ho, Wo):
     b = torch.randn(cout, device="cuda", generator=g)
     out = torch.full((n, Ho, Wo, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     wh, bh = wt.float().cpu().contiguous(), b.cpu().contiguous()
-    L.check(L.lib().cetpick_upconv_bf16(x.data_ptr(), cin, n, h, w, wh.data_ptr(), bh.data_ptr(), cout,
+    L.check(L.test_lib().cetpick_upconv_bf16(x.data_ptr(), cin, n, h, w, wh.data_ptr(), bh.data_ptr(), cout,
                                         out.data_ptr(), Ho, Wo, L.stream_ptr()), "cetpick_upconv_bf16")
     torch.cuda.synchronize()
     ref = F.relu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2))[:, :, :Ho, :Wo]
@@ -238,7 +238,7 @@ def test_conv_halo_kernel(L, nsrc, c, cout, n, h, w):
     b = torch.randn(cout, device="cuda", generator=g)
     out = torch.full((n, h, w, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     wh, bh = wt.float().cpu().contiguous(), b.cpu().contiguous()
-    L.check(L.lib().cetpick_conv_halo_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c,
+    L.check(L.test_lib().cetpick_conv_halo_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c,
                                            n, h, w, wh.data_ptr(), bh.data_ptr(), cout, 1, out.data_ptr(),
                                            L.stream_ptr()), "cetpick_conv_halo_bf16")
     torch.cuda.synchronize()
@@ -258,7 +258,7 @@ def test_stem_tensor_core_march(L, d, h, w):
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     out = torch.full((d, ho, wo, 16), float("nan"), device="cuda", dtype=torch.bfloat16)
     wh, sh, bh = wt.cpu().contiguous(), scale.cpu().contiguous(), shift.cpu().contiguous()
-    rc = L.lib().cetpick_conv_stem_bf16(x.data_ptr(), d, h, w, wh.data_ptr(), sh.data_ptr(), bh.data_ptr(),
+    rc = L.test_lib().cetpick_conv_stem_bf16(x.data_ptr(), d, h, w, wh.data_ptr(), sh.data_ptr(), bh.data_ptr(),
                                         out.data_ptr(), L.stream_ptr())
     L.check(rc, "cetpick_conv_stem_bf16")
     torch.cuda.synchronize()
@@ -291,7 +291,7 @@ def test_march_fused_maxpool(L, n, h, w, cin, cout):
     hp, wp = (h + 1) // 2, (w + 1) // 2
     pool = torch.full((n, hp, wp, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
     wh = wt.float().cpu().contiguous()
-    rc = L.lib().cetpick_conv_march_pool_bf16(0, 1, 1, x.data_ptr(), None, cin, n, h, w, wh.data_ptr(), cout,
+    rc = L.test_lib().cetpick_conv_march_pool_bf16(0, 1, 1, x.data_ptr(), None, cin, n, h, w, wh.data_ptr(), cout,
                                               b.data_ptr(), 1, out.data_ptr(), pool.data_ptr(), L.stream_ptr())
     L.check(rc, "cetpick_conv_march_pool_bf16")
     torch.cuda.synchronize()
@@ -325,7 +325,7 @@ def test_fused_block_equals_two_march_convs(L, n, h, w, c1, nsrc, pool):
     pl = torch.full((n, hp, wp, 32), float("nan"), device="cuda", dtype=torch.bfloat16) if pool else None
     w1h, w2h = w1.float().cpu().contiguous(), w2.float().cpu().contiguous()
     b1h, b2h = b1.cpu().contiguous(), b2.cpu().contiguous()
-    rc = L.lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
+    rc = L.test_lib().cetpick_conv_block_bf16(nsrc, srcs[0].data_ptr(), srcs[1].data_ptr() if nsrc > 1 else None, c1, n, h, w,
                                          w1h.data_ptr(), b1h.data_ptr(), w2h.data_ptr(), b2h.data_ptr(),
                                          out.data_ptr(), pl.data_ptr() if pool else None, L.stream_ptr())
     L.check(rc, "cetpick_conv_block_bf16")

@@ -24,7 +24,7 @@ def _detector(opt_kw):
 def test_pick_files_match_reference_golden(golden, tmp_path, tag, kw):
     """decode on the GPU + post_process + save_detection reproduce the reference's `<name>.txt` byte for byte
     (fixture written by the unmodified reference, tests/golden/make_golden.py)."""
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.models.decode import tomo_decode
     g = golden("pickfile")
     D, H, W = (int(v) for v in g["shape"])
@@ -43,7 +43,7 @@ def test_pick_files_match_reference_golden(golden, tmp_path, tag, kw):
 def test_run_end_to_end_from_checkpoint(tmp_path, monkeypatch):
     """opts -> detector_factory -> load_model(checkpoint) -> run(): picks agree with the oracle pipeline
     (fp32 forward + decode) within one voxel for every pick whose score clears the K-th by the BF16 tolerance."""
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.detectors.detector_factory import detector_factory
     from cet_pick_b200.opts import opts
     from oracle import decode_oracle as do
@@ -86,7 +86,7 @@ def test_pipeline_mrc_to_pick_file(tmp_path, monkeypatch):
     reconstruction -> load_tomos_from_list (order xzy, --compress, --gauss 0.8; csrc/preproc.cu) -> detector.run
     (forward + decode) -> `<name>.txt`.  The pre-processed volume equals the oracle's 256-level volume, and the
     heat-map written next to the picks is within the BF16 tolerance of the fp32 oracle forward on it."""
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.detectors.detector_factory import detector_factory
     from cet_pick_b200.opts import opts
     from cet_pick_b200.utils import loader, mrcio
@@ -125,7 +125,7 @@ def test_pipeline_mrc_to_pick_file(tmp_path, monkeypatch):
 def test_command_line_entry(tmp_path, monkeypatch):
     """`python -m cet_pick_b200.test semi ...` (the reference's test.py command line): image list -> MRC -> GPU
     pre-processing -> detector -> pick files and opt.txt, for two tomograms."""
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200 import test as cli
     from cet_pick_b200.opts import opts
     from cet_pick_b200.utils import mrcio
@@ -159,7 +159,7 @@ def test_command_line_entry(tmp_path, monkeypatch):
 def test_async_write_and_uint8_levels_give_identical_files(tmp_path, monkeypatch):
     """run() with the writer threads (set_async_write) and with the tomogram shipped as uint8 levels must leave the
     same `<name>.txt` and the same heat-map bytes on disk as the blocking float32 path."""
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.detectors.detector_factory import detector_factory
     from cet_pick_b200.opts import opts
     sd = synth.unet_state_dict_torch(317, 4)

@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from cet_pick_b200 import synth
+import synthdata as synth
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,7 @@ def run_small(L, x, w, stride, Ho, Wo, taps, bias=None, residual=None, relu=Fals
     out = torch.full((B, Z, Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
     wh = w.float().cpu().contiguous()
     tp = (C.c_int * (3 * len(taps)))(*[v for t in taps for v in t])
-    rc = L.lib().cetpick_conv_small_bf16(x.data_ptr(), Cc, B, Z, Hin, Win, stride, Ho, Wo, wh.data_ptr(), Cout, len(taps), tp,
+    rc = L.test_lib().cetpick_conv_small_bf16(x.data_ptr(), Cc, B, Z, Hin, Win, stride, Ho, Wo, wh.data_ptr(), Cout, len(taps), tp,
                                          bias.data_ptr() if bias is not None else None,
                                          residual.data_ptr() if residual is not None else None, int(relu), int(out_f32),
                                          out.data_ptr(), L.stream_ptr())

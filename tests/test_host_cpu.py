@@ -65,7 +65,7 @@ def test_load_model_contract(tmp_path, capsys):
     """models/model.py:195-251: 'module.' prefix stripped, shape mismatches and missing keys keep the model's own
     tensors, extra keys dropped, optimizer resume replays the lr schedule."""
     import torch
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.models.model import create_model, load_model, save_model
     m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
     sd = synth.unet_state_dict_torch(317, 4)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from cet_pick_b200 import synth
+import synthdata as synth
 from oracle import decode_oracle as do
 from oracle import refbridge
 from oracle import unet_oracle as uo

@@ -124,7 +124,7 @@ def _cand_worker(rank, world, port, depth, K, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
-    from cet_pick_b200 import synth
+    import synthdata as synth
     from cet_pick_b200.shard import gather_merge_candidates, shard_range
     from oracle import decode_oracle as do
     dist.init_process_group("gloo", rank=rank, world_size=world)
