@@ -526,7 +526,7 @@ def run_b200(a, rank, world, local_rank):
     # roofline of the dominant kernels (all tcgen05 conv layers): per-launch CUDA events inside the library,
     # median over 5 profiled forwards of distinct tomograms
     NPROF = 5
-    profs = [_lib.profile_forward(lambda i=i: model(pool[i % n_local][None])) for i in range(NPROF)] if n_local else []
+    profs = [_lib.profile_forward(model, lambda i=i: model(pool[i % n_local][None])) for i in range(NPROF)] if n_local else []
     fracs, conv_mss, tot_mss = [], [], []
     for prof in profs:
         conv = [(n, ms, fl) for n, ms, fl in prof if n.startswith("conv:")]
@@ -535,7 +535,7 @@ def run_b200(a, rank, world, local_rank):
     stem_u8_ms = None
     if n_local:
         dq[0].copy_(host_q[0])
-        stem_u8_ms = median([dict((n, ms) for n, ms, _ in _lib.profile_forward(lambda: model(dq[0][None])))["stem"]
+        stem_u8_ms = median([dict((n, ms) for n, ms, _ in _lib.profile_forward(model, lambda: model(dq[0][None])))["stem"]
                              for _ in range(3)])
     conv_fl = sum(f for n, _, f in profs[0] if n.startswith("conv:")) if profs else 0.0
     pk = peaks()
@@ -616,7 +616,7 @@ def run_b200(a, rank, world, local_rank):
             except Exception as e:
                 line["roofline_decode"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
-                prof = _lib.profile_forward(lambda: model_w1(x0[None]))
+                prof = _lib.profile_forward(model_w1, lambda: model_w1(x0[None]))
                 our_ms = sum(m for _, m, _ in prof)
                 our_hm = model_w1(x0[None])[-1]["hm"][0, 0]
                 line["torch_cuda_baseline"] = leg_torch_cuda_baseline(dev, (D, H, W), our_ms, our_hm)

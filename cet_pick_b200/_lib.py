@@ -60,8 +60,8 @@ SIGNATURES = {
     "cetpick_simsiam_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_simsiam_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "cetpick_last_launch_count": (_i64, []),
-    "cetpick_profile_enable": (_int, [_int]),
-    "cetpick_profile_read": (_int, [_int, C.POINTER(_int), _vp, _vp, _vp]),
+    "cetpick_unet_profile_enable": (_int, [_vp, _int]),
+    "cetpick_unet_profile_read": (_int, [_vp, _int, C.POINTER(_int), _vp, _vp, _vp]),
 }
 
 # test / tuning hooks of include/cetpick_test.h (libcetpick_test_sm100a.so only)
@@ -161,19 +161,20 @@ def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def profile_forward(fn):
-    """Run fn() (one or more cetpick_unet_forward calls) with per-launch CUDA-event timing and return
-    [(name, ms, flops)] of the LAST forward."""
+def profile_forward(model, fn):
+    """Run fn() (one or more forwards of `model`, a TomoConvUNet) with per-launch CUDA-event timing kept in the model's
+    plan and return [(name, ms, flops)] of the LAST forward."""
     L = lib()
-    L.cetpick_profile_enable(1)
+    plan = model.plan()
+    L.cetpick_unet_profile_enable(plan, 1)
     try:
         fn()
         n = C.c_int(0)
         ms = (C.c_float * 256)()
         fl = (C.c_double * 256)()
         names = C.create_string_buffer(256 * 32)
-        check(L.cetpick_profile_read(256, C.byref(n), ms, fl, names), "cetpick_profile_read")
+        check(L.cetpick_unet_profile_read(plan, 256, C.byref(n), ms, fl, names), "cetpick_unet_profile_read")
         return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), float(ms[i]), float(fl[i]))
                 for i in range(n.value)]
     finally:
-        L.cetpick_profile_enable(0)
+        L.cetpick_unet_profile_enable(plan, 0)

@@ -31,16 +31,33 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return ::cetpick::cuda_fail(e__, "kernel launch"); \
   } while (0)
 
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
 }
+
+inline int num_sms() {
+  static int n[64] = {};                       // per device: one process may hold plans on several GPUs
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
+// Function attributes (opt-in shared memory size) belong to a device context: set them once PER DEVICE.
+struct DeviceOnce {
+  unsigned long long done = 0;                 // bit d: the guarded block already ran on device d
+  bool first() {
+    const unsigned long long bit = 1ull << current_device();
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }

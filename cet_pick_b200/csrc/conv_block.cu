@@ -551,8 +551,9 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
   p.RS = std::min(MAX_RS, std::max(p.lag + 2, env_int("CETPICK_BLOCK_RS", p.lag + 3)));
   p.flags = env_int("CETPICK_BLOCK_FLAGS", 0);
   const int max_stages = std::min(MAX_STAGES, std::max(3, env_int("CETPICK_BLOCK_STAGES", MAX_STAGES)));
-  static int static_smem = -1;
-  if (static_smem < 0) {
+  static DeviceOnce attr_once;
+  static int static_smem = 0;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, kern));
     CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));

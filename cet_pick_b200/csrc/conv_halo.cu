@@ -280,8 +280,9 @@ int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {
     const uint32_t box[2] = {KC, NB};
     if ((rc = tmap_encode_bf16(&p.tmB, L.wpk, 2, dims, strides, box, KC))) return rc;
   }
-  static int static_smem = -1;
-  if (static_smem < 0) {
+  static DeviceOnce attr_once;
+  static int static_smem = 0;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_halo_kernel));
     CETPICK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

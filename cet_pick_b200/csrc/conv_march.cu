@@ -451,8 +451,9 @@ template <int COUT, int KC, int MODE, int MT>
 int launch_inst(MarchParams& p, const MarchLaunch& L, cudaStream_t stream) {
   using G = Geo<COUT, KC, MODE, MT>;
   auto kern = conv_march_kernel<COUT, KC, MODE, MT>;
-  static int static_smem = -1;
-  if (static_smem < 0) {
+  static DeviceOnce attr_once;
+  static int static_smem = 0;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, kern));
     CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

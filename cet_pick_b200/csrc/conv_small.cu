@@ -261,8 +261,9 @@ int conv_small_launch(const SmallLaunch& L, cudaStream_t stream) {
   for (int t = 0; t < L.ntaps; ++t) {
     p.tdz[t] = (signed char)L.tap[t][0]; p.tdy[t] = (signed char)L.tap[t][1]; p.tdx[t] = (signed char)L.tap[t][2];
   }
-  static int static_smem = -1;
-  if (static_smem < 0) {
+  static DeviceOnce attr_once;
+  static int static_smem = 0;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_small_kernel));
     CETPICK_CUDA(cudaFuncSetAttribute(conv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -347,11 +347,10 @@ int conv_stem_launch(const StemLaunch& L, cudaStream_t stream) {
   if ((!L.in && !u8) || (L.in && u8) || !L.wpk || !L.out || L.D <= 0 || L.H <= 0 || L.W <= 0) return CETPICK_ERR_BAD_ARG;
   if (u8 ? !stem_tc_supported_u8(L.in_u8, L.W) : !stem_tc_supported(L.in, L.W)) return CETPICK_ERR_UNSUPPORTED;
   if (u8 && L.lut[0] != 0) return CETPICK_ERR_BAD_ARG;     // level 0 doubles as the zero padding
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CETPICK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     CETPICK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_U8));
-    attr_done = true;
   }
   StemParams p;
   memset(&p, 0, sizeof(p));

@@ -406,13 +406,12 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel));
     CETPICK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024 - (int)fa.sharedSizeBytes));
-    attr_done = true;
   }
   const int grid = (int)std::min<long long>(p.total_tiles, num_sms());
   conv_tc_kernel<<<grid, CONV_THREADS, smem, stream>>>(p);

@@ -180,8 +180,9 @@ __global__ void __launch_bounds__(UP_THREADS, 1) conv_up_kernel(const __grid_con
 template <int NB>
 int launch_up(UpParams& p, cudaStream_t stream) {
   auto kern = conv_up_kernel<NB>;
-  static int static_smem = -1;
-  if (static_smem < 0) {
+  static DeviceOnce attr_once;
+  static int static_smem = 0;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     CETPICK_CUDA(cudaFuncGetAttributes(&fa, kern));
     CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));

@@ -1321,10 +1321,9 @@ template <int P, bool TMA, int MODE_T, int FIBER_T>
 int launch_scan_t(const ScanParams& p, int grid, cudaStream_t s) {
   const size_t smem = (size_t)(TMA ? NBUF : 3) * plane_buf_floats<P>() * sizeof(float) + HIST_BINS * sizeof(uint32_t);
   auto kern = scan_kernel<P, TMA, MODE_T, FIBER_T>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CETPICK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
   }
   CETPICK_CUDA(launch_k(kern, dim3(grid), dim3(SCAN_THREADS), smem, s, p));
   CETPICK_LAUNCH_CHECK();
@@ -1491,11 +1490,10 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   } else {
     const int use_smem = L.npad <= SORT_SMEM_MAX;
     const size_t smem = use_smem ? (size_t)L.npad * 8 : 0;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       CETPICK_CUDA(cudaFuncSetAttribute(sort_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         SORT_SMEM_MAX * 8));
-      attr_done = true;
     }
     CETPICK_CUDA(launch_k(sort_write_kernel, dim3(1), dim3(1024), smem, s, outb, K, L.npad, use_smem, heat, reg, D, H, W,
                             dets, inds));

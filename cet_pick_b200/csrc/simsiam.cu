@@ -337,11 +337,10 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
     const float* sw = reinterpret_cast<const float*>(blob + m->stem_w);
     const float* sb = reinterpret_cast<const float*>(blob + m->stem_b);
     auto smem_of = [](int hw) { const int ip = hw + 6, cw = hw / 2; return 49 * 64 * 4 + ((ip * (ip + 1) * 4 + 15) & ~15) + cw * cw * 66 * 2; };
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32)));
       CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(16)));
-      attr_done = true;
     }
     if (H == 32) stem_pool_kernel<32><<<grid, 256, smem_of(32), st>>>(x, n, sw, sb, buf[0]);
     else stem_pool_kernel<16><<<grid, 256, smem_of(16), st>>>(x, n, sw, sb, buf[0]);

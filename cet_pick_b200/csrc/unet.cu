@@ -214,7 +214,6 @@ struct Profiler {
     ++n;
   }
 };
-Profiler g_prof;
 
 }  // namespace
 }  // namespace cetpick
@@ -223,6 +222,7 @@ using namespace cetpick;
 
 struct cetpick_unet {
   int n_blocks, head_conv, proj_c;
+  mutable Profiler prof;         // per plan: two plans (or two streams of two plans) never share timing state
   std::map<std::string, std::vector<float>> params;
   bool finalized = false;
   std::vector<uint8_t> blob;     // host staging of all packed weights
@@ -381,7 +381,7 @@ struct HeadExtras {
 int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& pc, const void* s0, const void* s1,
              int NIMG, int H, int W, int epi, void* out, int Ho, int Wo, int Cout, cudaStream_t st,
              const HeadExtras* ex = nullptr, void* pool_out = nullptr) {
-  g_prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : pc.halo ? ":halo" : ":tc")).c_str(),
+  m->prof.mark((std::string("conv:") + name + (pc.march >= 0 ? ":march" : pc.halo ? ":halo" : ":tc")).c_str(),
               pc.flops_per_pixel * (double)NIMG * H * W, st);
   const float* bias = pc.has_bias ? reinterpret_cast<const float*>(static_cast<const uint8_t*>(m->d_blob) + pc.b_off) : nullptr;
   if (pc.march >= 0) {
@@ -434,7 +434,7 @@ bool use_block(const PackedConv& c1, const PackedConv& c2, int W) {
 
 int run_block(const cetpick_unet* m, const std::string& name, const PackedConv& c1, const PackedConv& c2, const void* s0,
               const void* s1, int NIMG, int H, int W, void* out, void* pool_out, cudaStream_t st) {
-  g_prof.mark((std::string("conv:") + name + ".c1+c2:block").c_str(), (c1.flops_per_pixel + c2.flops_per_pixel) * (double)NIMG * H * W, st);
+  m->prof.mark((std::string("conv:") + name + ".c1+c2:block").c_str(), (c1.flops_per_pixel + c2.flops_per_pixel) * (double)NIMG * H * W, st);
   BlockLaunch B;
   B.nsrc = c1.nsrc; B.src[0] = s0; B.src[1] = s1; B.C1 = c1.C[0]; B.NIMG = NIMG; B.H = H; B.W = W;
   B.w1pk = static_cast<const uint8_t*>(m->d_blob) + c1.w_off;
@@ -459,6 +459,7 @@ extern "C" int cetpick_unet_create(cetpick_unet** plan, int n_blocks, int head_c
 
 extern "C" void cetpick_unet_destroy(cetpick_unet* m) {
   if (!m) return;
+  for (cudaEvent_t e : m->prof.ev) cudaEventDestroy(e);
   if (m->d_blob) cudaFree(m->d_blob);
   delete m;
 }
@@ -644,8 +645,8 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
 
   // stem -> X0 (16 channels)
   {
-    g_prof.begin();
-    g_prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
+    m->prof.begin();
+    m->prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
     if (tomo_u8) {                              // quantised levels straight into the tensor-core march
       if (!stem_tc_supported_u8(tomo_u8, W)) return CETPICK_ERR_UNSUPPORTED;   // rows must be 16-byte aligned
       StemLaunch SL;
@@ -682,7 +683,7 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
                        nullptr, fuse_pool ? buf(i + 1, 0) : nullptr))) return rc;
     if (i < nb - 1 && !fuse_pool) {
       const int C = 32 << i;
-      g_prof.mark("pool2x2", 0.0, st);
+      m->prof.mark("pool2x2", 0.0, st);
       const size_t total = (size_t)D * dims[i + 1].h * dims[i + 1].w * (C / 8);
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
       pool2x2_kernel<<<grid, 256, 0, st>>>(buf(i, 2), D, h, w, C, buf(i + 1, 0));
@@ -696,7 +697,7 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
     const int h = dims[j].h, w = dims[j].w, Cout = 32 << j;
     if (m->upc[i].upk) {
       const PackedConv& u = m->upc[i];
-      g_prof.mark(("conv:up" + std::to_string(i) + ".upconv:up").c_str(), u.flops_per_pixel * (double)D * dims[j + 1].h * dims[j + 1].w, st);
+      m->prof.mark(("conv:up" + std::to_string(i) + ".upconv:up").c_str(), u.flops_per_pixel * (double)D * dims[j + 1].h * dims[j + 1].w, st);
       UpLaunch U;
       U.src = below; U.Cin = u.C[0]; U.NIMG = D; U.h = dims[j + 1].h; U.w = dims[j + 1].w;
       U.wpk = blob + u.w_off; U.bias = reinterpret_cast<const float*>(blob + u.b_off);
@@ -748,7 +749,7 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
       ex2.z_origin = (int)(z_origin % 840);
       if ((rc = run_conv(m, "fhead2", m->fh2, f_in, nullptr, D, h0, w0, EPI_BF16_NHWC, f_out, 0, 0, 0, st, &ex2))) return rc;
       const size_t plane = (size_t)h0 * w0, total = plane * D;
-      g_prof.mark("hm_head", 2.0 * 96 * (double)total, st);
+      m->prof.mark("hm_head", 2.0 * 96 * (double)total, st);
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
       hm_head_kernel<<<grid, 256, 0, st>>>(f_out, D, plane, hmw, apply_sigmoid, hm);
       CETPICK_LAUNCH_CHECK();
@@ -757,7 +758,7 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
       }
     }
   }
-  g_prof.mark("end", 0.0, st);
+  m->prof.mark("end", 0.0, st);
   return CETPICK_OK;
 }
 }  // namespace
@@ -786,24 +787,26 @@ extern "C" int cetpick_unet_forward_slab(cetpick_unet* m, const float* tomo, con
                            stream);
 }
 
-extern "C" int cetpick_profile_enable(int on) {
-  g_prof.on = on != 0;
+extern "C" int cetpick_unet_profile_enable(cetpick_unet* m, int on) {
+  if (!m) return CETPICK_ERR_BAD_ARG;
+  m->prof.on = on != 0;
   return CETPICK_OK;
 }
 
-// Per-launch device times of the most recent profiled cetpick_unet_forward (synchronises).
-extern "C" int cetpick_profile_read(int max_entries, int* n, float* ms, double* flops, char* names32) {
-  if (!n) return CETPICK_ERR_BAD_ARG;
-  const int cnt = std::max(0, g_prof.n - 1);
+// Per-launch device times of the most recent profiled cetpick_unet_forward of this plan (synchronises).
+extern "C" int cetpick_unet_profile_read(cetpick_unet* m, int max_entries, int* n, float* ms, double* flops, char* names32) {
+  if (!m || !n) return CETPICK_ERR_BAD_ARG;
+  Profiler& P = m->prof;
+  const int cnt = std::max(0, P.n - 1);
   *n = cnt;
   if (cnt == 0) return CETPICK_OK;
-  CETPICK_CUDA(cudaEventSynchronize(g_prof.ev[g_prof.n - 1]));
+  CETPICK_CUDA(cudaEventSynchronize(P.ev[P.n - 1]));
   for (int i = 0; i < cnt && i < max_entries; ++i) {
     float t = 0.f;
-    CETPICK_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    CETPICK_CUDA(cudaEventElapsedTime(&t, P.ev[i], P.ev[i + 1]));
     if (ms) ms[i] = t;
-    if (flops) flops[i] = g_prof.flops[i];
-    if (names32) { strncpy(names32 + (size_t)i * 32, g_prof.names[i].c_str(), 31); names32[(size_t)i * 32 + 31] = 0; }
+    if (flops) flops[i] = P.flops[i];
+    if (names32) { strncpy(names32 + (size_t)i * 32, P.names[i].c_str(), 31); names32[(size_t)i * 32 + 31] = 0; }
   }
   return CETPICK_OK;
 }

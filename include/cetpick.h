@@ -236,11 +236,11 @@ int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, in
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);
 
-/* Per-launch timing of cetpick_unet_forward with CUDA events on the launching stream (bench.py's
- * roofline).  enable(1), run a forward, then read(): n entries of (milliseconds, algorithmic FLOPs,
+/* Per-launch timing of cetpick_unet_forward with CUDA events on the launching stream (bench.py's roofline), kept in
+ * the plan.  enable(plan, 1), run a forward of that plan, then read(): n entries of (milliseconds, algorithmic FLOPs,
  * 32-byte name) in launch order.  read() synchronises; profiling adds one event per launch. */
-int cetpick_profile_enable(int on);
-int cetpick_profile_read(int max_entries, int* n, float* ms, double* flops, char* names32);
+int cetpick_unet_profile_enable(cetpick_unet* plan, int on);
+int cetpick_unet_profile_read(cetpick_unet* plan, int max_entries, int* n, float* ms, double* flops, char* names32);
 
 #ifdef __cplusplus
 }
