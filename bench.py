@@ -620,6 +620,18 @@ def run_b200(a, rank, world, local_rank):
                 our_ms = sum(m for _, m, _ in prof)
                 our_hm = model_w1(x0[None])[-1]["hm"][0, 0]
                 line["torch_cuda_baseline"] = leg_torch_cuda_baseline(dev, (D, H, W), our_ms, our_hm)
+                # TF32 mode of the same forward (north_star's second tolerance): time and distance to the BF16 heat-map
+                model_w1.precision = "tf32"
+                model_w1._ws = None
+                torch.cuda.empty_cache()
+                prof = _lib.profile_forward(model_w1, lambda: model_w1(x0[None]))
+                hm32 = model_w1(x0[None])[-1]["hm"][0, 0]
+                line["tf32_mode"] = {"forward_ms": sum(m for _, m, _ in prof),
+                                     "max_abs_diff_vs_bf16_mode": float((hm32 - our_hm).abs().max()),
+                                     "note": "tcgen05 kind::tf32 through the generic implicit-GEMM kernel, fp32 activations; "
+                                             "parity <= 1e-4 vs the fp32 oracle is asserted in tests/test_gpu_unet.py"}
+                model_w1.precision = "bf16"
+                del hm32
             except Exception as e:
                 line["torch_cuda_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         finally:

@@ -48,6 +48,7 @@ SIGNATURES = {
     "cetpick_unet_create": (_int, [C.POINTER(_vp), _int, _int, _int]),
     "cetpick_unet_destroy": (None, [_vp]),
     "cetpick_unet_set_param": (_int, [_vp, C.c_char_p, _vp, _i64]),
+    "cetpick_unet_set_precision": (_int, [_vp, _int]),
     "cetpick_unet_finalize": (_int, [_vp]),
     "cetpick_unet_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "cetpick_unet_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),

@@ -39,11 +39,30 @@ struct alignas(64) ConvParams {
   int stages, a_sub, b_sub;    // pipeline depth, bytes of one A / B k-block
   int layout_type;             // UMMA swizzle code
   int epi, relu;
+  int tf32;                    // 1: fp32 activations / weights (pre-rounded to TF32), kind::tf32 UMMA, fp32 NHWC out
   const float* bias;
   void* out;
   int out_cstride, Ho, Wo, Cout;
   signed char tdz[27], tdy[27], tdx[27];
 };
+
+// fp32 -> nearest TF32 (10-bit mantissa), ties away from zero: stored activations are exactly what the UMMA reads
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 x TF32 -> FP32 (K = 8 per instruction)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, long long t, int& img, int& y0,
                                             int& x0, int& nb) {
@@ -122,9 +141,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, p.NB);
-      const uint32_t sbo = 16u * (uint32_t)p.KC;          // 8 rows x (KC * 2 bytes)
-      const int k16s = p.KC / 16;
+      // kind::tf32: a_format = b_format = 2 (TF32) in bits [7,10) / [10,13), c_format = 1 (F32)
+      const uint32_t idesc = p.tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24))
+                                    : ptx::make_idesc_bf16(TILE_M, p.NB);
+      const uint32_t esz = p.tf32 ? 4u : 2u;
+      const uint32_t sbo = 8u * esz * (uint32_t)p.KC;     // 8 rows x (KC * element bytes)
+      const int k16s = (int)(p.KC * esz / 32u);           // one UMMA consumes 32 bytes of K per row
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -144,7 +166,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             for (int k = 0; k < k16s; ++k) {
               const uint64_t da = ptx::make_smem_desc(a0 + j * p.a_sub + k * 32, sbo, p.layout_type);
               const uint64_t db = ptx::make_smem_desc(b0 + j * p.b_sub + k * 32, sbo, p.layout_type);
-              ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
+              if (p.tf32) umma_tf32(d_tmem, da, db, idesc, accumulate);
+              else ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
               accumulate = 1;
             }
           }
@@ -206,18 +229,26 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         if (!valid) {
           // masked pixel of a ragged edge tile: nothing to store
         } else if (p.epi == EPI_BF16_NHWC || p.epi == EPI_UPCONV_2X2) {
-          __nv_bfloat16* dst;
+          size_t off;
           bool store = true;
           if (p.epi == EPI_BF16_NHWC) {
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                  (((size_t)img * p.H + y) * p.W + x) * p.out_cstride + col;
+            off = (((size_t)img * p.H + y) * p.W + x) * p.out_cstride + col;
           } else {
             const int qd = col / p.Cout, ch = col - qd * p.Cout;
             const int oy = 2 * y + (qd >> 1), ox = 2 * x + (qd & 1);
             store = (oy < p.Ho) && (ox < p.Wo);              // autocrop (unet.py:285-292)
-            dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                  (((size_t)img * p.Ho + oy) * p.Wo + ox) * p.Cout + ch;
+            off = (((size_t)img * p.Ho + oy) * p.Wo + ox) * p.Cout + ch;
           }
+          if (p.tf32) {                                      // fp32 NHWC activations, rounded to TF32 once here
+            if (store) {
+              float* d32 = reinterpret_cast<float*>(p.out) + off;
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(d32 + i) = make_float4(round_tf32(f[i]), round_tf32(f[i + 1]), round_tf32(f[i + 2]), round_tf32(f[i + 3]));
+            }
+            continue;
+          }
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
           uint4 w0, w1;
           w0.x = pack_bf16x2(f[0], f[1]);   w0.y = pack_bf16x2(f[2], f[3]);
           w0.z = pack_bf16x2(f[4], f[5]);   w0.w = pack_bf16x2(f[6], f[7]);
@@ -364,13 +395,16 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
   while (L.Ntot % NB) NB -= 16;
   p.NB = NB;
   p.n_nb = L.Ntot / NB;
-  const int kstage = (NB <= 64) ? 128 : 64;
-  p.NKB = kstage / L.KC;
-  p.a_sub = TILE_M * L.KC * 2;
-  p.b_sub = NB * L.KC * 2;
+  const int esz = L.tf32 ? 4 : 2;
+  if (L.tf32 && L.KC > 32) return CETPICK_ERR_BAD_ARG;      // the swizzle span is KC * 4 bytes <= 128
+  p.tf32 = L.tf32;
+  const int kstage_bytes = (NB <= 64) ? 256 : 128;
+  p.NKB = std::max(1, kstage_bytes / (L.KC * esz));
+  p.a_sub = TILE_M * L.KC * esz;
+  p.b_sub = NB * L.KC * esz;
   const int stage_bytes = (p.a_sub + p.b_sub) * p.NKB;
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes)));
-  p.layout_type = L.KC == 64 ? 2 : L.KC == 32 ? 4 : 6;
+  p.layout_type = L.KC * esz == 128 ? 2 : L.KC * esz == 64 ? 4 : 6;
   p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.tiles_x = ceil_div(L.W, TILE_W);
   p.tiles_y = ceil_div(L.H, TILE_H);
@@ -383,24 +417,25 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
   if (L.epi == EPI_UPCONV_2X2 && (L.Cout <= 0 || (L.Cout % 16) || L.Ntot != 4 * L.Cout)) return CETPICK_ERR_BAD_ARG;
   if (L.epi == EPI_F32_L2NORM_NCDHW && p.n_nb != 1) return CETPICK_ERR_UNSUPPORTED;
 
-  const CUtensorMapSwizzle sw = swizzle_of(L.KC);
+  const CUtensorMapSwizzle sw = swizzle_of(L.KC * esz / 2);
+  const CUtensorMapDataType dt = L.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   for (int s = 0; s < L.nsrc; ++s) {
     const cuuint64_t C = (cuuint64_t)L.C[s];
     cuuint64_t dims[4] = {C, (cuuint64_t)L.W, (cuuint64_t)L.H, (cuuint64_t)L.NIMG};
-    cuuint64_t strides[3] = {C * 2, C * 2 * L.W, C * 2 * (cuuint64_t)L.W * L.H};
+    cuuint64_t strides[3] = {C * esz, C * esz * L.W, C * esz * (cuuint64_t)L.W * L.H};
     cuuint32_t box[4] = {(cuuint32_t)L.KC, TILE_W, TILE_H, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(L.src[s]), dims,
+    CUresult r = enc(&p.tmA[s], dt, 4, const_cast<void*>(L.src[s]), dims,
                      strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)L.KC, (cuuint64_t)p.nkb * L.Ntot};
-    cuuint64_t strides[1] = {(cuuint64_t)L.KC * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)L.KC * esz};
     cuuint32_t box[2] = {(cuuint32_t)L.KC, (cuuint32_t)NB};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(L.wpk), dims, strides,
+    CUresult r = enc(&p.tmB, dt, 2, const_cast<void*>(L.wpk), dims, strides,
                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }

@@ -22,7 +22,8 @@ struct ConvLaunch {
   int NIMG = 0, H = 0, W = 0;
   // weights: bf16 [k-block][Ntot][KC], k-block = ((source, tap, channel chunk)) in loop order
   const void* wpk = nullptr;
-  int KC = 64;              // channels per k-block: 16 / 32 / 64 (selects the 32/64/128-byte swizzle)
+  int KC = 64;              // channels per k-block: 16 / 32 / 64 (selects the 32/64/128-byte swizzle); tf32: 8 / 16 / 32
+  int tf32 = 0;             // 1: sources, weights and NHWC outputs are fp32 holding TF32 values (kind::tf32 UMMA)
   int ntaps = 1;
   int tap[27][3] = {};      // (dz, dy, dx) input offsets per tap
   int Ntot = 0;             // GEMM N (output columns), multiple of 16

@@ -41,10 +41,18 @@ constexpr double BN_EPS = 1e-5;
 // so that the stride-2 window reads of a warp hit consecutive banks.
 constexpr int ST_TW = 64, ST_TH = 16, ST_IW = 2 * ST_TW + 5, ST_IH = 2 * ST_TH + 5, ST_HP = 68;
 
+__device__ __forceinline__ float round_tf32_dev(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <bool F32OUT>
 __global__ void __launch_bounds__(256, 2) stem_kernel(const float* __restrict__ in, int D, int H, int W,
                                                       int h, int w, const float* __restrict__ wgt /*[49][16]*/,
                                                       const float* __restrict__ bias /*[16]*/,
-                                                      __nv_bfloat16* __restrict__ out) {
+                                                      void* __restrict__ out_v) {
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_v);
   __shared__ float s_par[2][ST_IH][ST_HP];       // [column parity][patch row][patch column / 2]
   __shared__ __align__(16) float s_w[49 * 16];
   __shared__ float s_b[16];
@@ -100,7 +108,15 @@ __global__ void __launch_bounds__(256, 2) stem_kernel(const float* __restrict__ 
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         const int ox = tx0 + lx + 32 * b, oy = ty0 + 2 * ty + a;
-        if (ox < w && oy < h) {
+        if (F32OUT) {                       // TF32 mode: fp32 NHWC16, values rounded to TF32
+          if (ox < w && oy < h) {
+            float4* d4 = reinterpret_cast<float4*>(static_cast<float*>(out_v) + (((size_t)z * h + oy) * w + ox) * 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              d4[c] = make_float4(round_tf32_dev(fmaxf(acc[a][b][4 * c], 0.f)), round_tf32_dev(fmaxf(acc[a][b][4 * c + 1], 0.f)),
+                                  round_tf32_dev(fmaxf(acc[a][b][4 * c + 2], 0.f)), round_tf32_dev(fmaxf(acc[a][b][4 * c + 3], 0.f)));
+          }
+        } else if (ox < w && oy < h) {
           uint32_t pk[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -144,6 +160,61 @@ __global__ void __launch_bounds__(256) pool2x2_kernel(const __nv_bfloat16* __res
     if (hy) m = mx(m, at(y0 + 1, x0));
     if (hx && hy) m = mx(m, at(y0 + 1, x0 + 1));
     reinterpret_cast<uint4*>(out)[i] = m;
+  }
+}
+
+// TF32 mode twins (fp32 NHWC activations): MaxPool2d(2, ceil) with one thread per 4 channels, and the hm head
+__global__ void __launch_bounds__(256) pool2x2_f32_kernel(const float* __restrict__ in, int N, int H, int W, int C,
+                                                          float* __restrict__ out) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  const float4* base = reinterpret_cast<const float4*>(in);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const int y0 = 2 * oy, x0 = 2 * ox;
+    auto at = [&](int y, int x) { return base[(((size_t)n * H + y) * W + x) * C4 + c4]; };
+    auto mx = [](float4 a, float4 b) { return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)); };
+    float4 m = at(y0, x0);
+    const bool hx = x0 + 1 < W, hy = y0 + 1 < H;
+    if (hx) m = mx(m, at(y0, x0 + 1));
+    if (hy) m = mx(m, at(y0 + 1, x0));
+    if (hx && hy) m = mx(m, at(y0 + 1, x0 + 1));
+    reinterpret_cast<float4*>(out)[i] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) hm_head_f32_kernel(const float* __restrict__ feat, int D, size_t plane,
+                                                          const float* __restrict__ wgt /*[3][32]*/, int apply_sigmoid,
+                                                          float* __restrict__ out) {
+  __shared__ float s_w[96];
+  if (threadIdx.x < 96) s_w[threadIdx.x] = wgt[threadIdx.x];
+  __syncthreads();
+  const size_t total = (size_t)D * plane;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(i / plane);
+    float acc = 0.f;
+#pragma unroll
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int zz = z + dz;
+      if (zz < 0 || zz >= D) continue;
+      const float4* src = reinterpret_cast<const float4*>(feat + (i + (ptrdiff_t)dz * (ptrdiff_t)plane) * 32);
+      const float* wr = &s_w[(dz + 1) * 32];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = src[q];
+        acc = fmaf(v.x, wr[4 * q], acc); acc = fmaf(v.y, wr[4 * q + 1], acc);
+        acc = fmaf(v.z, wr[4 * q + 2], acc); acc = fmaf(v.w, wr[4 * q + 3], acc);
+      }
+    }
+    if (apply_sigmoid) {
+      const float y = 1.0f / (1.0f + expf(-acc));
+      acc = fminf(fmaxf(y, 1e-4f), 1.0f - 1e-4f);
+    }
+    out[i] = acc;
   }
 }
 
@@ -222,6 +293,7 @@ using namespace cetpick;
 
 struct cetpick_unet {
   int n_blocks, head_conv, proj_c;
+  int precision = 0;             // 0: BF16 operands (the specialised kernels); 1: TF32 operands (generic kernel, fp32 maps)
   mutable Profiler prof;         // per plan: two plans (or two streams of two plans) never share timing state
   std::map<std::string, std::vector<float>> params;
   bool finalized = false;
@@ -260,6 +332,16 @@ bool bn_fold(const cetpick_unet* m, const std::string& p, int C, Fold& f) {
   return true;
 }
 
+// fp32 -> nearest TF32 (10-bit mantissa, ties away from zero like cvt.rna.tf32.f32)
+float tf32_round_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
 size_t blob_alloc(cetpick_unet* m, size_t bytes) {
   const size_t off = align_up(m->blob.size(), 256);
   m->blob.resize(off + bytes, 0);
@@ -274,14 +356,30 @@ bool pack_conv(cetpick_unet* m, const std::string& wkey, int Cout, int nsrc, int
   const int Cin = nsrc * Csrc;
   auto w = w_override ? w_override : m->get(wkey, (size_t)Cout * Cin * ntaps);
   if (!w || w->size() != (size_t)Cout * Cin * ntaps) return false;
-  pc.KC = std::min(64, Csrc);
+  const bool tf32 = m->precision == 1;
+  pc.KC = std::min(tf32 ? 32 : 64, Csrc);
   if (Csrc % pc.KC) return false;
   pc.ntaps = ntaps; pc.Ntot = Cout; pc.nsrc = nsrc; pc.C[0] = Csrc; pc.C[1] = nsrc > 1 ? Csrc : 0;
   pc.relu = relu;
   const int chunks = Csrc / pc.KC;
   const size_t nkb = (size_t)nsrc * ntaps * chunks;
   const int mmode = ntaps == 9 ? MARCH_2D_ROWS : ntaps == 27 ? MARCH_3D_PLANES : -1;
-  if (mmode >= 0 && march_supported(mmode, Csrc, nsrc, Cout)) {
+  if (tf32) {
+    // TF32 mode: every convolution runs through the generic implicit GEMM with fp32 weights rounded to TF32
+    pc.w_off = blob_alloc(m, nkb * Cout * pc.KC * 4);
+    float* dst = reinterpret_cast<float*>(m->blob.data() + pc.w_off);
+    for (int s = 0; s < nsrc; ++s)
+      for (int t = 0; t < ntaps; ++t)
+        for (int ch = 0; ch < chunks; ++ch) {
+          const size_t kb = ((size_t)s * ntaps + t) * chunks + ch;
+          for (int n = 0; n < Cout; ++n)
+            for (int k = 0; k < pc.KC; ++k) {
+              const int ci = s * Csrc + ch * pc.KC + k;
+              const double v = (double)(*w)[((size_t)n * Cin + ci) * ntaps + t] * (fold ? fold->scale[n] : 1.0);
+              dst[(kb * Cout + n) * pc.KC + k] = tf32_round_host((float)v);
+            }
+        }
+  } else if (mmode >= 0 && march_supported(mmode, Csrc, nsrc, Cout)) {
     // narrow layer: weight image of the marching kernel (conv_march.cu)
     const std::vector<uint16_t> pk = march_pack_weights(mmode, w->data(), Cout, nsrc, Csrc, fold ? fold->scale.data() : nullptr);
     pc.march = mmode;
@@ -354,13 +452,13 @@ struct WsPlan {
   size_t total = 0;
 };
 
-WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W) {
+WsPlan ws_plan(int n_blocks, int64_t D, int64_t H, int64_t W, int esz = 2) {
   WsPlan p;
   auto dims = level_dims(n_blocks, H, W);
   size_t o = 0;
   for (int i = 0; i < n_blocks; ++i) {
     const size_t C = (size_t)32 << i;
-    const size_t sz = align_up((size_t)D * dims[i].h * dims[i].w * C * 2, 1024);
+    const size_t sz = align_up((size_t)D * dims[i].h * dims[i].w * C * esz, 1024);
     p.size.push_back(sz);
     for (int b = 0; b < 3; ++b) { p.off.push_back(o); o += sz; }
   }
@@ -411,7 +509,7 @@ int run_conv(const cetpick_unet* m, const std::string& name, const PackedConv& p
   L.nsrc = pc.nsrc; L.src[0] = s0; L.src[1] = s1; L.C[0] = pc.C[0]; L.C[1] = pc.C[1];
   L.NIMG = NIMG; L.H = H; L.W = W;
   L.wpk = static_cast<const uint8_t*>(m->d_blob) + pc.w_off;
-  L.KC = pc.KC; L.ntaps = pc.ntaps;
+  L.KC = pc.KC; L.ntaps = pc.ntaps; L.tf32 = m->precision == 1;
   memcpy(L.tap, pc.tap, sizeof(L.tap));
   L.Ntot = pc.Ntot;
   L.bias = bias;
@@ -473,6 +571,13 @@ extern "C" int cetpick_unet_set_param(cetpick_unet* m, const char* key, const fl
   return CETPICK_OK;
 }
 
+extern "C" int cetpick_unet_set_precision(cetpick_unet* m, int mode) {
+  if (!m || (mode != 0 && mode != 1)) return CETPICK_ERR_BAD_ARG;
+  if (m->precision != mode) m->finalized = false;
+  m->precision = mode;
+  return CETPICK_OK;
+}
+
 extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
   if (!m) return CETPICK_ERR_BAD_ARG;
   m->blob.clear();
@@ -518,8 +623,21 @@ extern "C" int cetpick_unet_finalize(cetpick_unet* m) {
       auto w = m->get(p + ".upconv.weight", (size_t)ins * outs * 4);
       auto b = m->get(p + ".upconv.bias", outs);
       if (!w || !b || !bn_fold(m, p + ".norm0", outs, f)) return CETPICK_ERR_STATE;
-      u.KC = std::min(64, ins); u.ntaps = 1; u.Ntot = 4 * outs; u.nsrc = 1; u.C[0] = ins; u.relu = 1;
-      if (upconv_supported(ins, outs)) {
+      const bool tf32 = m->precision == 1;
+      u.KC = std::min(tf32 ? 32 : 64, ins); u.ntaps = 1; u.Ntot = 4 * outs; u.nsrc = 1; u.C[0] = ins; u.relu = 1;
+      if (tf32) {
+        const int chunks = ins / u.KC;
+        u.w_off = blob_alloc(m, (size_t)chunks * u.Ntot * u.KC * 4);
+        float* dst = reinterpret_cast<float*>(m->blob.data() + u.w_off);
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int q = 0; q < 4; ++q)
+            for (int co = 0; co < outs; ++co)
+              for (int k = 0; k < u.KC; ++k) {
+                const int ci = ch * u.KC + k;
+                const double v = (double)(*w)[((size_t)ci * outs + co) * 4 + q] * f.scale[co];
+                dst[((size_t)ch * u.Ntot + q * outs + co) * u.KC + k] = tf32_round_host((float)v);
+              }
+      } else if (upconv_supported(ins, outs)) {
         const std::vector<uint16_t> pk = upconv_pack_weights(w->data(), ins, outs, f.scale.data());
         u.upk = true;
         u.w_off = blob_alloc(m, pk.size() * 2);
@@ -618,7 +736,7 @@ extern "C" int cetpick_unet_workspace_bytes(const cetpick_unet* m, int64_t D, in
   if (!m || !bytes || D <= 0 || H <= 0 || W <= 0) return CETPICK_ERR_BAD_ARG;
   auto dims = level_dims(m->n_blocks, H, W);
   if (dims.back().h < 1 || dims.back().w < 1) return CETPICK_ERR_BAD_ARG;
-  *bytes = ws_plan(m->n_blocks, D, H, W).total + 1024;
+  *bytes = ws_plan(m->n_blocks, D, H, W, m->precision == 1 ? 4 : 2).total + 1024;
   return CETPICK_OK;
 }
 
@@ -633,7 +751,8 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
   if (proj && m->proj_c == 0) return CETPICK_ERR_STATE;
   if (D64 > 32767 || H64 > (1 << 20) || W64 > (1 << 20)) return CETPICK_ERR_BAD_ARG;
   const int D = (int)D64, H = (int)H64, W = (int)W64, nb = m->n_blocks;
-  const WsPlan wp = ws_plan(nb, D, H, W);
+  const bool tf32 = m->precision == 1;
+  const WsPlan wp = ws_plan(nb, D, H, W, tf32 ? 4 : 2);
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   if (!ws || ws_bytes < wp.total + (size_t)(base - static_cast<uint8_t*>(ws))) return CETPICK_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -647,7 +766,14 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
   {
     m->prof.begin();
     m->prof.mark("stem", 2.0 * 49 * 16 * (double)D * dims[0].h * dims[0].w, st);
-    if (tomo_u8) {                              // quantised levels straight into the tensor-core march
+    if (tf32) {                                 // TF32 mode: CUDA-core fp32 stem (exact fp32 FMAs), fp32 NHWC16 out
+      if (tomo_u8) return CETPICK_ERR_UNSUPPORTED;
+      const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
+      const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
+      stem_kernel<true><<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w, reinterpret_cast<const float*>(blob + m->stem_w),
+                                              reinterpret_cast<const float*>(blob + m->stem_b), buf(0, 0));
+      CETPICK_LAUNCH_CHECK();
+    } else if (tomo_u8) {                       // quantised levels straight into the tensor-core march
       if (!stem_tc_supported_u8(tomo_u8, W)) return CETPICK_ERR_UNSUPPORTED;   // rows must be 16-byte aligned
       StemLaunch SL;
       SL.in_u8 = tomo_u8; SL.D = D; SL.H = H; SL.W = W; SL.wpk = blob + m->stem_tc_w; SL.out = buf(0, 0);
@@ -662,7 +788,7 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
     } else {                                    // rows not 16-byte aligned: CUDA-core kernel
       const long long tiles = (long long)ceil_div(dims[0].w, ST_TW) * ceil_div(dims[0].h, ST_TH) * D;
       const int grid = (int)std::min<long long>(tiles, (long long)sms * 2);
-      stem_kernel<<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
+      stem_kernel<false><<<grid, 256, 0, st>>>(tomo, D, H, W, dims[0].h, dims[0].w,
                                         reinterpret_cast<const float*>(blob + m->stem_w),
                                         reinterpret_cast<const float*>(blob + m->stem_b), buf(0, 0));
       CETPICK_LAUNCH_CHECK();
@@ -684,9 +810,10 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
     if (i < nb - 1 && !fuse_pool) {
       const int C = 32 << i;
       m->prof.mark("pool2x2", 0.0, st);
-      const size_t total = (size_t)D * dims[i + 1].h * dims[i + 1].w * (C / 8);
+      const size_t total = (size_t)D * dims[i + 1].h * dims[i + 1].w * (C / (tf32 ? 4 : 8));
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
-      pool2x2_kernel<<<grid, 256, 0, st>>>(buf(i, 2), D, h, w, C, buf(i + 1, 0));
+      if (tf32) pool2x2_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(buf(i, 2)), D, h, w, C, reinterpret_cast<float*>(buf(i + 1, 0)));
+      else pool2x2_kernel<<<grid, 256, 0, st>>>(buf(i, 2), D, h, w, C, buf(i + 1, 0));
       CETPICK_LAUNCH_CHECK();
     }
   }
@@ -751,7 +878,8 @@ int unet_forward_impl(cetpick_unet* m, const float* tomo, const uint8_t* tomo_u8
       const size_t plane = (size_t)h0 * w0, total = plane * D;
       m->prof.mark("hm_head", 2.0 * 96 * (double)total, st);
       const int grid = (int)std::min<size_t>(ceil_div<size_t>(total, 256), (size_t)sms * 16);
-      hm_head_kernel<<<grid, 256, 0, st>>>(f_out, D, plane, hmw, apply_sigmoid, hm);
+      if (tf32) hm_head_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(f_out), D, plane, hmw, apply_sigmoid, hm);
+      else hm_head_kernel<<<grid, 256, 0, st>>>(f_out, D, plane, hmw, apply_sigmoid, hm);
       CETPICK_LAUNCH_CHECK();
       if (proj) {
         if ((rc = run_conv(m, "proj", m->proj, f_out, nullptr, D, h0, w0, EPI_F32_L2NORM_NCDHW, proj, 0, 0, 0, st))) return rc;

@@ -35,6 +35,8 @@ class BaseDetector(object):
         net = create_model(opt.arch, opt.heads, opt.head_conv, last_k=opt.last_k)
         net = load_model(net, opt.load_model)            # a checkpoint is always loaded, like the reference (:24)
         self.model = net.to(opt.device).eval()
+        if hasattr(self.model, "precision"):
+            self.model.precision = getattr(opt, "precision", "bf16")
         self.max_per_image = 900
         self.opt = opt
         self.pause = True

@@ -100,6 +100,9 @@ class TomoConvUNet(nn.Module):
         self.level_values = None
         # absolute z of plane 0 of the tensors passed to forward() (a z-shard of a larger volume, shard.py)
         self.z_origin = 0
+        # operand precision of the tensor-core convolutions: "bf16" (default, heat-map within 1e-2 of the fp32 reference)
+        # or "tf32" (within 1e-4; generic kernel, about half the throughput ceiling).  north_star's two tolerances.
+        self.precision = "bf16"
         self.compute_proj = "proj" in heads      # detectors switch this off (they never read 'proj')
         self.fuse_sigmoid = False                # TomodetDetector fuses _sigmoid into the hm epilogue
         self._plan = None
@@ -108,7 +111,7 @@ class TomoConvUNet(nn.Module):
 
     # ------------------------------------------------------------------ plan management
     def _param_key(self):
-        return tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
+        return (self.precision,) + tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
 
     def _destroy_plan(self):
         if self._plan is not None:
@@ -138,6 +141,9 @@ class TomoConvUNet(nn.Module):
                 continue
             t = v.detach().to("cpu", torch.float32).contiguous()
             _lib.check(L.cetpick_unet_set_param(h, k.encode(), t.data_ptr(), t.numel()), f"set_param({k})")
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError("TomoConvUNet.precision must be 'bf16' or 'tf32'")
+        _lib.check(L.cetpick_unet_set_precision(h, 1 if self.precision == "tf32" else 0), "cetpick_unet_set_precision")
         _lib.check(L.cetpick_unet_finalize(h), "cetpick_unet_finalize")
         self._plan, self._plan_key = h, key
         return h
@@ -180,7 +186,7 @@ class TomoConvUNet(nn.Module):
                                        else np.asarray(lv, dtype=np.float32))
             if lut.shape != (256,) or lut[0] != 0:
                 raise ValueError("TomoConvUNet: level_values must be 256 float32 values with level_values[0] == 0")
-            if w % 16:        # the TMA path needs 16-byte aligned rows: expand the levels on the device instead
+            if w % 16 or self.precision == "tf32":   # the uint8 TMA stem is BF16-only / needs 16-byte rows: expand on the device
                 x, lut = torch.from_numpy(lut).to(x.device)[x.long()], None
             else:
                 x = x.contiguous()

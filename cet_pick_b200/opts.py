@@ -31,7 +31,10 @@ _FLAGS = [
     ("--save_all", dict(action="store_true")), ("--metric", dict(default="loss")),
     ("--vis_thresh", dict(type=float, default=0.3)),
     ("--debugger_theme", dict(default="white", choices=["white", "black"])),
-    ("--arch", dict(default="unet_4")), ("--last_k", dict(type=int, default=3)),
+    ("--arch", dict(default="unet_4")),
+    # not in the reference: operand precision of the detector's tensor-core convolutions (bf16: heat-map within 1e-2 of
+    # the fp32 reference; tf32: within 1e-4)
+    ("--precision", dict(default="bf16", choices=["bf16", "tf32"])), ("--last_k", dict(type=int, default=3)),
     ("--head_conv", dict(type=int, default=-1)), ("--down_ratio", dict(type=int, default=2)),
     ("--pretrained_model", dict(type=str, default=None)),
     ("--input_res", dict(type=int, default=-1)), ("--input_h", dict(type=int, default=-1)),

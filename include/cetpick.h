@@ -175,6 +175,11 @@ void cetpick_unet_destroy(cetpick_unet* plan);
 int cetpick_unet_set_param(cetpick_unet* plan, const char* key, const float* data_host,
                            int64_t numel);
 
+/* Operand precision, to be chosen before cetpick_unet_finalize: 0 = BF16 (default; the specialised kernels, heat-map
+ * within 1e-2 of the fp32 reference), 1 = TF32 (fp32 activations holding TF32 values, tcgen05 kind::tf32 through the
+ * generic implicit-GEMM kernel, heat-map within 1e-4; about half the tensor peak and twice the activation bytes). */
+int cetpick_unet_set_precision(cetpick_unet* plan, int mode);
+
 /* Fold BatchNorm, repack to the tensor-core layouts and upload.  Synchronous. */
 int cetpick_unet_finalize(cetpick_unet* plan);
 

@@ -286,3 +286,41 @@ def test_fused_block_path_equals_two_kernel_path(monkeypatch):
     b = m(x)[-1]["hm"]
     assert m.last_launches == n_plain - 2            # two blocks: four convolutions became two launches
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["unet4_even", "unet4_odd", "unet5_small"])
+def test_tf32_mode_vs_reference_golden(golden, name):
+    """north_star's second tolerance: TF32 operands (tcgen05 kind::tf32, fp32 activations rounded to TF32 once per layer)
+    keep the heat-map within 1e-4 of the fp32 reference."""
+    g = golden(name)
+    D, H, W = [int(v) for v in g["shape"]]
+    m = build_model(int(g["n_blocks"]), int(g["seed_w"]))
+    m.precision = "tf32"
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, int(g["seed_x"])))[None].cuda()
+    out = m(x)[-1]
+    torch.cuda.synchronize()
+    from cet_pick_b200.models.utils import _sigmoid
+    err_raw = np.abs(out["hm"].cpu().numpy() - g["hm_raw"]).max()
+    hm = _sigmoid(out["hm"]).cpu().numpy()
+    err = np.abs(hm - g["hm"]).max()
+    perr = np.abs(out["proj"].cpu().numpy() - g["proj"]).max()
+    print(f"{name} TF32: raw hm max-abs err {err_raw:.3e}, hm err {err:.3e}, proj err {perr:.3e}")
+    assert err <= 1e-4 and perr <= 5e-3
+
+
+def test_tf32_mode_medium_vs_oracle_and_bf16():
+    from oracle import unet_oracle as uo
+    D, H, W = 10, 144, 208
+    sd = synth.unet_state_dict_torch(317, 4)
+    x = torch.from_numpy(synth.tomogram_np(D, H, W, 3))[None]
+    with torch.no_grad():
+        ref = uo.sigmoid_clamp(uo.forward(x, sd, want_proj=False)["hm"]).numpy()
+    m = build_model(4, 317)
+    m.compute_proj, m.fuse_sigmoid = False, True
+    e_bf16 = np.abs(m(x.cuda())[-1]["hm"].cpu().numpy() - ref).max()
+    m.precision = "tf32"
+    e_tf32 = np.abs(m(x.cuda())[-1]["hm"].cpu().numpy() - ref).max()
+    m.precision = "bf16"
+    again = np.abs(m(x.cuda())[-1]["hm"].cpu().numpy() - ref).max()
+    print(f"heat-map max-abs error vs fp32 oracle: bf16 {e_bf16:.3e}, tf32 {e_tf32:.3e}")
+    assert e_tf32 <= 1e-4 and e_bf16 <= HM_TOL and again == e_bf16
