@@ -60,6 +60,11 @@ SIGNATURES = {
     "cetpick_simsiam_finalize": (_int, [_vp]),
     "cetpick_simsiam_workspace_bytes": (_int, [_vp, _i64, _i64, _i64, _i64, C.POINTER(_sz)]),
     "cetpick_simsiam_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "cetpick_train_workspace_bytes": (_int, [C.POINTER(_sz)]),
+    "cetpick_pu_loss_f32": (_int, [_vp, _vp, _i64, _int, C.c_double, C.c_double, _vp, _vp, C.c_float, _vp, _sz, _vp]),
+    "cetpick_mse_loss_f32": (_int, [_vp, _vp, _i64, _vp, _vp, C.c_float, _vp, _sz, _vp]),
+    "cetpick_adam_step_f32": (_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     _i64, C.c_double, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_unet_profile_enable": (_int, [_vp, _int]),
     "cetpick_unet_profile_read": (_int, [_vp, _int, C.POINTER(_int), _vp, _vp, _vp]),

@@ -237,6 +237,28 @@ int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* plan, int64_t B, int6
 int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, int64_t D, int64_t H, int64_t W,
                             float* proj, float* pred, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Refinement training step, the pieces around the network (BASELINE.json configs[4]).  The forward /
+ * backward of the U-Net in training mode is not part of this library yet.
+ * ------------------------------------------------------------------------------------------ */
+int cetpick_train_workspace_bytes(size_t* bytes);
+/* cet_pick/models/loss.py:255-325 `PULoss(tau)(pred, gt)`, pred = `_sigmoid(logits)` (models/utils.py:167-169) when
+ * apply_sigmoid -- the training loss of trains/tomo_cr_semi_trainer.py:43-60 without `--contrastive`.  gt: 1 labelled
+ * positive, (-1,1) soft positive, -1 unlabelled.  out4 (device): loss, positive risk, negative risk, #positives (the
+ * reference raises when that is 0).  grad (device [n], nullable): grad_scale * d loss / d logits.  ws: 256-byte aligned,
+ * >= cetpick_train_workspace_bytes.  Reductions are two-stage with a fixed grid: reproducible. */
+int cetpick_pu_loss_f32(const float* logits, const float* gt, int64_t n, int apply_sigmoid, double tau, double beta,
+                        float* out4, float* grad, float grad_scale, void* ws, size_t ws_bytes, void* stream);
+/* loss.py:701-715 `ConsistencyLoss` = mse_loss(a, b); out1 (device); grad_a (nullable) = grad_scale * d loss / d a. */
+int cetpick_mse_loss_f32(const float* a, const float* b, int64_t n, float* out1, float* grad_a, float grad_scale,
+                         void* ws, size_t ws_bytes, void* stream);
+/* One torch.optim.Adam step (main.py:55: Adam(model.parameters(), lr), betas (0.9, 0.999), eps 1e-8) fused over a flat
+ * fp32 bucket of n parameters; step counts from 1; gradients are multiplied by grad_scale first (1 / world size after a
+ * summed all-reduce of the same bucket). */
+int cetpick_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                          double beta1, double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
+                          void* stream);
+
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */
 int64_t cetpick_last_launch_count(void);

@@ -169,3 +169,48 @@ def test_merge_topk_canonical_order():
     ix = torch.tensor([40, 7, 3, 99, 2, 11])
     s, i = merge_topk(sc, ix, 4)
     assert torch.equal(s, torch.tensor([0.9, 0.9, 0.5, 0.5])) and i.tolist() == [2, 7, 3, 11]
+
+
+# ---- training step: one flat-bucket all-reduce of the gradients ----
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    from cet_pick_b200.models.model import create_model
+    from cet_pick_b200.trains.step import FlatBucket, allreduce_gradients
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+        bucket = FlatBucket(m)
+        ok = bucket.numel == sum(p.numel() for p in m.parameters()) and bucket.numel * 4 < 8.1e6     # one 7.97 MB bucket
+        for i, p in enumerate(m.parameters()):
+            p.grad.fill_(float(rank + 1) * (i + 1))                # rank-dependent gradients, written through the views
+        scale = allreduce_gradients(bucket)
+        exp = sum(r + 1 for r in range(world)) / world
+        for i, p in enumerate(m.parameters()):
+            ok = ok and bool(torch.allclose(p.grad, torch.full_like(p.grad, exp * (i + 1))))
+        ok = ok and scale == 1.0
+        for i, p in enumerate(m.parameters()):
+            p.grad.fill_(float(rank + 1))
+        ok = ok and allreduce_gradients(bucket, average=False) == 1.0 / world and float(bucket.grads[0]) == sum(r + 1 for r in range(world))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_gradient_allreduce_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
