@@ -17,10 +17,11 @@
 // mbarrier.  No recompute in x, and the results are bit-identical to the two separate kernels.
 // y strips overlap by one conv1 row (two input rows) per side.
 //
-// Roles (512 threads, 1 CTA/SM, persistent over (image, row strip)):
-//   warp 0 TMA producer | warp 1 UMMA issuer (both convolutions) | warp 2 TMEM allocator |
-//   warp 3 relay (tells the neighbours when a ring row of this CTA is free again) |
-//   warps 4-7 conv1 epilogue (TMEM -> ring) | warps 8-15 conv2 epilogue (TMEM -> global, fused pool)
+// Roles (640 threads, 1 CTA/SM, persistent over (image, row strip)):
+//   warp 0 TMA producer | warp 1 UMMA issuer of conv1 | warp 3 UMMA issuer of conv2 (tcgen05.commit tracks the issuing
+//   thread's own UMMAs, so the two convolutions pipeline independently) | warp 2 TMEM allocator, then relay (tells the
+//   neighbours when a ring row of this CTA is free again) | warps 4-11 conv1 epilogue, two groups alternating rows
+//   (TMEM -> ring) | warps 12-19 conv2 epilogue, two groups (TMEM -> global, fused pool)
 #include "conv_block.cuh"
 #include "common.cuh"
 #include "conv_march.cuh"
@@ -34,7 +35,7 @@ namespace cetpick {
 
 namespace {
 
-constexpr int BLK_THREADS = 512;
+constexpr int BLK_THREADS = 640;
 constexpr int COUT = 32;
 constexpr int SP = 8, SLOTS = 6;            // physical / logical TMEM slots per convolution (phantom ring, conv_march.cu)
 constexpr int TMEM_C1 = 0, TMEM_C2 = SP * COUT;
@@ -87,6 +88,7 @@ __device__ __noinline__ void dbg_timeout(uint32_t tag, uint32_t a, uint32_t b) {
 
 template <bool CLUSTER>
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, uint32_t tag, uint32_t a = 0, uint32_t b = 0) {
+  if (!CLUSTER && ptx::mbar_try_wait(bar, parity)) return;      // the common case: no clock read, no loop
   const long long t0 = clock64();
   uint32_t ok, spins = 0;
   bool reported = false;
@@ -157,6 +159,13 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, const uint4& v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// asynchronous 16-byte store into another CTA's shared memory that reports its bytes to an mbarrier of THAT CTA
+// (tx-count): no fence and no release on the sending side, the receiving barrier completes when the bytes have landed
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, const uint4& v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(caddr),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cbar)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t caddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
@@ -197,11 +206,13 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&in_full[s], 1); ptx::mbar_init(&in_empty[s], 1); }
     for (int s = 0; s < SLOTS; ++s) {
-      ptx::mbar_init(&c1_full[s], 1); ptx::mbar_init(&c1_empty[s], 4);
-      ptx::mbar_init(&c2_full[s], 1); ptx::mbar_init(&c2_empty[s], 4);
+      // *_empty: the draining group AND the observing group arrive (8 warps): the issuer must not start a slot's next
+      // phase before both have seen the current one (a parity wait cannot tell phase n from phase n + 2)
+      ptx::mbar_init(&c1_full[s], 1); ptx::mbar_init(&c1_empty[s], 8);
+      ptx::mbar_init(&c2_full[s], 1); ptx::mbar_init(&c2_empty[s], 8);
     }
     for (int s = 0; s < p.RS; ++s) {
-      ptx::mbar_init(&ring_full[s], 4u + (has_left ? 1u : 0u) + (has_right ? 1u : 0u));
+      ptx::mbar_init(&ring_full[s], 4u);       // the four warps of the owning group; the neighbours' edge pixels arrive as tx bytes
       ptx::mbar_init(&ring_empty[s], 1);
       ptx::mbar_init(&nb_empty[0][s], 1);
       ptx::mbar_init(&nb_empty[1][s], 1);
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
   ptx::tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
 
-  if (warp >= 4 && warp < 12) {   // every accumulator slot starts at zero: all UMMAs accumulate
+  if ((warp >= 4 && warp < 8) || (warp >= 12 && warp < 16)) {   // every accumulator slot starts at zero: all UMMAs accumulate
     const uint32_t row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp < 8 ? TMEM_C1 : TMEM_C2);
     for (int c = 0; c < SP * COUT; c += 16) ptx::tmem_st16_fill(row + c, 0u);
     ptx::tmem_st_wait();
@@ -253,96 +264,102 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ================================ UMMA issuer =================================
+    // ================================ UMMA issuer, conv1 ===========================
     constexpr uint32_t A1_HI = ptx::smem_desc_hi(8 * G::PIX, G::LAYOUT), B1_HI = ptx::smem_desc_hi(8 * G::PIX, G::LAYOUT);
-    constexpr uint32_t A2_HI = ptx::smem_desc_hi(8 * 64, 4), B2_HI = ptx::smem_desc_hi(8 * 64, 4);
     constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
-    const uint32_t sW1_lo = ptx::smem_desc_lo(ptx::smem_u32(sW1)), sW2_lo = ptx::smem_desc_lo(ptx::smem_u32(sW2));
-    const uint32_t sA_lo = ptx::smem_desc_lo(ptx::smem_u32(sA)), sR_lo = ptx::smem_desc_lo(ptx::smem_u32(sRing));
+    const uint32_t sW1_lo = ptx::smem_desc_lo(ptx::smem_u32(sW1)), sA_lo = ptx::smem_desc_lo(ptx::smem_u32(sA));
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t umask1 = 0, umask2 = 0;    // per logical TMEM slot: parity of the number of rows that have used it
+    uint32_t umask1 = 0;                // per logical TMEM slot: parity of the number of rows that have used it
+    wait_t<false>(&bar_w, 0, 2);
+    for (long long k = kfirst; k < p.total_strips; k += kstep) {
+      Strip s;
+      decode_strip(p, k, s);
+      int r1_touched = s.c1a;
+      for (int i = s.i_lo; i <= s.i_hi; ++i) {
+        // input row i feeds conv1 rows i-1, i, i+1 (inside [c1a, c1b))
+        const int r_lo = max(s.c1a, i - 1), r_hi = min(s.c1b - 1, i + 1);
+        const int n = r_hi - r_lo + 1;
+        for (; r1_touched <= r_hi; ++r1_touched) {          // rows touched for the first time: slot must be drained
+          const uint32_t sl = (uint32_t)r1_touched % SLOTS;
+          wait_t<false>(&c1_empty[sl], ((umask1 >> sl) & 1u) ^ 1u, 3, (uint32_t)r1_touched, (uint32_t)i);
+          umask1 ^= 1u << sl;
+        }
+        const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
+        const uint32_t boff = (uint32_t)(r_lo - (i - 1)) * ((COUT * G::PIX) >> 4);
+        const uint32_t d = tmem_base + TMEM_C1 + ((uint32_t)(i + SLOTS - 1) % SLOTS + (uint32_t)(r_lo - (i - 1))) * COUT;
+        for (int src = 0; src < p.nsrc; ++src) {
+          wait_t<false>(&in_full[stage], phase, 4, (uint32_t)i, (uint32_t)stage);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = sA_lo + (uint32_t)(stage * (G::STAGE_BYTES >> 4));
+          const uint32_t w_lo = sW1_lo + (uint32_t)(src * 3 * (G::WBLK >> 4));
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int kk = 0; kk < G::K16; ++kk)
+                ptx::umma_bf16_lohi(d, a_lo + ((j * G::PIX + kk * 32) >> 4), A1_HI,
+                                    w_lo + boff + ((j * G::WBLK + kk * 32) >> 4), B1_HI, idesc);
+            ptx::umma_commit(&in_empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (ptx::elect_one()) {
+          if (i - 1 >= s.c1a) ptx::umma_commit(&c1_full[(uint32_t)(i - 1) % SLOTS]);
+          if (i == p.H - 1 && i < s.c1b) ptx::umma_commit(&c1_full[(uint32_t)i % SLOTS]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ UMMA issuer, conv2 ===========================
+    constexpr uint32_t A2_HI = ptx::smem_desc_hi(8 * 64, 4), B2_HI = ptx::smem_desc_hi(8 * 64, 4);
+    constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const uint32_t sW2_lo = ptx::smem_desc_lo(ptx::smem_u32(sW2)), sR_lo = ptx::smem_desc_lo(ptx::smem_u32(sRing));
+    uint32_t umask2 = 0;
     uint32_t rg_slot = 0, rg_par = 0;   // next ring row conv2 consumes
     wait_t<false>(&bar_w, 0, 2);
     for (long long k = kfirst; k < p.total_strips; k += kstep) {
       Strip s;
       decode_strip(p, k, s);
-      int r1_touched = s.c1a, r2_touched = s.ma;
-      for (int tck = s.i_lo; tck <= s.i_hi + p.lag; ++tck) {
-        if (tck <= s.i_hi) {
-          // ---- conv1: input row i feeds conv1 rows i-1, i, i+1 (inside [c1a, c1b))
-          const int i = tck;
-          const int r_lo = max(s.c1a, i - 1), r_hi = min(s.c1b - 1, i + 1);
-          const int n = r_hi - r_lo + 1;
-          for (; r1_touched <= r_hi; ++r1_touched) {          // rows touched for the first time: slot must be drained
-            const uint32_t sl = (uint32_t)r1_touched % SLOTS;
-            wait_t<false>(&c1_empty[sl], ((umask1 >> sl) & 1u) ^ 1u, 3, (uint32_t)r1_touched, (uint32_t)tck);
-            umask1 ^= 1u << sl;
-          }
-          const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
-          const uint32_t boff = (uint32_t)(r_lo - (i - 1)) * ((COUT * G::PIX) >> 4);
-          const uint32_t d = tmem_base + TMEM_C1 + ((uint32_t)(i + SLOTS - 1) % SLOTS + (uint32_t)(r_lo - (i - 1))) * COUT;
-          for (int src = 0; src < p.nsrc; ++src) {
-            wait_t<false>(&in_full[stage], phase, 4, (uint32_t)i, (uint32_t)stage);
-            ptx::tc_fence_after();
-            const uint32_t a_lo = sA_lo + (uint32_t)(stage * (G::STAGE_BYTES >> 4));
-            const uint32_t w_lo = sW1_lo + (uint32_t)(src * 3 * (G::WBLK >> 4));
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-#pragma unroll
-                for (int kk = 0; kk < G::K16; ++kk)
-                  ptx::umma_bf16_lohi(d, a_lo + ((j * G::PIX + kk * 32) >> 4), A1_HI,
-                                      w_lo + boff + ((j * G::WBLK + kk * 32) >> 4), B1_HI, idesc);
-              ptx::umma_commit(&in_empty[stage]);
-            }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-          }
-          if (ptx::elect_one()) {
-            if (i - 1 >= s.c1a) ptx::umma_commit(&c1_full[(uint32_t)(i - 1) % SLOTS]);
-            if (i == p.H - 1 && i < s.c1b) ptx::umma_commit(&c1_full[(uint32_t)i % SLOTS]);
-          }
-          __syncwarp();
+      int r2_touched = s.ma;
+      for (int j = s.c1a; j < s.c1b; ++j) {
+        // ring row j (= conv1 output row j) feeds conv2 rows j-1, j, j+1 (inside [ma, mb))
+        const int r_lo = max(s.ma, j - 1), r_hi = min(s.mb - 1, j + 1);
+        const int n = r_hi - r_lo + 1;
+        for (; r2_touched <= r_hi; ++r2_touched) {
+          const uint32_t sl = (uint32_t)r2_touched % SLOTS;
+          wait_t<false>(&c2_empty[sl], ((umask2 >> sl) & 1u) ^ 1u, 5, (uint32_t)r2_touched, (uint32_t)j);
+          umask2 ^= 1u << sl;
         }
-        const int j = tck - p.lag;
-        if (j >= s.c1a && j < s.c1b) {
-          // ---- conv2: ring row j (= conv1 output row j) feeds conv2 rows j-1, j, j+1 (inside [ma, mb))
-          const int r_lo = max(s.ma, j - 1), r_hi = min(s.mb - 1, j + 1);
-          const int n = r_hi - r_lo + 1;
-          for (; r2_touched <= r_hi; ++r2_touched) {
-            const uint32_t sl = (uint32_t)r2_touched % SLOTS;
-            wait_t<false>(&c2_empty[sl], ((umask2 >> sl) & 1u) ^ 1u, 5, (uint32_t)r2_touched, (uint32_t)tck);
-            umask2 ^= 1u << sl;
-          }
-          // The ring row lives in THIS SM's shared memory (a neighbour's edge pixel arrives through DSMEM before its
-          // release.cluster arrive is counted), so a CTA-scope wait plus a consumer-side proxy fence orders it before
-          // the UMMA reads; an acquire.cluster poll would invalidate L1 (CCTL.IVALL, ~500 cycles) on every try.
-          if (p.flags & 1) wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
-          else wait_t<false>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
-          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-          ptx::tc_fence_after();
-          const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
-          const uint32_t boff = (uint32_t)(r_lo - (j - 1)) * ((COUT * 64) >> 4);
-          const uint32_t d = tmem_base + TMEM_C2 + ((uint32_t)(j + SLOTS - 1) % SLOTS + (uint32_t)(r_lo - (j - 1))) * COUT;
-          const uint32_t a_lo = sR_lo + (uint32_t)(rg_slot * (RING_ROW >> 4));
-          if (ptx::elect_one()) {
+        // The ring row lives in THIS SM's shared memory (a neighbour's edge pixel arrives through DSMEM before its
+        // release.cluster arrive is counted), so a CTA-scope wait plus a consumer-side proxy fence orders it before
+        // the UMMA reads; an acquire.cluster poll would invalidate L1 (CCTL.IVALL, ~500 cycles) on every try.
+        if (p.flags & 1) wait_t<true>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+        else wait_t<false>(&ring_full[rg_slot], rg_par, 6, (uint32_t)j, rg_slot);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        ptx::tc_fence_after();
+        const uint32_t idesc = IDESC0 | ((uint32_t)(n * COUT >> 3) << 17);
+        const uint32_t boff = (uint32_t)(r_lo - (j - 1)) * ((COUT * 64) >> 4);
+        const uint32_t d = tmem_base + TMEM_C2 + ((uint32_t)(j + SLOTS - 1) % SLOTS + (uint32_t)(r_lo - (j - 1))) * COUT;
+        const uint32_t a_lo = sR_lo + (uint32_t)(rg_slot * (RING_ROW >> 4));
+        if (ptx::elect_one()) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t)
+          for (int t = 0; t < 3; ++t)
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-                ptx::umma_bf16_lohi(d, a_lo + ((t * 64 + kk * 32) >> 4), A2_HI,
-                                    sW2_lo + boff + ((t * W2BLK + kk * 32) >> 4), B2_HI, idesc);
-            ptx::umma_commit(&ring_empty[rg_slot]);
-            if (j - 1 >= s.ma) ptx::umma_commit(&c2_full[(uint32_t)(j - 1) % SLOTS]);
-            if (j == p.H - 1 && j < s.mb) ptx::umma_commit(&c2_full[(uint32_t)j % SLOTS]);
-          }
-          __syncwarp();
-          if (++rg_slot == (uint32_t)p.RS) { rg_slot = 0; rg_par ^= 1u; }
+            for (int kk = 0; kk < 2; ++kk)
+              ptx::umma_bf16_lohi(d, a_lo + ((t * 64 + kk * 32) >> 4), A2_HI,
+                                  sW2_lo + boff + ((t * W2BLK + kk * 32) >> 4), B2_HI, idesc);
+          ptx::umma_commit(&ring_empty[rg_slot]);
+          if (j - 1 >= s.ma) ptx::umma_commit(&c2_full[(uint32_t)(j - 1) % SLOTS]);
+          if (j == p.H - 1 && j < s.mb) ptx::umma_commit(&c2_full[(uint32_t)j % SLOTS]);
         }
+        __syncwarp();
+        if (++rg_slot == (uint32_t)p.RS) { rg_slot = 0; rg_par ^= 1u; }
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == 2) {
     // ================================ relay =======================================
     // a ring row of THIS CTA is free again once conv2 has consumed it: tell the neighbours, whose epilogue
     // threads store their edge pixel of a later row into it
@@ -364,9 +381,10 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ================================ conv1 epilogue: TMEM -> ring ==================
-    const int quad = warp & 3;
+    const int quad = warp & 3, g1 = (warp - 4) >> 2;       // two groups alternate rows: a row's drain -> convert -> ring
+                                                            // store -> arrive chain is longer than one row time
     const int m = quad * 32 + lane;
     const int x = x0 + m;
     const bool valid = x < p.W;
@@ -385,7 +403,10 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
       for (int r = s.c1a; r < s.c1b; ++r) {
         const uint32_t slot = (uint32_t)r % SLOTS, par = (emask >> slot) & 1u;
         emask ^= 1u << slot;
-        wait_t<false>(&c1_full[slot], par, 8, (uint32_t)r, slot);
+        const uint32_t my_rslot = rslot, my_rpar = rpar;     // ring slot of this row; both groups count every row
+        if (++rslot == (uint32_t)p.RS) { rslot = 0; rpar ^= 1u; }
+        wait_t<false>(&c1_full[slot], par, 8, (uint32_t)r, slot);      // every group observes every phase
+        if ((r & 1) != g1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&c1_empty[slot]); continue; }
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_C1 + (int)slot * COUT);
         uint32_t v[COUT];
@@ -421,28 +442,31 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
           w4[c] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
         // the ring row must have been consumed by conv2 (here, and in the neighbour the edge pixel goes to)
-        wait_t<false>(&ring_empty[rslot], rpar ^ 1u, 9, (uint32_t)r, rslot);
-        if (quad == 0 && has_left) wait_t<false>(&nb_empty[0][rslot], rpar ^ 1u, 10, (uint32_t)r, rslot);
-        if (quad == 3 && has_right) wait_t<false>(&nb_empty[1][rslot], rpar ^ 1u, 11, (uint32_t)r, rslot);
-        uint8_t* row = sRing + (size_t)rslot * RING_ROW;
+        wait_t<false>(&ring_empty[my_rslot], my_rpar ^ 1u, 9, (uint32_t)r, my_rslot);
+        if (quad == 0 && has_left) wait_t<false>(&nb_empty[0][my_rslot], my_rpar ^ 1u, 10, (uint32_t)r, my_rslot);
+        if (quad == 3 && has_right) wait_t<false>(&nb_empty[1][my_rslot], my_rpar ^ 1u, 11, (uint32_t)r, my_rslot);
+        uint8_t* row = sRing + (size_t)my_rslot * RING_ROW;
 #pragma unroll
         for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(row + sw(own_off + c * 16u)) = w4[c];
         if (edge_l || edge_r) {
-          const uint32_t rb = rem_base + rslot * (uint32_t)RING_ROW;
+          const uint32_t rb = rem_base + my_rslot * (uint32_t)RING_ROW;
           const uint32_t poff = edge_l ? 129u * 64u : 0u;    // swizzle is a function of the offset inside the (1024-aligned) row
 #pragma unroll
-          for (int c = 0; c < 4; ++c) st_cluster_v4(rb - poff + sw(poff + c * 16u), w4[c]);
-          mbar_arrive_remote(rem_full + rslot * 8u);      // release.cluster: the four stores above are visible first
+          for (int c = 0; c < 4; ++c) st_async_v4(rb - poff + sw(poff + c * 16u), w4[c], rem_full + my_rslot * 8u);
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ring_full[rslot]);
-        if (++rslot == (uint32_t)p.RS) { rslot = 0; rpar ^= 1u; }
+        if (lane == 0) {
+          // quad 0's arrive also announces the 64 bytes each neighbour's edge thread sends into this ring row
+          const uint32_t nb_bytes = (quad == 0) ? 64u * ((has_left ? 1u : 0u) + (has_right ? 1u : 0u)) : 0u;
+          if (nb_bytes) ptx::mbar_arrive_expect_tx(&ring_full[my_rslot], nb_bytes);
+          else ptx::mbar_arrive(&ring_full[my_rslot]);
+        }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ================================ conv2 epilogue: TMEM -> global (+ pool) =======
-    const int quad = warp & 3, eg = (warp - 8) >> 2;
+    const int quad = warp & 3, eg = (warp - 12) >> 2;
     const int m = quad * 32 + lane;
     const int x = x0 + m;
     const bool valid = x < p.W;
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) conv_block_kernel(const __grid
         // wait only tells the current phase from the one before it, and a group that skipped a phase could run two
         // phases ahead across a strip boundary and take the stale parity for "done".
         wait_t<false>(&c2_full[slot], par, 12, (uint32_t)r, slot);
-        if (pool ? (((r >> 1) & 1) != eg) : ((int)(q & 1u) != eg)) continue;
+        if (pool ? (((r >> 1) & 1) != eg) : ((int)(q & 1u) != eg)) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&c2_empty[slot]); continue; }
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(TMEM_C2 + (int)slot * COUT);
         uint32_t v[COUT];
@@ -547,8 +571,8 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
   p.nsrc = L.nsrc; p.NIMG = L.NIMG; p.H = L.H; p.W = L.W;
   p.NC = ceil_div(L.W, 128);
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
-  p.lag = std::min(MAX_LAG, std::max(2, env_int("CETPICK_BLOCK_LAG", 3)));
-  p.RS = std::min(MAX_RS, std::max(p.lag + 2, env_int("CETPICK_BLOCK_RS", p.lag + 3)));
+  p.lag = 0;
+  p.RS = std::min(MAX_RS, std::max(4, env_int("CETPICK_BLOCK_RS", 8)));        // ring rows between the two convolutions
   p.flags = env_int("CETPICK_BLOCK_FLAGS", 0);
   const int max_stages = std::min(MAX_STAGES, std::max(3, env_int("CETPICK_BLOCK_STAGES", MAX_STAGES)));
   static DeviceOnce attr_once;
@@ -589,7 +613,7 @@ int launch_block(const BlockLaunch& L, cudaStream_t stream) {
     const int nn = ceil_div(L.H, R);
     const long long strips = (long long)L.NIMG * nn;
     const double waves = (double)ceil_div<long long>(strips, max_clusters);
-    const double eff = ((double)strips / (waves * max_clusters)) * ((double)R / (R + 4 + p.lag));
+    const double eff = ((double)strips / (waves * max_clusters)) * ((double)R / (R + 6));
     if (eff > best_eff + 1e-9) { best_eff = eff; best_n = nn; best_R = R; }
   }
   p.nchunk = best_n; p.R = best_R;

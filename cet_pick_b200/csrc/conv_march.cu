@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&bar_full[s], 1); ptx::mbar_init(&bar_empty[s], 1); }
-    for (int s = 0; s < p.SL; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 4 * MT); }
+    // a slot is free again when BOTH epilogue groups are through with its row: MT = 2: each group drains its own M-tile;
+    // MT = 1: one group drains, the other only observes the phase -- and must arrive too, or the issuer could start the
+    // slot's next phase (and the one after) before the observer has looked, which a parity wait cannot tell apart
+    for (int s = 0; s < p.SL; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 8); }
     ptx::mbar_init(&bar_w, 1);
     ptx::fence_barrier_init();
   }
@@ -290,7 +293,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           // a parity wait only tells the current phase from the one before it, and a group that skipped a phase
           // could run two phases ahead across a strip boundary and take the stale parity for "done")
           ptx::mbar_wait(&bar_afull[slot], par);
-          if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) continue;
+          if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) {
+            if (MT == 1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar_aempty[slot]); }   // observed: see bar_aempty's init
+            continue;
+          }
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
           uint32_t v[COUT];

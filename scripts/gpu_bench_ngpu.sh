@@ -1,8 +1,12 @@
 #!/bin/bash
+# bench.py under torchrun on N GPUs of one box: scripts/gpu_bench_ngpu.sh <tag> <N> [steps] [warmup]
+TAG=${1:-rX}; N=${2:-2}; K=${3:-3}; W=${4:-2}
 mkdir -p gpurun_out
-N=${1:-8}
-nvidia-smi -L | wc -l
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 2 --warmup 3 > gpurun_out/r2b_bench_c2_${N}gpu.json 2> gpurun_out/r2b_bench_${N}gpu.err; echo rc=$?
-tail -3 gpurun_out/r2b_bench_${N}gpu.err | cut -c1-300
-cut -c1-330 gpurun_out/r2b_bench_c2_${N}gpu.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 scripts/check_zshard_nccl.py 2>&1 | grep "z-sharded"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps $K --warmup $W --no-cpu-baseline \
+  > gpurun_out/${TAG}_bench_c2_${N}gpu.json 2> gpurun_out/${TAG}_bench_${N}gpu.err
+echo "rc=$?"; python - <<PY
+import json
+j = json.loads(open("gpurun_out/${TAG}_bench_c2_${N}gpu.json").read().strip().splitlines()[-1])
+print({k: j[k] for k in ("n_gpus", "value", "value_w1", "ms_per_step")}, "e2e", j["e2e"]["value"], j["clocks"])
+PY
+tail -3 gpurun_out/${TAG}_bench_${N}gpu.err
