@@ -16,7 +16,7 @@ NMS_NONE, NMS_3D, NMS_FIBER, NMS_XY, NMS_Z = 0, 1, 2, 3, 4
 EPI_BF16_NHWC, EPI_UPCONV_2X2, EPI_F32_ROWMAJOR, EPI_F32_L2NORM_NCDHW = 0, 1, 2, 3
 MARCH_2D_ROWS, MARCH_3D_PLANES = 0, 1
 
-_i64, _int, _vp, _sz = C.c_int64, C.c_int, C.c_void_p, C.c_size_t
+_i64, _int, _vp, _sz, _ll = C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_longlong
 
 # every symbol include/cetpick.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -65,6 +65,19 @@ SIGNATURES = {
     "cetpick_mse_loss_f32": (_int, [_vp, _vp, _i64, _vp, _vp, C.c_float, _vp, _sz, _vp]),
     "cetpick_adam_step_f32": (_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                      _i64, C.c_double, _vp]),
+    "cetpick_train_conv_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "cetpick_train_flip_weights_f32": (_int, [_vp, _vp, _int, _int, _int, _vp]),
+    "cetpick_train_conv_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "cetpick_train_upconv_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cetpick_train_net_workspace_bytes": (_int, [_int, C.POINTER(_sz)]),
+    "cetpick_train_bn_f32": (_int, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, C.c_float,
+                                    C.c_float, _int, _vp, _sz, _vp]),
+    "cetpick_train_bn_bwd_f32": (_int, [_vp, _ll, _ll, _vp, _vp, _ll, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _int, _int,
+                                        _int, _int, _vp, _sz, _vp]),
+    "cetpick_train_channel_sum_f32": (_int, [_vp, _ll, _ll, _vp, _int, _int, _int, _int, _vp, _sz, _vp]),
+    "cetpick_train_pool_f32": (_int, [_vp, _ll, _ll, _vp, _ll, _ll, _int, _int, _int, _int, _vp]),
+    "cetpick_train_pool_bwd_f32": (_int, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _ll, _ll, _int, _int, _int, _int, _int, _vp]),
+    "cetpick_train_relu_bwd_f32": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "cetpick_last_launch_count": (_i64, []),
     "cetpick_unet_profile_enable": (_int, [_vp, _int]),
     "cetpick_unet_profile_read": (_int, [_vp, _int, C.POINTER(_int), _vp, _vp, _vp]),
@@ -85,6 +98,7 @@ TEST_SIGNATURES = {
     "cetpick_upconv_bf16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _int, _vp, _int, _int, _vp]),
     "cetpick_conv_halo_bf16": (_int, [_int, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _int, _int, _vp, _vp]),
     "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "cetpick_decode_set_stop_stage": (_int, [_int]),
     "cetpick_probe_mma_rate": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_probe_mma_rate2": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,

@@ -62,6 +62,9 @@ struct DecodeState {
   uint32_t hit_total;     // sieve: voxels >= threshold queued so far (reported in batches)
   uint32_t dense;         // sieve: hit density too high for the hit-by-hit path: bail out
   uint32_t need_dense;    // set by the sieve's last CTA: scan_kernel COLLECT (gate 2) takes over with the same t0
+  uint32_t csel_wl;       // csel_done == 3: log2 width of the composite class [csel_prefix, +2^wl) holding the K-th one
+  uint32_t tail_bar;      // tail_kernel: arrivals at its grid barrier
+  unsigned long long cmax; // tail_kernel: largest selected composite
   uint32_t n_sel;         // entries handed to the rank stage: K, or (fast final select) the M >= K candidates of the last histogram bin and above
 };
 
@@ -834,7 +837,7 @@ __device__ __noinline__ uint32_t sieve_okey(const float* __restrict__ heat, uint
 // recomputes the running threshold: stage the histogram, walk it from the top until K appended candidates
 // are covered, publish the lower edge of that bin.
 __device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K, uint32_t t0key, uint32_t* t_run,
-                              uint32_t* s_res /*[2]: delta of the bin edge, candidates at or above it (0 = fewer than K)*/) {
+                              uint32_t* s_res /*[4]: delta of the bin edge, candidates at or above it (0 = fewer than K), candidates in the bin, bin*/) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { s_res[0] = 0u; s_res[1] = 0u; }
   __syncthreads();
@@ -861,7 +864,7 @@ __device__ void sieve_publish(const uint32_t* rhist, uint32_t* s_rh, uint32_t K,
       // >= K appended survivors have delta >= lo: key > t0key + lo - 1 keeps all of them
       const uint32_t lo = refine_bin_lo((uint32_t)b);
       if (lo > 0) atomicMax(t_run, t0key + lo - 1u);
-      s_res[0] = lo; s_res[1] = cum;
+      s_res[0] = lo; s_res[1] = cum; s_res[2] = s_rh[b]; s_res[3] = (uint32_t)b;
     }
   }
   __syncthreads();
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
   __shared__ uint32_t s_q[SIEVE_THREADS / 32][SIEVE_QUEUE];
   __shared__ uint32_t s_rh[REFINE_BINS];
   __shared__ volatile uint32_t s_trun, s_dense;
-  __shared__ uint32_t s_ticket, s_res[2];
+  __shared__ uint32_t s_ticket, s_res[4];
   DecodeState* st = p.st;
   if (st->need_dense || st->need_fallback) return;   // the sample pass already handed COLLECT to scan_kernel
   const uint32_t t0key = st->t0key;
@@ -1057,111 +1060,27 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
         st->out_count = 0;
         st->n_final = min(st->cand_count, p.cap_total);
         st->csel_done = 2;
+      } else if (threadIdx.x == 0 && s_res[1] >= (uint32_t)p.K) {
+        // too many for the rank stage, but the bin holding the K-th key is known: the exact select starts inside it
+        const uint32_t b = s_res[3];
+        const uint32_t kbits = (b < 64u) ? 0u : ((b - 64u) >> 6);        // the bin spans 2^kbits keys (refine_bin_lo)
+        st->csel_prefix = (unsigned long long)(t0key + s_res[0]) << 32;
+        st->csel_wl = 32u + kbits;
+        st->csel_kleft = (uint32_t)p.K - (s_res[1] - s_res[2]);
+        st->csel_done = 3;
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final stage: exact K-th largest composite among the candidates, compaction, sort, write.
+// Final stage, ONE launch (tail_kernel): exact K-th largest composite among the candidates, compaction, ordering,
+// pick rows.  The stages that used to be nine launches (six digit histograms, compaction, rank, write) are phases of
+// one kernel whose CTAs are all resident (grid <= SM count) and meet at a counting barrier in the decode state.
 // ---------------------------------------------------------------------------------------------
-constexpr int CAND_THREADS = 256;
-
-__global__ void __launch_bounds__(CAND_THREADS) cand_hist_kernel(
-    const unsigned long long* __restrict__ cand, DecodeState* st, uint32_t* ghist, int shift,
-    int bits, int first, int last, uint32_t cap_total, int K) {
-  __shared__ uint32_t s_hist[HIST_BINS];
-  __shared__ uint32_t s_sel[3];
-  __shared__ uint32_t s_ticket;
-  if (st->csel_done == 2) return;          // fast final select (sieve_kernel): nothing to resolve
-  if (!first && st->csel_done) return;     // the key digits already fixed the K-th composite
-  const uint32_t n = min(st->cand_count, cap_total);
-  const int hs = shift + bits;
-  const unsigned long long prefix = first ? 0ull : st->csel_prefix;
-  const uint32_t dmask = (1u << bits) - 1u;
-  for (int i = threadIdx.x; i < HIST_BINS; i += CAND_THREADS) s_hist[i] = 0;
-  __syncthreads();
-  for (uint32_t i0 = blockIdx.x * CAND_THREADS; i0 < n; i0 += gridDim.x * CAND_THREADS) {   // CTA-uniform trip count
-    const uint32_t i = i0 + threadIdx.x;
-    const unsigned long long c = (i < n) ? cand[i] : 0ull;
-    // candidates sit just above the threshold, so whole warps fall into one bin of the upper digits:
-    // one shared-memory atomic per group of equal bins instead of a 32-way serialised one
-    const bool in = (i < n) && (first || (c >> hs) == prefix);
-    const uint32_t bin = in ? ((uint32_t)(c >> shift) & dmask) : (0x80000000u | (threadIdx.x & 31));
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < (1 << bits); i += CAND_THREADS)
-    if (s_hist[i]) atomicAdd(&ghist[i], s_hist[i]);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->done_ctr, 1u);
-  __syncthreads();
-  if (s_ticket != gridDim.x - 1) return;
-  __threadfence();
-  const uint32_t kleft = first ? (uint32_t)K : st->csel_kleft;
-  select_digit(ghist, 1 << bits, kleft, s_hist, s_sel);
-  if (threadIdx.x == 0) {
-    const unsigned long long np = (prefix << bits) | (unsigned long long)s_sel[0];
-    st->csel_prefix = np;
-    st->csel_kleft = s_sel[1];
-    if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
-    if (first) { st->n_final = n; st->n_sel = (uint32_t)K; }
-    if (last) { st->kth_comp = np; st->out_count = 0; }
-    if (shift == 32 && s_sel[1] == s_sel[2]) {
-      // every candidate with the K-th key is needed (the usual case: no ties): skip the index digits
-      st->kth_comp = np << 32;
-      st->out_count = 0;
-      st->csel_done = 1;
-    }
-    st->done_ctr = 0;
-  }
-}
-
-__global__ void __launch_bounds__(CAND_THREADS) cand_compact_kernel(
-    const unsigned long long* __restrict__ cand, DecodeState* st, unsigned long long* out,
-    uint32_t cap_total, int K) {
-  const uint32_t n = min(st->cand_count, cap_total);
-  const unsigned long long kth = st->kth_comp;
-  const uint32_t cap_out = st->n_sel;      // K, or M >= K in the fast mode
-  (void)K;
-  for (uint32_t i = blockIdx.x * CAND_THREADS + threadIdx.x; i < n; i += gridDim.x * CAND_THREADS) {
-    const unsigned long long c = cand[i];
-    if (c >= kth) {
-      const uint32_t o = atomicAdd(&st->out_count, 1u);
-      if (o < cap_out) out[o] = c;
-    }
-  }
-}
-
-// K <= RANK_MAX_K: the K composites are distinct, so rank = #{composites greater than mine} is the
-// output row.  rank_kernel counts against one slice of the list per blockIdx.y (slice in shared
-// memory, broadcast reads); rank_write_kernel writes the picks.  O(K^2 / PARTS) per thread, all SMs
-// busy: ~20 us at K = 10 000 where a one-CTA bitonic sort needs ~260 us.
-constexpr int RANK_PARTS = 16, RANK_THREADS = 128;
-
-__global__ void __launch_bounds__(RANK_THREADS) rank_kernel(const unsigned long long* __restrict__ keys,
-                                                            const DecodeState* __restrict__ st,
-                                                            uint32_t* __restrict__ ranks) {
-  __shared__ unsigned long long s_k[RANK_MAX_K / RANK_PARTS];
-  const int K = (int)st->n_sel;            // entries to order (the grid is sized for RANK_MAX_K)
-  const int per = ceil_div(K, RANK_PARTS);
-  const int j0 = blockIdx.y * per, j1 = min(K, j0 + per);
-  for (int j = j0 + threadIdx.x; j < j1; j += RANK_THREADS) s_k[j - j0] = keys[j];
-  __syncthreads();
-  const int r = blockIdx.x * RANK_THREADS + threadIdx.x;
-  if (r >= K) return;
-  const unsigned long long c = keys[r];
-  uint32_t cnt = 0;
-  const int n = j1 - j0;
-  int j = 0;
-  for (; j + 4 <= n; j += 4) {
-    cnt += (s_k[j] > c) + (s_k[j + 1] > c) + (s_k[j + 2] > c) + (s_k[j + 3] > c);
-  }
-  for (; j < n; ++j) cnt += (s_k[j] > c);
-  if (cnt) atomicAdd(&ranks[r], cnt);
-}
+constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_DIGITS = 6;
+constexpr int RANK_BINS = 4096;        // buckets of the ordering phase (linear in the composite)
 
 __device__ __forceinline__ void write_pick(unsigned long long c, int r, const float* __restrict__ heat,
                                            const float* __restrict__ reg, size_t n_vox, int hw, int W,
@@ -1186,17 +1105,210 @@ __device__ __forceinline__ void write_pick(unsigned long long c, int r, const fl
   if (inds) inds[r] = (long long)idx;
 }
 
-__global__ void __launch_bounds__(256) rank_write_kernel(const unsigned long long* __restrict__ keys, int K,
-                                                         const DecodeState* __restrict__ st,
-                                                         uint32_t* __restrict__ ranks,
-                                                         const float* __restrict__ heat,
-                                                         const float* __restrict__ reg, int D, int H, int W,
-                                                         float* __restrict__ dets, long long* __restrict__ inds) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= (int)st->n_sel) return;
-  const uint32_t r = ranks[i];
-  ranks[i] = 0;                                               // ready for the next decode
-  if (r < (uint32_t)K) write_pick(keys[i], (int)r, heat, reg, (size_t)D * H * W, H * W, W, dets, inds);
+// all CTAs of the grid (co-resident) have arrived `phase` times
+__device__ __forceinline__ void tail_grid_sync(uint32_t* ctr, uint32_t& phase) {
+  ++phase;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const uint32_t target = phase * gridDim.x;
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// monotone map of a composite onto RANK_BINS buckets (any monotone map keeps the ordering exact)
+__device__ __forceinline__ int rank_bin(unsigned long long c, unsigned long long cmin, float scale) {
+  const float f = __ull2float_rz(c - cmin) * scale;
+  return min(RANK_BINS - 1, (int)f);
+}
+
+// Phases (every CTA takes the same branches: all decisions come from state written before a barrier):
+//   1. unless the sieve already fixed the selection (fast final select, csel_done == 2): radix select of the K-th
+//      largest composite, 11 bits a pass, starting from the bin the sieve's histogram put the K-th key in when it has
+//      one (csel_done == 3); each pass = per-CTA shared histogram -> global bins -> barrier -> every CTA walks the bins;
+//   2. compaction of the composites >= the K-th one (n_sel = K of them, or the M >= K of the fast mode) and their maximum;
+//   3. do_rank (K <= RANK_MAX_K): ordering by counting.  Every CTA buckets the n_sel composites into shared memory
+//      (RANK_BINS monotone buckets, descending), then ranks its share of the list: rank = elements in higher
+//      buckets + bucket peers that are greater (one warp per element, 32 lanes over the peers: a bucket swollen by
+//      tied scores is still shared out over the whole grid), and writes the pick row (rank < K).
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long long* __restrict__ cand, DecodeState* st,
+                                                            uint32_t* thist /*[TAIL_DIGITS][HIST_BINS], zeroed*/,
+                                                            unsigned long long* out, uint32_t cap_total, int K, int do_rank,
+                                                            const float* __restrict__ heat, const float* __restrict__ reg,
+                                                            int D, int H, int W, float* __restrict__ dets,
+                                                            long long* __restrict__ inds) {
+  extern __shared__ __align__(16) unsigned char tail_smem[];
+  __shared__ uint32_t s_hist[HIST_BINS];
+  __shared__ uint32_t s_sel[3];
+  __shared__ unsigned long long s_max;
+  uint32_t phase = 0;
+  const uint32_t n = min(st->cand_count, cap_total);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long kth;
+  uint32_t n_sel;
+  if (st->csel_done == 2) {                 // fast final select: every composite with key >= the bin edge
+    kth = st->kth_comp;
+    n_sel = st->n_sel;
+  } else {
+    // Radix select over a shrinking class [base, base + 2^wl) of composites, 11 bits a pass (at most 6).  Start: the
+    // whole 64-bit range, or -- when the sieve's last histogram located the K-th key (csel_done == 3) -- that bin:
+    // base = its lowest key, wl = 32 index bits + the bin's key bits, kleft = K minus the candidates in higher bins.
+    // A pass ends the search early when EVERY element of the chosen digit is needed: the K-th composite is then the
+    // digit's lower edge (tie-free scores: after the first pass that resolves single key values).
+    unsigned long long base = 0ull;
+    int wl = 64;
+    uint32_t kleft = (uint32_t)K;
+    if (st->csel_done == 3) { base = st->csel_prefix; wl = (int)st->csel_wl; kleft = st->csel_kleft; }
+    kth = 0ull;
+    for (int d = 0; d < TAIL_DIGITS; ++d) {
+      const int bits = min(11, wl), shift = wl - bits;
+      uint32_t* gh = thist + d * HIST_BINS;
+      for (int i = threadIdx.x; i < HIST_BINS; i += TAIL_THREADS) s_hist[i] = 0;
+      __syncthreads();
+      for (uint32_t i0 = blockIdx.x * TAIL_THREADS; i0 < n; i0 += gridDim.x * TAIL_THREADS) {   // CTA-uniform trip count
+        const uint32_t i = i0 + threadIdx.x;
+        const unsigned long long c = (i < n) ? cand[i] : 0ull;
+        const unsigned long long off = c - base;
+        // candidates sit just above the threshold, so whole warps fall into one bin of the upper digits:
+        // one shared-memory atomic per group of equal bins instead of a 32-way serialised one
+        const bool in = (i < n) && (c >= base) && (wl == 64 || (off >> wl) == 0ull);
+        const uint32_t bin = in ? (uint32_t)(off >> shift) : (0x80000000u | (uint32_t)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < (1 << bits); i += TAIL_THREADS)
+        if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
+      tail_grid_sync(&st->tail_bar, phase);
+      // every CTA resolves the digit itself (same bins, same answer): no second barrier
+      for (int i = threadIdx.x; i < HIST_BINS; i += TAIL_THREADS) s_hist[i] = (i < (1 << bits)) ? __ldcg(&gh[i]) : 0u;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const int nb = max(32, 1 << bits), per = nb / 32;      // (bins beyond 2^bits are zero)
+        uint32_t sum = 0;
+        for (int i = 0; i < per; ++i) sum += s_hist[nb - 1 - lane * per - i];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - sum;
+        const bool mine = (excl < kleft) && (incl >= kleft);
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        if (who == 0) {                       // fewer than kleft elements in the class (cannot happen: K <= candidates)
+          if (lane == 0) { s_sel[0] = 0; s_sel[1] = 0xffffffffu; s_sel[2] = 0; }
+        } else if (lane == __ffs(who) - 1) {
+          uint32_t cum = excl;
+          int b = nb - 1 - lane * per;
+          for (int i = 0; i < per; ++i, --b) {
+            const uint32_t h = s_hist[b];
+            if (cum + h >= kleft) break;
+            cum += h;
+          }
+          s_sel[0] = (uint32_t)b; s_sel[1] = kleft - cum; s_sel[2] = s_hist[b];
+        }
+      }
+      __syncthreads();
+      base += (unsigned long long)s_sel[0] << shift;
+      wl = shift;
+      kleft = s_sel[1];
+      const uint32_t in_bin = s_sel[2];
+      __syncthreads();
+      if (kleft == 0xffffffffu) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
+        kleft = in_bin;
+      }
+      kth = base;
+      if (kleft == in_bin || wl == 0) break;   // the whole digit is needed / the composite is resolved to the last bit
+    }
+    n_sel = (uint32_t)K;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_final = n; st->n_sel = n_sel; st->kth_comp = kth; }
+  }
+
+  // ---- compaction (order irrelevant: the ordering phase ranks by value) and the maximum
+  {
+    unsigned long long mx = 0ull;
+    for (uint32_t i0 = blockIdx.x * TAIL_THREADS; i0 < n; i0 += gridDim.x * TAIL_THREADS) {
+      const uint32_t i = i0 + threadIdx.x;
+      const unsigned long long c = (i < n) ? cand[i] : 0ull;
+      const bool take = (i < n) && (c >= kth);
+      const unsigned tb = __ballot_sync(0xffffffffu, take);
+      if (tb) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&st->out_count, (uint32_t)__popc(tb));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t o = base + __popc(tb & ((1u << lane) - 1u));
+        if (take && o < n_sel) out[o] = c;
+        if (take) mx = max(mx, c);
+      }
+    }
+    if (do_rank) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0 && mx) atomicMax(&st->cmax, mx);
+    }
+  }
+  if (!do_rank) return;                       // K > RANK_MAX_K: sort_write_kernel orders the K composites
+  tail_grid_sync(&st->tail_bar, phase);
+
+  // ---- ordering by counting
+  unsigned long long* s_sorted = reinterpret_cast<unsigned long long*>(tail_smem);            // [RANK_MAX_K]
+  uint32_t* s_above = reinterpret_cast<uint32_t*>(tail_smem + (size_t)RANK_MAX_K * 8);          // [RANK_BINS]
+  uint32_t* s_fill = s_above + RANK_BINS;                                                       // [RANK_BINS]
+  const uint32_t m = min(__ldcg(&st->out_count), n_sel);       // == n_sel unless the internal-error flag is up
+  const unsigned long long cmax = __ldcg(&st->cmax);
+  const float scale = (float)RANK_BINS / (__ull2float_ru(cmax - kth) + 1.0f);
+  for (int i = threadIdx.x; i < RANK_BINS; i += TAIL_THREADS) { s_above[i] = 0; s_fill[i] = 0; }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < m; i += TAIL_THREADS) atomicAdd(&s_above[rank_bin(__ldcg(&out[i]), kth, scale)], 1u);
+  __syncthreads();
+  if (warp == 0) {                            // s_above[b] <- number of elements in buckets above b
+    constexpr int PER = RANK_BINS / 32;
+    uint32_t sum = 0;
+    for (int i = 0; i < PER; ++i) sum += s_above[RANK_BINS - 1 - lane * PER - i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t run = incl - sum;
+    for (int i = 0; i < PER; ++i) {
+      const int b = RANK_BINS - 1 - lane * PER - i;
+      const uint32_t h = s_above[b];
+      s_above[b] = run;
+      run += h;
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < m; i += TAIL_THREADS) {
+    const unsigned long long c = __ldcg(&out[i]);
+    const int b = rank_bin(c, kth, scale);
+    s_sorted[s_above[b] + atomicAdd(&s_fill[b], 1u)] = c;
+  }
+  __syncthreads();
+  const uint32_t per_cta = ceil_div<uint32_t>(m, gridDim.x);
+  const uint32_t p0 = blockIdx.x * per_cta, p1 = min(m, p0 + per_cta);
+  const size_t n_vox = (size_t)D * H * W;
+  // (shares are taken from the compacted list, which is the same for every CTA; the order INSIDE a bucket of
+  // s_sorted is not -- each CTA scattered it with its own atomics)
+  for (uint32_t e = p0 + warp; e < p1; e += TAIL_THREADS / 32) {
+    const unsigned long long c = __ldcg(&out[e]);
+    const int b = rank_bin(c, kth, scale);
+    const uint32_t lo = s_above[b], cnt = s_fill[b];
+    uint32_t g = 0;
+    for (uint32_t j = lane; j < cnt; j += 32) g += (s_sorted[lo + j] > c) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    const uint32_t r = lo + g;
+    if (lane == 0 && r < (uint32_t)K) write_pick(c, (int)r, heat, reg, n_vox, H * W, W, dets, inds);
+  }
 }
 
 // One CTA: bitonic sort (descending) of K composites, then the pick writer
@@ -1231,7 +1343,7 @@ __global__ void __launch_bounds__(1024) sort_write_kernel(
 }
 
 __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqcnt, int D,
-                                  uint32_t t0key, uint32_t* ranks, int n_ranks, uint32_t* rhist) {
+                                  uint32_t t0key, uint32_t* thist, int n_thist, uint32_t* rhist) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     DecodeState z = {};
@@ -1241,7 +1353,7 @@ __global__ void init_state_kernel(DecodeState* st, uint32_t* hist, uint32_t* eqc
   }
   if (i < HIST_BINS) hist[i] = 0;
   for (int k = i; k < D; k += gridDim.x * blockDim.x) eqcnt[k] = 0;
-  for (int k = i; k < n_ranks; k += gridDim.x * blockDim.x) ranks[k] = 0;
+  for (int k = i; k < n_thist; k += gridDim.x * blockDim.x) thist[k] = 0;
   for (int k = i; k < REFINE_BINS; k += gridDim.x * blockDim.x) rhist[k] = 0;
 }
 
@@ -1287,7 +1399,7 @@ __global__ void sigmoid_clamp_kernel(float* __restrict__ x, size_t n) {
 }
 
 struct WsLayout {
-  size_t off_state, off_hist, off_eq, off_rhist, off_cand, off_out, off_rank, total;
+  size_t off_state, off_hist, off_eq, off_rhist, off_cand, off_out, off_thist, total;
   uint32_t cap_gt, cap_total;
   int npad;
 };
@@ -1312,7 +1424,7 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   L.off_rhist = o; o = align_up(o + (size_t)REFINE_BINS * sizeof(uint32_t), 256);
   L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
   L.off_out = o;   o = align_up(o + (size_t)std::max(npad, RANK_MAX_K) * 8, 256);
-  L.off_rank = o;  o = align_up(o + (size_t)RANK_MAX_K * 4, 256);
+  L.off_thist = o; o = align_up(o + (size_t)TAIL_DIGITS * HIST_BINS * sizeof(uint32_t), 256);
   L.total = o;
   return L;
 }
@@ -1375,6 +1487,13 @@ int scan_grid(int D, int H, int W, int zlo, int zhi, int* ZC_out) {
 
 }  // namespace
 
+#ifdef CETPICK_TEST_HOOKS
+int g_stop_stage = 0;   // stage timing (scripts/decode_stages.py): return after stage n of decode_one
+#define CETPICK_STAGE(n) do { if (g_stop_stage == (n)) return CETPICK_OK; } while (0)
+#else
+#define CETPICK_STAGE(n) do { } while (0)
+#endif
+
 int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int nms_mode,
                const float* reg, float* dets, long long* inds, void* ws, cudaStream_t s) {
   const WsLayout L = ws_layout(D, H, W, K);
@@ -1388,11 +1507,11 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   const int P = (nms_mode == CETPICK_NMS_NONE) ? 0 : (kernel_xy - 1) / 2;
   const bool collect_all = (n <= L.cap_gt);
 
-  uint32_t* ranks = reinterpret_cast<uint32_t*>(base + L.off_rank);
-  const int n_ranks = RANK_MAX_K;
+  uint32_t* thist = reinterpret_cast<uint32_t*>(base + L.off_thist);
   uint32_t* rhist = reinterpret_cast<uint32_t*>(base + L.off_rhist);
-  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, ranks, n_ranks, rhist);
+  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, thist, TAIL_DIGITS * HIST_BINS, rhist);
   CETPICK_LAUNCH_CHECK();
+  CETPICK_STAGE(1);
 
   ScanParams p = {};
   p.heat = heat; p.D = D; p.H = H; p.W = W;
@@ -1454,7 +1573,9 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     const int zlo = (D - sp) / 2, zhi = zlo + sp;
     p.sample_ratio = (uint32_t)std::max<uint64_t>(1, n / ((uint64_t)sp * hw));
     if ((rc = run_select(zlo, zhi, 0, 2))) return rc;
+    CETPICK_STAGE(2);
     if ((rc = run_collect(0, 0, 0))) return rc;
+    CETPICK_STAGE(3);
     if (p.vec_ok && (rc = run_collect(2, 0, 0))) return rc;   // taken only if the sieve found the hits dense
     // exact fallback (device-gated): full-volume select, then COLLECT again
     if ((rc = run_select(0, D, 1, 3))) return rc;
@@ -1466,28 +1587,23 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     const int grid = scan_grid(D, H, W, 0, D, &q.ZC);
     if ((rc = launch_scan_p(P, q, grid, s))) return rc;
   }
-  {  // exact K-th composite: digits 11,11,10 over the key and 11,11,10 over ~index
-    const int cs[6] = {53, 42, 32, 21, 10, 0}, cb[6] = {11, 11, 10, 11, 11, 10};
-    const int grid = std::min<int>(num_sms() * 2, std::max<uint32_t>(1, ceil_div<uint32_t>(L.cap_total, CAND_THREADS * 8)));
-    for (int i = 0; i < 6; ++i) {
-      CETPICK_CUDA(launch_k(cand_hist_kernel, dim3(grid), dim3(CAND_THREADS), 0, s, cand, st, hist, cs[i], cb[i],
-                              (int)(i == 0), (int)(i == 5), L.cap_total, K));
-      CETPICK_LAUNCH_CHECK();
+  CETPICK_STAGE(4);
+  {  // exact K-th composite, compaction and (K <= RANK_MAX_K) ordering + pick rows: one launch
+    const int do_rank = K <= RANK_MAX_K;
+    const size_t smem = do_rank ? (size_t)RANK_MAX_K * 8 + 2 * (size_t)RANK_BINS * 4 : 0;
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
+      CETPICK_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        RANK_MAX_K * 8 + 2 * RANK_BINS * 4));
     }
-    CETPICK_CUDA(launch_k(cand_compact_kernel, dim3(grid), dim3(CAND_THREADS), 0, s, cand, st, outb, L.cap_total, K));
+    // all CTAs must be resident at once (they meet at a barrier): at most one per SM
+    const int grid = std::min<int>(num_sms(), std::max<uint32_t>(1, ceil_div<uint32_t>(L.cap_total, TAIL_THREADS * 4)));
+    CETPICK_CUDA(launch_k(tail_kernel, dim3(grid), dim3(TAIL_THREADS), smem, s, (const unsigned long long*)cand, st, thist, outb,
+                            L.cap_total, K, do_rank, heat, reg, D, H, W, dets, inds));
     CETPICK_LAUNCH_CHECK();
   }
-  if (K <= RANK_MAX_K) {
-    // grids sized for the fast mode's upper bound (M <= RANK_MAX_K); surplus CTAs exit at once
-    const bool vec_fast = p.vec_ok && !collect_all;     // sieve_kernel ran: it may have chosen the fast final select
-    const int nsel_max = vec_fast ? RANK_MAX_K : K;
-    CETPICK_CUDA(launch_k(rank_kernel, dim3(ceil_div(nsel_max, RANK_THREADS), RANK_PARTS), dim3(RANK_THREADS), 0, s, outb,
-                            (const DecodeState*)st, ranks));
-    CETPICK_LAUNCH_CHECK();
-    CETPICK_CUDA(launch_k(rank_write_kernel, dim3(ceil_div(nsel_max, 256)), dim3(256), 0, s, outb, K,
-                            (const DecodeState*)st, ranks, heat, reg, D, H, W, dets, inds));
-    CETPICK_LAUNCH_CHECK();
-  } else {
+  CETPICK_STAGE(5);
+  if (K > RANK_MAX_K) {
     const int use_smem = L.npad <= SORT_SMEM_MAX;
     const size_t smem = use_smem ? (size_t)L.npad * 8 : 0;
     static DeviceOnce attr_once;
@@ -1537,6 +1653,10 @@ extern "C" int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64
   }
   return CETPICK_OK;
 }
+
+#ifdef CETPICK_TEST_HOOKS
+extern "C" int cetpick_decode_set_stop_stage(int n) { g_stop_stage = n; return CETPICK_OK; }
+#endif
 
 extern "C" int cetpick_decode_status(const void* ws, void* stream, int* flags, int64_t* n_candidates) {
   if (!ws) return CETPICK_ERR_BAD_ARG;

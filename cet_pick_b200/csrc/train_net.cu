@@ -1,0 +1,563 @@
+// Training-mode layers of the detector (BASELINE.json configs[4]): fp32 forward with batch-statistics
+// BatchNorm and the backward of every layer kind the network has -- what `loss.backward()` of
+// cet_pick/trains/base_trainer.py:135-155,484-489 runs through for cet_pick/models/networks/unet_small.py:63-97 and
+// unet.py:198-249 (DownConv), :319-399 (UpConv), :861-886 (UNet.forward).
+//
+//   conv (2-D trunk 3x3 / 1x1 / stem 7x7 stride 2, 3-D head 3x3x3 dilated (1,4,4) and 3x1x1)   conv_f32_kernel
+//   data gradient of a stride-1 conv = the same kernel on flipped, transposed weights          flip_weights_kernel
+//   weight gradient (all of the above and the transposed conv)                                 wgrad_f32_kernel
+//   ConvTranspose2d(k=2, s=2) forward; its data gradient is a stride-2 2x2 conv                upconv_f32_kernel
+//   BatchNorm2d (batch statistics, running-stat update) [+ ReLU] forward / backward            bn_*_kernel
+//   MaxPool2d(2, ceil_mode) forward / backward (first maximum wins, like ATen)                 pool_*_kernel
+//   ReLU backward, per-channel sums (bias gradients)
+//
+// Tensors are fp32 with DENSE rows and explicit (slice, channel) strides, so one buffer serves the 2-D trunk
+// ((D,C,h,w): slice = z) and the 3-D head ((C,D,h,w) read through the same strides): the reference's permutes
+// (unet_small.py:71,83-84) and the channel concat (unet.py:390) are views here, not copies.
+// This is the FIRST correct training path: CUDA-core fp32, gradients within 1e-3 of torch autograd.  The tensor-core
+// kernels of the inference path are not used here.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace cetpick {
+namespace {
+
+using Geom = cetpick_conv_geom;
+
+constexpr int CV_THREADS = 128;
+constexpr int CV_CO = 16;      // output channels per thread
+constexpr int CV_CI = 8;       // input channels per weight stage
+
+// y[n][co][oy][ox] (+)= bias[co] + sum_{ci,tz,ty,tx} x[n + tz*dz - pz][ci][oy*s + ty*dy - py][ox*s + tx*dx - px] * w[co][ci][tz][ty][tx]
+// (z taps stay inside the crop of `zdepth` slices that n belongs to)
+__global__ void __launch_bounds__(CV_THREADS) conv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ y,
+                                                              const Geom g, const int flags) {
+  extern __shared__ float s_w[];                       // [CV_CI][taps][CV_CO]
+  const bool accumulate = flags & 1, relu = flags & 2;
+  const int taps = g.kz * g.ky * g.kx;
+  const int p = blockIdx.x * CV_THREADS + threadIdx.x;
+  const int n = blockIdx.y, co0 = blockIdx.z * CV_CO;
+  const bool valid = p < g.Ho * g.Wo;
+  const int oy = valid ? p / g.Wo : 0, ox = valid ? p - oy * g.Wo : 0;
+  const int crop0 = (n / g.zdepth) * g.zdepth;
+  float acc[CV_CO];
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) acc[c] = 0.f;
+  for (int ci0 = 0; ci0 < g.Cin; ci0 += CV_CI) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CV_CI * taps * CV_CO; i += CV_THREADS) {
+      const int co = i % CV_CO, t = (i / CV_CO) % taps, ci = i / (CV_CO * taps);
+      float v = 0.f;
+      if (ci0 + ci < g.Cin && co0 + co < g.Cout) v = w[((size_t)(co0 + co) * g.Cin + ci0 + ci) * taps + t];
+      s_w[i] = v;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    const int nci = min(CV_CI, g.Cin - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+      const float* xc = x + (size_t)(ci0 + ci) * g.xs_c;
+      const float* wc = s_w + (size_t)ci * taps * CV_CO;
+      for (int tz = 0; tz < g.kz; ++tz) {
+        const int zin = n + tz * g.dz - g.pz;
+        if (zin < crop0 || zin >= crop0 + g.zdepth) continue;
+        for (int ty = 0; ty < g.ky; ++ty) {
+          const int iy = oy * g.stride + ty * g.dy - g.py;
+          if (iy < 0 || iy >= g.H) continue;
+          const float* xr = xc + (size_t)zin * g.xs_n + (size_t)iy * g.W;
+          const float* wr = wc + (size_t)((tz * g.ky + ty) * g.kx) * CV_CO;
+          for (int tx = 0; tx < g.kx; ++tx) {
+            const int ix = ox * g.stride + tx * g.dx - g.px;
+            if (ix < 0 || ix >= g.W) continue;
+            const float v = __ldg(xr + ix);
+            const float4* w4 = reinterpret_cast<const float4*>(wr + tx * CV_CO);
+#pragma unroll
+            for (int q = 0; q < CV_CO / 4; ++q) {
+              const float4 ww = w4[q];
+              acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
+              acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+              acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) {
+    if (co0 + c >= g.Cout) break;
+    float* o = y + (size_t)n * g.ys_n + (size_t)(co0 + c) * g.ys_c + p;
+    float v = acc[c] + (bias ? bias[co0 + c] : 0.f);
+    if (accumulate) v += *o;
+    *o = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+// wt[ci][co][taps-1-t] = w[co][ci][t]: the weights with which a stride-1 conv of dy gives dx
+__global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int taps) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps), ci = (int)((i / taps) % Cin), co = (int)(i / ((size_t)taps * Cin));
+    wt[((size_t)ci * Cout + co) * taps + (taps - 1 - t)] = w[i];
+  }
+}
+
+// dw[co][ci][t] += sum_{n,oy,ox} dy[n][co][oy][ox] * x[n + tz*dz - pz][ci][oy*s + ty*dy - py][ox*s + tx*dx - px]
+// One CTA: one co, CI_T input channels, all taps in registers, a chunk of the (n, pixel) range; CTA reduction, atomics.
+constexpr int WG_THREADS = 256;
+template <int KZ, int KY, int KX, int CI_T>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, const Geom g, const long long chunk) {
+  constexpr int TAPS = KZ * KY * KX;
+  const int ncig = ceil_div(g.Cin, CI_T);
+  const int co = blockIdx.x / ncig, ci0 = (blockIdx.x % ncig) * CI_T;
+  const long long hw = (long long)g.Ho * g.Wo, total = (long long)g.N * hw;
+  const long long i0 = (long long)blockIdx.y * chunk, i1 = min(total, i0 + chunk);
+  float acc[CI_T][TAPS];
+#pragma unroll
+  for (int c = 0; c < CI_T; ++c)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) acc[c][t] = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += WG_THREADS) {
+    const int n = (int)(i / hw), p = (int)(i - (long long)n * hw);
+    const int oy = p / g.Wo, ox = p - oy * g.Wo;
+    const float d = __ldg(dy + (size_t)n * g.ys_n + (size_t)co * g.ys_c + p);
+    if (d == 0.f) continue;                                 // ReLU-masked gradients are exact zeros
+    const int crop0 = (n / g.zdepth) * g.zdepth;
+#pragma unroll
+    for (int tz = 0; tz < KZ; ++tz) {
+      const int zin = n + tz * g.dz - g.pz;
+      if (zin < crop0 || zin >= crop0 + g.zdepth) continue;
+#pragma unroll
+      for (int ty = 0; ty < KY; ++ty) {
+        const int iy = oy * g.stride + ty * g.dy - g.py;
+        if (iy < 0 || iy >= g.H) continue;
+        const float* xr = x + (size_t)zin * g.xs_n + (size_t)iy * g.W;
+#pragma unroll
+        for (int tx = 0; tx < KX; ++tx) {
+          const int ix = ox * g.stride + tx * g.dx - g.px;
+          if (ix < 0 || ix >= g.W) continue;
+#pragma unroll
+          for (int c = 0; c < CI_T; ++c)
+            if (ci0 + c < g.Cin) acc[c][(tz * KY + ty) * KX + tx] = fmaf(d, __ldg(xr + (size_t)(ci0 + c) * g.xs_c + ix), acc[c][(tz * KY + ty) * KX + tx]);
+        }
+      }
+    }
+  }
+  __shared__ float s_red[WG_THREADS / 32][CI_T * TAPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < CI_T; ++c)
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      float v = acc[c][t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp][c * TAPS + t] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CI_T * TAPS; i += WG_THREADS) {
+    const int c = i / TAPS, t = i - c * TAPS;
+    if (ci0 + c >= g.Cin) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < WG_THREADS / 32; ++k) v += s_red[k][i];
+    if (v != 0.f) atomicAdd(dw + ((size_t)co * g.Cin + ci0 + c) * TAPS + t, v);
+  }
+}
+
+// ConvTranspose2d(k=2, s=2) + bias, cropped to (Ho, Wo) <= (2H, 2W) (unet.py:285-292): weights [Cin][Cout][2][2]
+__global__ void __launch_bounds__(CV_THREADS) upconv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ y,
+                                                                const Geom g) {
+  extern __shared__ float s_w[];                       // [CV_CI][4][CV_CO]
+  const int p = blockIdx.x * CV_THREADS + threadIdx.x;
+  const int n = blockIdx.y, co0 = blockIdx.z * CV_CO;
+  const bool valid = p < g.Ho * g.Wo;
+  const int oy = valid ? p / g.Wo : 0, ox = valid ? p - oy * g.Wo : 0;
+  const int iy = oy >> 1, ix = ox >> 1, tap = (oy & 1) * 2 + (ox & 1);
+  float acc[CV_CO];
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) acc[c] = 0.f;
+  for (int ci0 = 0; ci0 < g.Cin; ci0 += CV_CI) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CV_CI * 4 * CV_CO; i += CV_THREADS) {
+      const int co = i % CV_CO, t = (i / CV_CO) % 4, ci = i / (CV_CO * 4);
+      float v = 0.f;
+      if (ci0 + ci < g.Cin && co0 + co < g.Cout) v = w[((size_t)(ci0 + ci) * g.Cout + co0 + co) * 4 + t];
+      s_w[i] = v;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    const int nci = min(CV_CI, g.Cin - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+      const float v = __ldg(x + (size_t)n * g.xs_n + (size_t)(ci0 + ci) * g.xs_c + (size_t)iy * g.W + ix);
+      const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)(ci * 4 + tap) * CV_CO);
+#pragma unroll
+      for (int q = 0; q < CV_CO / 4; ++q) {
+        const float4 ww = w4[q];
+        acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) {
+    if (co0 + c >= g.Cout) break;
+    y[(size_t)n * g.ys_n + (size_t)(co0 + c) * g.ys_c + p] = acc[c] + (bias ? bias[co0 + c] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-channel sums
+// part[c][split][k]: k = 0: sum a, 1: sum a*b (b optional).  Rows are dense (HW contiguous), (slice, channel) strided.
+constexpr int RED_THREADS = 256, RED_SPLITS = 32;
+
+// MODE 0: a = x, b = x (sum, sum of squares)           -- BatchNorm statistics
+// MODE 1: a = g = dy * (relu ? y > 0 : 1), b = xhat    -- BatchNorm backward sums (sum g, sum g * xhat)
+// MODE 2: a = x                                        -- bias gradient
+template <int MODE>
+__global__ void __launch_bounds__(RED_THREADS) chan_reduce_kernel(const float* __restrict__ x, long long xs_n, long long xs_c,
+                                                                  const float* __restrict__ y, const float* __restrict__ dy,
+                                                                  long long ys_n, long long ys_c,
+                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                  int N, int HW, int relu, double* __restrict__ part) {
+  const int c = blockIdx.x, sp = blockIdx.y;
+  const long long total = (long long)N * HW;
+  const long long chunk = ceil_div<long long>(total, RED_SPLITS);
+  const long long i0 = sp * chunk, i1 = min(total, i0 + chunk);
+  double s0 = 0.0, s1 = 0.0;
+  const float mu = (MODE == 1) ? mean[c] : 0.f, is = (MODE == 1) ? invstd[c] : 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += RED_THREADS) {
+    const int n = (int)(i / HW), p = (int)(i - (long long)n * HW);
+    if (MODE == 0) {
+      const float v = x[(size_t)n * xs_n + (size_t)c * xs_c + p];
+      s0 += v; s1 += (double)v * v;
+    } else if (MODE == 1) {
+      const size_t o = (size_t)n * ys_n + (size_t)c * ys_c + p;
+      float gv = dy[o];
+      if (relu && !(y[o] > 0.f)) gv = 0.f;
+      const float xh = (x[(size_t)n * xs_n + (size_t)c * xs_c + p] - mu) * is;
+      s0 += gv; s1 += (double)gv * xh;
+    } else {
+      s0 += x[(size_t)n * xs_n + (size_t)c * xs_c + p];
+    }
+  }
+  __shared__ double sh[2][RED_THREADS];
+  sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[((size_t)c * RED_SPLITS + sp) * 2] = sh[0][0]; part[((size_t)c * RED_SPLITS + sp) * 2 + 1] = sh[1][0]; }
+}
+
+// BatchNorm2d training statistics (F.batch_norm(training=True)): biased variance for the normalisation, unbiased for
+// the running estimate, running <- (1 - momentum) * running + momentum * batch
+__global__ void bn_stats_final_kernel(const double* __restrict__ part, int C, double count, float eps, float momentum,
+                                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < RED_SPLITS; ++k) { s0 += part[((size_t)c * RED_SPLITS + k) * 2]; s1 += part[((size_t)c * RED_SPLITS + k) * 2 + 1]; }
+  const double mu = s0 / count;
+  const double var = fmax(s1 / count - mu * mu, 0.0);
+  save_mean[c] = (float)mu;
+  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mu);
+  if (running_var) running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * var * (count > 1 ? count / (count - 1.0) : 1.0));
+}
+
+// sums[c] = {sum g, sum g*xhat}; dgamma += sum g*xhat, dbeta += sum g
+__global__ void bn_bwd_final_kernel(const double* __restrict__ part, int C, float* __restrict__ sums,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < RED_SPLITS; ++k) { s0 += part[((size_t)c * RED_SPLITS + k) * 2]; s1 += part[((size_t)c * RED_SPLITS + k) * 2 + 1]; }
+  sums[2 * c] = (float)s0; sums[2 * c + 1] = (float)s1;
+  if (dgamma) dgamma[c] += (float)s1;
+  if (dbeta) dbeta[c] += (float)s0;
+}
+
+__global__ void chan_sum_final_kernel(const double* __restrict__ part, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0;
+  for (int k = 0; k < RED_SPLITS; ++k) s0 += part[((size_t)c * RED_SPLITS + k) * 2];
+  out[c] = accumulate ? out[c] + (float)s0 : (float)s0;
+}
+
+// y = [relu](gamma * (x - mean) * invstd + beta)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, long long xs_n, long long xs_c,
+                                                       float* __restrict__ y, long long ys_n, long long ys_c,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       int C, int HW, int relu) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const float a = gamma[c] * invstd[c], b = beta[c] - mean[c] * a;
+  const float* xp = x + (size_t)n * xs_n + (size_t)c * xs_c;
+  float* yp = y + (size_t)n * ys_n + (size_t)c * ys_c;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+    float v = fmaf(xp[p], a, b);
+    if (relu) v = fmaxf(v, 0.f);
+    yp[p] = v;
+  }
+  (void)C;
+}
+
+// dx = gamma * invstd * (g - sum_g / M - xhat * sum_gx / M),  g = dy * (relu ? y > 0 : 1)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ x, long long xs_n, long long xs_c,
+                                                           const float* __restrict__ y, const float* __restrict__ dy,
+                                                           long long ys_n, long long ys_c, float* __restrict__ dx,
+                                                           long long dxs_n, long long dxs_c, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ sums, float inv_count, int HW, int relu) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const float mu = mean[c], is = invstd[c], k = gamma[c] * is;
+  const float m0 = sums[2 * c] * inv_count, m1 = sums[2 * c + 1] * inv_count;
+  const float* xp = x + (size_t)n * xs_n + (size_t)c * xs_c;
+  const float* yp = y + (size_t)n * ys_n + (size_t)c * ys_c;
+  const float* gp = dy + (size_t)n * ys_n + (size_t)c * ys_c;
+  float* dp = dx + (size_t)n * dxs_n + (size_t)c * dxs_c;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < HW; p += gridDim.x * 256) {
+    float gv = gp[p];
+    if (relu && !(yp[p] > 0.f)) gv = 0.f;
+    const float xh = (xp[p] - mu) * is;
+    dp[p] = k * (gv - m0 - xh * m1);
+  }
+}
+
+// MaxPool2d(2, ceil_mode=True) (unet.py:225): windows clipped at the border
+__global__ void __launch_bounds__(256) pool_f32_kernel(const float* __restrict__ x, long long xs_n, long long xs_c,
+                                                       float* __restrict__ y, long long ys_n, long long ys_c, int H, int W,
+                                                       int Ho, int Wo) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const float* xp = x + (size_t)n * xs_n + (size_t)c * xs_c;
+  float* yp = y + (size_t)n * ys_n + (size_t)c * ys_c;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < Ho * Wo; p += gridDim.x * 256) {
+    const int oy = p / Wo, ox = p - oy * Wo;
+    float m = -INFINITY;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int iy = 2 * oy + a, ix = 2 * ox + b;
+        if (iy < H && ix < W) { const float v = xp[(size_t)iy * W + ix]; if (v > m || v != v) m = v; }
+      }
+    yp[p] = m;
+  }
+}
+
+// dx[iy][ix] (+)= dy[iy/2][ix/2] if (iy, ix) is the FIRST maximum of its window in scan order (ATen's argmax rule)
+__global__ void __launch_bounds__(256) pool_bwd_f32_kernel(const float* __restrict__ x, long long xs_n, long long xs_c,
+                                                           const float* __restrict__ dy, long long dys_n, long long dys_c,
+                                                           float* __restrict__ dx, long long dxs_n, long long dxs_c, int H, int W,
+                                                           int Ho, int Wo, int accumulate) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const float* xp = x + (size_t)n * xs_n + (size_t)c * xs_c;
+  const float* gp = dy + (size_t)n * dys_n + (size_t)c * dys_c;
+  float* dp = dx + (size_t)n * dxs_n + (size_t)c * dxs_c;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < H * W; p += gridDim.x * 256) {
+    const int iy = p / W, ix = p - iy * W;
+    const int oy = iy >> 1, ox = ix >> 1;
+    float m = -INFINITY;
+    int arg = -1;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int yy = 2 * oy + a, xx = 2 * ox + b;
+        if (yy < H && xx < W) { const float v = xp[(size_t)yy * W + xx]; if (v > m || v != v) { m = v; arg = yy * W + xx; } }
+      }
+    const float gv = (arg == p) ? gp[(size_t)oy * Wo + ox] : 0.f;
+    dp[p] = accumulate ? dp[p] + gv : gv;
+  }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                       float* __restrict__ dx, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dx[i] = (y[i] > 0.f) ? dy[i] : 0.f;
+}
+
+bool geom_ok(const Geom* g) {
+  return g && g->N > 0 && g->Cin > 0 && g->Cout > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kz > 0 && g->ky > 0 &&
+         g->kx > 0 && g->dz > 0 && g->dy > 0 && g->dx > 0 && g->stride > 0 && g->zdepth > 0 && g->N % g->zdepth == 0 &&
+         g->pz >= 0 && g->py >= 0 && g->px >= 0;
+}
+
+template <int KZ, int KY, int KX, int CI_T>
+int launch_wgrad(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.Ho * g.Wo;
+  const int groups = g.Cout * ceil_div(g.Cin, CI_T);
+  // enough CTAs to fill the machine a few times over, chunks of at least 4096 (n, pixel) positions
+  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(total, 4096), ceil_div<long long>(8LL * num_sms(), groups)));
+  const long long chunk = ceil_div<long long>(total, splits);
+  splits = ceil_div<long long>(total, chunk);
+  wgrad_f32_kernel<KZ, KY, KX, CI_T><<<dim3(groups, (unsigned)splits), WG_THREADS, 0, s>>>(x, dy, dw, g, chunk);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+}  // namespace
+}  // namespace cetpick
+
+using namespace cetpick;
+
+extern "C" int cetpick_train_conv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g,
+                                      int flags, void* stream) {
+  g_launches = 0;
+  if (!x || !w || !y || !geom_ok(g)) return CETPICK_ERR_BAD_ARG;
+  const int taps = g->kz * g->ky * g->kx;
+  const size_t smem = (size_t)CV_CI * taps * CV_CO * sizeof(float);
+  if (smem > 48 * 1024) return CETPICK_ERR_UNSUPPORTED;
+  if (g->N > 65535) return CETPICK_ERR_UNSUPPORTED;
+  const dim3 grid(ceil_div(g->Ho * g->Wo, CV_THREADS), g->N, ceil_div(g->Cout, CV_CO));
+  conv_f32_kernel<<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, *g, flags);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_flip_weights_f32(const float* w, float* wt, int Cout, int Cin, int taps, void* stream) {
+  g_launches = 0;
+  if (!w || !wt || Cout <= 0 || Cin <= 0 || taps <= 0) return CETPICK_ERR_BAD_ARG;
+  const size_t total = (size_t)Cout * Cin * taps;
+  flip_weights_kernel<<<(int)std::min<size_t>(ceil_div<size_t>(total, 256), 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, wt, Cout, Cin, taps);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, float* dw, const cetpick_conv_geom* g, void* stream) {
+  g_launches = 0;
+  if (!x || !dy || !dw || !geom_ok(g)) return CETPICK_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int kz = g->kz, ky = g->ky, kx = g->kx;
+  if (kz == 1 && ky == 3 && kx == 3) return launch_wgrad<1, 3, 3, 4>(x, dy, dw, *g, s);
+  if (kz == 3 && ky == 3 && kx == 3) return launch_wgrad<3, 3, 3, 2>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 7 && kx == 7) return launch_wgrad<1, 7, 7, 1>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 1 && kx == 1) return launch_wgrad<1, 1, 1, 8>(x, dy, dw, *g, s);
+  if (kz == 3 && ky == 1 && kx == 1) return launch_wgrad<3, 1, 1, 8>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 2 && kx == 2) return launch_wgrad<1, 2, 2, 8>(x, dy, dw, *g, s);
+  return CETPICK_ERR_UNSUPPORTED;
+}
+
+extern "C" int cetpick_train_upconv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g,
+                                        void* stream) {
+  g_launches = 0;
+  if (!x || !w || !y || !geom_ok(g)) return CETPICK_ERR_BAD_ARG;
+  if (g->Ho > 2 * g->H || g->Wo > 2 * g->W || g->N > 65535) return CETPICK_ERR_BAD_ARG;
+  const dim3 grid(ceil_div(g->Ho * g->Wo, CV_THREADS), g->N, ceil_div(g->Cout, CV_CO));
+  upconv_f32_kernel<<<grid, CV_THREADS, CV_CI * 4 * CV_CO * sizeof(float), static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, *g);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_net_workspace_bytes(int C_max, size_t* bytes) {
+  if (!bytes || C_max <= 0) return CETPICK_ERR_BAD_ARG;
+  *bytes = align_up((size_t)C_max * RED_SPLITS * 2 * sizeof(double), 256) + align_up((size_t)C_max * 2 * sizeof(float), 256);
+  return CETPICK_OK;
+}
+
+namespace {
+struct RedWs { double* part; float* sums; };
+int red_ws(void* ws, size_t ws_bytes, int C, RedWs* out) {
+  const size_t a = align_up((size_t)C * RED_SPLITS * 2 * sizeof(double), 256), b = align_up((size_t)C * 2 * sizeof(float), 256);
+  if (!ws || ws_bytes < a + b || (reinterpret_cast<uintptr_t>(ws) & 255)) return CETPICK_ERR_WORKSPACE;
+  out->part = static_cast<double*>(ws);
+  out->sums = reinterpret_cast<float*>(static_cast<char*>(ws) + a);
+  return CETPICK_OK;
+}
+dim3 ew_grid(int HW, int C, int N) { return dim3(std::max(1, std::min(ceil_div(HW, 256), 64)), C, N); }
+}  // namespace
+
+extern "C" int cetpick_train_bn_f32(const float* x, long long xs_n, long long xs_c, float* y, long long ys_n, long long ys_c,
+                                    const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                    float* save_mean, float* save_invstd, int N, int C, int HW, float eps, float momentum,
+                                    int relu, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || N <= 0 || C <= 0 || HW <= 0 || N > 65535 || C > 65535)
+    return CETPICK_ERR_BAD_ARG;
+  RedWs r;
+  if (int rc = red_ws(ws, ws_bytes, C, &r)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  chan_reduce_kernel<0><<<dim3(C, RED_SPLITS), RED_THREADS, 0, s>>>(x, xs_n, xs_c, nullptr, nullptr, 0, 0, nullptr, nullptr, N, HW, 0,
+                                                                    r.part);
+  CETPICK_LAUNCH_CHECK();
+  bn_stats_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(r.part, C, (double)N * HW, eps, momentum, save_mean, save_invstd,
+                                                        running_mean, running_var);
+  CETPICK_LAUNCH_CHECK();
+  bn_apply_kernel<<<ew_grid(HW, C, N), 256, 0, s>>>(x, xs_n, xs_c, y, ys_n, ys_c, gamma, beta, save_mean, save_invstd, C, HW, relu);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_bn_bwd_f32(const float* x, long long xs_n, long long xs_c, const float* y, const float* dy,
+                                        long long ys_n, long long ys_c, float* dx, long long dxs_n, long long dxs_c,
+                                        const float* gamma, const float* save_mean, const float* save_invstd, float* dgamma,
+                                        float* dbeta, int N, int C, int HW, int relu, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  if (!x || !y || !dy || !dx || !gamma || !save_mean || !save_invstd || N <= 0 || C <= 0 || HW <= 0 || N > 65535 || C > 65535)
+    return CETPICK_ERR_BAD_ARG;
+  RedWs r;
+  if (int rc = red_ws(ws, ws_bytes, C, &r)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  chan_reduce_kernel<1><<<dim3(C, RED_SPLITS), RED_THREADS, 0, s>>>(x, xs_n, xs_c, y, dy, ys_n, ys_c, save_mean, save_invstd, N, HW,
+                                                                    relu, r.part);
+  CETPICK_LAUNCH_CHECK();
+  bn_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(r.part, C, r.sums, dgamma, dbeta);
+  CETPICK_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<ew_grid(HW, C, N), 256, 0, s>>>(x, xs_n, xs_c, y, dy, ys_n, ys_c, dx, dxs_n, dxs_c, gamma, save_mean,
+                                                        save_invstd, r.sums, (float)(1.0 / ((double)N * HW)), HW, relu);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_channel_sum_f32(const float* x, long long xs_n, long long xs_c, float* out, int N, int C, int HW,
+                                             int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  if (!x || !out || N <= 0 || C <= 0 || HW <= 0 || C > 65535) return CETPICK_ERR_BAD_ARG;
+  RedWs r;
+  if (int rc = red_ws(ws, ws_bytes, C, &r)) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  chan_reduce_kernel<2><<<dim3(C, RED_SPLITS), RED_THREADS, 0, s>>>(x, xs_n, xs_c, nullptr, nullptr, 0, 0, nullptr, nullptr, N, HW, 0,
+                                                                    r.part);
+  CETPICK_LAUNCH_CHECK();
+  chan_sum_final_kernel<<<ceil_div(C, 128), 128, 0, s>>>(r.part, C, out, accumulate);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_pool_f32(const float* x, long long xs_n, long long xs_c, float* y, long long ys_n, long long ys_c,
+                                      int N, int C, int H, int W, void* stream) {
+  g_launches = 0;
+  if (!x || !y || N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535 || C > 65535) return CETPICK_ERR_BAD_ARG;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  pool_f32_kernel<<<ew_grid(Ho * Wo, C, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, xs_n, xs_c, y, ys_n, ys_c, H, W, Ho, Wo);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_pool_bwd_f32(const float* x, long long xs_n, long long xs_c, const float* dy, long long dys_n,
+                                          long long dys_c, float* dx, long long dxs_n, long long dxs_c, int N, int C, int H, int W,
+                                          int accumulate, void* stream) {
+  g_launches = 0;
+  if (!x || !dy || !dx || N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 65535 || C > 65535) return CETPICK_ERR_BAD_ARG;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  pool_bwd_f32_kernel<<<ew_grid(H * W, C, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, xs_n, xs_c, dy, dys_n, dys_c, dx, dxs_n,
+                                                                                          dxs_c, H, W, Ho, Wo, accumulate);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+extern "C" int cetpick_train_relu_bwd_f32(const float* y, const float* dy, float* dx, size_t n, void* stream) {
+  g_launches = 0;
+  if (!y || !dy || !dx || n == 0) return CETPICK_ERR_BAD_ARG;
+  relu_bwd_kernel<<<(int)std::min<size_t>(ceil_div<size_t>(n, 256), (size_t)num_sms() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, dy, dx, n);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}

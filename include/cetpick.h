@@ -238,8 +238,9 @@ int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, in
                             float* proj, float* pred, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Refinement training step, the pieces around the network (BASELINE.json configs[4]).  The forward /
- * backward of the U-Net in training mode is not part of this library yet.
+ * Refinement training step (BASELINE.json configs[4]): losses, optimiser, and -- further down -- the
+ * training-mode layers (cetpick_train_conv_f32 ...) that cet_pick_b200/trains/engine.py strings into the forward and
+ * backward of the detector.
  * ------------------------------------------------------------------------------------------ */
 int cetpick_train_workspace_bytes(size_t* bytes);
 /* cet_pick/models/loss.py:255-325 `PULoss(tau)(pred, gt)`, pred = `_sigmoid(logits)` (models/utils.py:167-169) when
@@ -258,6 +259,62 @@ int cetpick_mse_loss_f32(const float* a, const float* b, int64_t n, float* out1,
 int cetpick_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                           double beta1, double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training-mode layers, fp32 (csrc/train_net.cu): what `loss.backward()` of trains/base_trainer.py:484-489 runs through
+ * for models/networks/unet_small.py:63-97 and unet.py:198-249,319-399.  Tensors have dense rows and explicit (slice,
+ * channel) element strides: (D,C,h,w) of the 2-D trunk and (C,D,h,w) of the 3-D head are the same buffer, a channel
+ * concat is a channel offset.  Gradients of parameters ACCUMULATE (+=) into their buffers like torch's `.grad`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cetpick_conv_geom {
+  int N, Cin, Cout;            /* slices (2-D: batch; 3-D: z), channels                                             */
+  int H, W, Ho, Wo;            /* input / output rows and columns                                                   */
+  long long xs_n, xs_c;        /* input element strides of slice and channel                                        */
+  long long ys_n, ys_c;        /* output (forward) / output-gradient (wgrad) strides                                */
+  int kz, ky, kx;              /* taps; kz > 1 = 3-D conv over the slice axis                                       */
+  int dz, dy, dx;              /* dilation                                                                          */
+  int pz, py, px;              /* zero padding                                                                      */
+  int stride;                  /* in-plane stride (1; 2 for the stem and for the transposed conv's data gradient)   */
+  int zdepth;                  /* slices per crop: z taps never cross a multiple of zdepth (N % zdepth == 0)        */
+} cetpick_conv_geom;
+
+/* y = [relu]([y +] conv(x, w) + bias); flags: bit 0 accumulate into y, bit 1 ReLU.  w: [Cout][Cin][kz][ky][kx] (torch
+ * layout), bias nullable.  Also the DATA GRADIENT of a
+ * stride-1 conv: x = dy, w = cetpick_train_flip_weights_f32(w) ([Cin][Cout][reversed taps]), pad' = (k-1)*dil - pad, and of
+ * ConvTranspose2d(2, stride 2): x = dy, w = the transposed conv's own [Cin][Cout][2][2] weights, 2x2 taps, stride 2. */
+int cetpick_train_conv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g,
+                           int flags, void* stream);
+int cetpick_train_flip_weights_f32(const float* w, float* wt, int Cout, int Cin, int taps, void* stream);
+/* dw[Cout][Cin][taps] += sum over (slice, pixel) of dy * shifted x  (tap sets 3x3, 3x3x3, 7x7, 1x1, 3x1x1, 2x2; others
+ * CETPICK_ERR_UNSUPPORTED).  Sums in fp32 with atomics: order, hence the last bits, vary from run to run (like cuDNN's
+ * default weight-gradient algorithms). */
+int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, float* dw, const cetpick_conv_geom* g, void* stream);
+/* ConvTranspose2d(Cin, Cout, 2, stride 2) + bias cropped to (Ho, Wo) <= (2H, 2W) (unet.py:285-292,375-380); w [Cin][Cout][2][2]. */
+int cetpick_train_upconv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g, void* stream);
+/* workspace of the reductions below for up to C_max channels (256-byte aligned) */
+int cetpick_train_net_workspace_bytes(int C_max, size_t* bytes);
+/* BatchNorm2d in training mode (+ ReLU when relu): batch mean / biased variance over (N, HW) per channel -> save_mean,
+ * save_invstd; running statistics updated with `momentum` (unbiased variance), nullable. */
+int cetpick_train_bn_f32(const float* x, long long xs_n, long long xs_c, float* y, long long ys_n, long long ys_c,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float* save_mean,
+                         float* save_invstd, int N, int C, int HW, float eps, float momentum, int relu, void* ws, size_t ws_bytes,
+                         void* stream);
+/* Backward of the above: dy is the gradient w.r.t. the (ReLU'd) output y; dx w.r.t. the BatchNorm input x; dgamma / dbeta
+ * accumulate (nullable).  y and dy share strides. */
+int cetpick_train_bn_bwd_f32(const float* x, long long xs_n, long long xs_c, const float* y, const float* dy, long long ys_n,
+                             long long ys_c, float* dx, long long dxs_n, long long dxs_c, const float* gamma,
+                             const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int N, int C, int HW,
+                             int relu, void* ws, size_t ws_bytes, void* stream);
+/* out[c] (+)= sum over (N, HW) of x: bias gradients */
+int cetpick_train_channel_sum_f32(const float* x, long long xs_n, long long xs_c, float* out, int N, int C, int HW, int accumulate,
+                                  void* ws, size_t ws_bytes, void* stream);
+/* MaxPool2d(2, ceil_mode=True) (unet.py:225) and its backward (the first maximum of a window takes the gradient) */
+int cetpick_train_pool_f32(const float* x, long long xs_n, long long xs_c, float* y, long long ys_n, long long ys_c, int N, int C,
+                           int H, int W, void* stream);
+int cetpick_train_pool_bwd_f32(const float* x, long long xs_n, long long xs_c, const float* dy, long long dys_n, long long dys_c,
+                               float* dx, long long dxs_n, long long dxs_c, int N, int C, int H, int W, int accumulate, void* stream);
+/* dx = dy * (y > 0), contiguous */
+int cetpick_train_relu_bwd_f32(const float* y, const float* dy, float* dx, size_t n, void* stream);
 
 /* Number of kernels the most recent cetpick_unet_forward / cetpick_decode_f32 on this thread
  * enqueued (bench.py's gpu_launches). */

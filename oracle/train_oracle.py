@@ -45,3 +45,20 @@ def focal_loss(pred, gt):
 def consistency_loss(a, b):
     """loss.py:701-715."""
     return torch.nn.functional.mse_loss(a, b)
+
+
+def training_step(x, gt, sd, tau, beta=0.0, param_names=None):
+    """One training forward + backward of the detector as trains/base_trainer.py:135-155,484-489 runs it for
+    `TomoCRSemiLoss` without `--contrastive` (tomo_cr_semi_trainer.py:52-60,101-104): model in train mode (batch-statistics
+    BatchNorm, running statistics updated in `sd` IN PLACE), loss = PULoss(tau)(_sigmoid(hm), gt), autograd gradients.
+    x: (b,d,h,w); gt: same number of elements as hm.  -> (loss, {name: grad}, hm logits)."""
+    from . import unet_oracle as uo
+    names = param_names or [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k and "num_batches" not in k]
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+    sdl = dict(sd)
+    sdl.update(leaves)
+    out = uo.forward(x, sdl, want_proj=False, train=True)
+    hm = out["hm"]
+    loss = pu_focal_loss(uo.sigmoid_clamp(hm), gt.reshape(hm.shape), tau, beta)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}, hm.detach()

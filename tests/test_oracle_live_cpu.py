@@ -93,3 +93,41 @@ def test_patch_dataset_against_live_reference(shape, params):
         idx, x = ds[n]
         oi, ox, grid = co.patch(vol, n, *params)
         assert np.array_equal(idx, oi) and np.array_equal(x, ox) and tuple(grid) == tuple(ds.shape)
+
+
+def test_training_step_against_live_reference():
+    """Train-mode forward (batch-statistics BatchNorm, b > 1 branch) + PULoss + autograd of the oracle against the
+    imported reference model and loss: loss, every parameter gradient and the updated running statistics."""
+    from oracle import train_oracle as to
+    refbridge.install()
+    from cet_pick.models.loss import PULoss
+    from cet_pick.models.utils import _sigmoid
+    torch.manual_seed(0)
+    m = refbridge.create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+    sd = {k: v.clone() for k, v in synth.unet_state_dict_torch(29, 4).items()}
+    m.load_state_dict(sd)
+    m.train()
+    b, d, h, w = 2, 4, 36, 44
+    x = torch.from_numpy(np.stack([synth.tomogram_np(d, h, w, 4 + i) for i in range(b)]))
+    gt = torch.full((b, 1, d, h // 2, w // 2), -1.0)
+    gt[0, 0, 1, 5, 7] = 1.0
+    gt[1, 0, 2, 9, 3] = 1.0
+    gt[0, 0, 1, 5, 8] = 0.6
+    gt[1, 0, 2, 10, 3] = 0.3
+    out = m(x)[-1]
+    loss = PULoss(0.02)(_sigmoid(out["hm"]), gt)
+    loss.backward()
+    oloss, grads, ohm = to.training_step(x, gt, sd, 0.02)
+    assert abs(float(loss) - float(oloss)) <= 1e-6 * max(1.0, abs(float(loss)))
+    # models/utils.py:167-169 `_sigmoid` works in place: out["hm"] holds the clamped sigmoid by now
+    assert (uo.sigmoid_clamp(ohm) - out["hm"].detach()).abs().max().item() <= 1e-6
+    for k, p in m.named_parameters():
+        if k.startswith("proj"):
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        ref = p.grad
+        err = (grads[k] - ref).abs().max().item()
+        assert err <= 1e-5 * max(1e-3, ref.abs().max().item()) + 1e-9, (k, err, ref.abs().max().item())
+    for k, v in m.named_buffers():
+        if "running" in k:
+            assert (sd[k] - v).abs().max().item() <= 1e-6, k
