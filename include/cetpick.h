@@ -65,6 +65,9 @@ int cetpick_decode_workspace_bytes(int64_t D, int64_t H, int64_t W, int K, size_
  * inds : NULL or (B,K) int64 out, linear indices (decode.py:87).
  * kernel_xy : odd, 1..7 (opt.nms).  nms_mode : CETPICK_NMS_*.  FIBER needs kernel_xy == 3.
  * ws   : >= cetpick_decode_workspace_bytes bytes, 256-byte aligned; reused across the batch.
+ * Repeated calls with identical arguments (the detector loop) are replayed as one cached CUDA graph from the third
+ * call on (at most 16 argument sets are kept per process; CETPICK_DECODE_GRAPH=0 disables it).  A call made while
+ * `stream` is itself being captured simply adds its launches to the caller's capture.
  */
 int cetpick_decode_f32(const float* heat, int64_t B, int64_t D, int64_t H, int64_t W,
                        int kernel_xy, int K, int nms_mode, const float* reg,

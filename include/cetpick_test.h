@@ -105,6 +105,8 @@ int cetpick_probe_mma_rate2(int N, int KC, int sbo_a, int a_step, int ntap, int 
 /* Stage timing of the decode (scripts/decode_stages.py): cetpick_decode_f32 returns after stage n of its launch
  * sequence (1 init, 2 sample select, 3 sieve, 4 gated fall-backs + EQ pass, 5 tail kernel); 0 = all. */
 int cetpick_decode_set_stop_stage(int n);
+/* calls of cetpick_decode_f32 in this process that were served by a cached CUDA graph (one cudaGraphLaunch) */
+int64_t cetpick_decode_graph_hits(void);
 
 #ifdef __cplusplus
 }

@@ -293,3 +293,36 @@ def test_sieve_batch_of_two_reuses_the_workspace(dec, do):
     hm[1] = np.minimum(hm[1], np.float32(0.9))            # a plateau at the top in the second element only
     out = dec.tomo_decode(cu(hm), kernel=3, K=K).cpu().numpy()
     assert np.array_equal(bits(out), bits(do.tomo_decode(hm, 3, None, K)))
+
+
+def test_repeated_identical_calls_replay_a_graph_and_stay_bit_exact(dec):
+    """The third call with the same pointers / shape / K is one cudaGraphLaunch (csrc/decode.cu); results identical to
+    the first (plain) call, also after the map's CONTENT changed (the graph holds launches, not data)."""
+    import ctypes as C
+    from cet_pick_b200 import _lib
+    T = _lib.test_lib()
+    D, H, W, K = 40, 512, 512, 500
+    hm = synth.heatmap_tiefree_torch(D, H, W, 11)[None, None]
+    hm2 = synth.heatmap_tiefree_torch(D, H, W, 12)[None, None]
+    L = _lib.lib()
+    nb = C.c_size_t(0)
+    _lib.check(L.cetpick_decode_workspace_bytes(D, H, W, K, C.byref(nb)), "ws")
+    ws = torch.empty(nb.value + 256, dtype=torch.uint8, device="cuda")
+    wp = (ws.data_ptr() + 255) // 256 * 256
+    dets = torch.empty((1, K, 5), device="cuda")
+
+    def call(lib):
+        _lib.check(lib.cetpick_decode_f32(hm.data_ptr(), 1, D, H, W, 3, K, 1, None, dets.data_ptr(), None, wp, nb.value,
+                                          _lib.stream_ptr()), "decode")
+        return dets.clone()
+
+    ref1 = dec.tomo_decode(hm, kernel=3, K=K)
+    h0 = T.cetpick_decode_graph_hits()
+    outs = [call(T) for _ in range(4)]
+    assert T.cetpick_decode_graph_hits() - h0 == 3          # call 1 plain, call 2 captures and launches, 3 and 4 replay
+    for o in outs:
+        assert torch.equal(o.view(torch.int32), ref1.view(torch.int32))
+    hm.copy_(hm2)
+    ref2 = dec.tomo_decode(hm2, kernel=3, K=K)
+    assert torch.equal(call(T).view(torch.int32), ref2.view(torch.int32))
+    assert not torch.equal(ref1, ref2)
