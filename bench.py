@@ -16,6 +16,7 @@ Legs (all inside one run; the extra ones are rank 0 / N = 1 only so the scaling 
   e2e            host uint8 levels in (pinned, 3 staging buffers) -> H2D -> forward -> decode -> picks D2H
   e2e_run        TomodetDetector.run(): the drop-in call incl. heat-map D2H and the <name>.txt / _hm.mrc files (tmpfs)
   roofline       tcgen05 conv kernels of one forward: median of 5 profiled forwards (+ frac_step at step level)
+  train_config5    BASELINE.json configs[4]: training step on 128^3 crops (all ranks; gradient all-reduce + Adam)
   roofline_decode  BASELINE.json configs[2]: decode of a 512x1024x1024 map, K = 10 000, with a bit-exact self-check
   simsiam_config3  BASELINE.json configs[3]: SimSiam 3-D encoder embedding inference on 8192 sub-volumes of 32^3
   torch_cuda_baseline  the reference's op sequence run by PyTorch (cuDNN) on the same GPU: fp32 / TF32 / bf16 autocast
@@ -229,6 +230,109 @@ def leg_roofline_decode(dev, pk, iters=10):
             "launches_per_decode": int(launches), "bit_exact_vs_torch_cuda": exact, "status_flags": int(flags),
             "torch_cuda_decode_ms": torch_ms, "speedup_vs_torch_cuda": torch_ms / mean_ms,
             "peak_source": pk["src"] + " HBM copy bandwidth", "gvoxels_per_sec": D * H * W / (mean_ms * 1e-3) / 1e9}
+
+
+def leg_train(dev, rank, world, crops_per_rank=2, steps=3, with_torch=False):
+    """BASELINE.json configs[4]: refinement training step on 128^3 crops -- forward + backward (csrc/train_net.cu through
+    trains/engine.py), ONE all-reduce of the flat gradient bucket over the ranks, fused Adam.  Every rank trains
+    `crops_per_rank` crops per step (micro-batches of one crop, gradients accumulated in the bucket); collective: all
+    ranks call this.  value = crops per second over all ranks (max-over-ranks step time)."""
+    import torch
+    import torch.distributed as dist
+    import synthdata as synth
+    from cet_pick_b200.models.model import create_model
+    from cet_pick_b200.trains.engine import DetectorTrainer
+    S = 128
+    sd = {k: v.to(dev) for k, v in synth.unet_state_dict_torch(317, 4).items()}
+    m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    tr = DetectorTrainer(m, tau=0.01)
+    crops = [synth.tomogram_torch(S, S, S, seed=5000 + rank * crops_per_rank + i, device=dev)[None] for i in range(crops_per_rank)]
+    gt = torch.full((1, 1, S, S // 2, S // 2), -1.0, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for _ in range(200):
+        z, y, x = (int(torch.randint(1, n - 1, (1,), generator=g)) for n in (S, S // 2, S // 2))
+        gt[0, 0, z, y, x] = 1.0
+        gt[0, 0, z, y, x + 1] = 0.6
+    ok = torch.ones(1, device=dev)
+    err = ""
+
+    def local():
+        tr.zero_grad()
+        for c in crops:
+            tr.forward_backward(c, gt)
+
+    ar_ms = []
+
+    def step():
+        local()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scale = 1.0
+        if world > 1:
+            dist.all_reduce(tr.bucket.grads)
+            scale = 1.0 / world
+        e1.record()
+        tr.bucket.adam_step(1e-4, grad_scale=scale / crops_per_rank)
+        return e0, e1
+
+    try:
+        local()
+        torch.cuda.synchronize()
+    except Exception as e:                                  # no collective was entered yet: report and agree to stop
+        ok.zero_()
+        err = f"{type(e).__name__}: {e}"[:200]
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) == 0:
+        return {"error": err or "another rank failed"}
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    evs = [step() for _ in range(steps)]
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+    flops = 3 * 214.6e9 * crops_per_rank * world
+    out = {"workload": f"refinement training step, {crops_per_rank} x 128^3 crops per rank, unet_4, PULoss, Adam (configs[4]; "
+                       "fp32 CUDA-core layers, batch-statistics BatchNorm per crop)",
+           "ms_per_step": ms, "crops_per_s": world * crops_per_rank / (ms * 1e-3), "n_gpus": world,
+           "allreduce_ms": ar if world > 1 else 0.0, "gradient_bucket_bytes": int(tr.bucket.numel * 4),
+           "model_tflops": flops / (ms * 1e-3) / 1e12, "launches_per_crop": int(tr.stats.get("launches", 0)),
+           "loss": float(tr.stats["loss"])}
+    if with_torch:
+        from oracle import train_oracle as to
+        names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k and not k.startswith("proj")]
+        for tag, tf32 in (("torch_cuda_fp32_ms_per_crop", False), ("torch_cuda_tf32_ms_per_crop", True)):
+            old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            try:
+                sdt = {k: v.clone() for k, v in sd.items()}
+                to.training_step(crops[0], gt, sdt, 0.01, param_names=names)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(2):
+                    to.training_step(crops[0], gt, sdt, 0.01, param_names=names)
+                a1.record()
+                torch.cuda.synchronize()
+                out[tag] = a0.elapsed_time(a1) / 2
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        out["ours_ms_per_crop"] = ms / crops_per_rank
+        out["torch_note"] = ("the same step as functional PyTorch + autograd on this GPU (cuDNN); the reference trains in "
+                             "fp32 with PyTorch's default cudnn.allow_tf32 = True")
+    return out
 
 
 def leg_torch_cuda_baseline(dev, shape, our_forward_ms, our_hm):
@@ -637,6 +741,16 @@ def run_b200(a, rank, world, local_rank):
         finally:
             del our_hm
             torch.cuda.empty_cache()
+    # ---- training step (configs[4]): every rank takes part (the gradient all-reduce is the path's one collective)
+    if not a.no_extras:
+        del pool[:]
+        torch.cuda.empty_cache()
+        try:
+            res = leg_train(dev, rank, world, with_torch=(world == 1))
+        except Exception as e:
+            res = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0:
+            line["train_config5"] = res
     if rank == 0:
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample((D, H, W), a.K, a.nms, a.cpu_sample_slices)

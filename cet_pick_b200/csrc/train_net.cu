@@ -96,6 +96,96 @@ __global__ void __launch_bounds__(CV_THREADS) conv_f32_kernel(const float* __res
   }
 }
 
+
+// The network's hot shapes -- (1,3,3) dilation 1 (trunk) and (3,3,3) dilation (1,4,4) (head), stride 1 -- with the taps
+// unrolled: each thread owns TWO horizontally adjacent output pixels x CV_CO output channels, loads each input row
+// segment once for both pixels and all three x taps, and reads each weight vector once for both pixels.
+template <int KZ, int DXY>
+__global__ void __launch_bounds__(CV_THREADS) conv3x3_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y,
+                                                                 const Geom g, const int flags) {
+  constexpr int TAPS = KZ * 9;
+  constexpr int NCOL = 2 * DXY + 2;                    // input columns the two pixels touch: ox - DXY .. ox + 1 + DXY
+  __shared__ __align__(16) float s_w[CV_CI * TAPS * CV_CO];
+  const bool accumulate = flags & 1, relu = flags & 2;
+  const int pairs_per_row = (g.Wo + 1) >> 1;
+  const int q = blockIdx.x * CV_THREADS + threadIdx.x;
+  const int n = blockIdx.y, co0 = blockIdx.z * CV_CO;
+  const bool valid = q < g.Ho * pairs_per_row;
+  const int oy = valid ? q / pairs_per_row : 0, ox = valid ? 2 * (q - oy * pairs_per_row) : 0;
+  const bool valid1 = valid && (ox + 1 < g.Wo);
+  const int crop0 = (n / g.zdepth) * g.zdepth;
+  float acc0[CV_CO], acc1[CV_CO];
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) acc0[c] = acc1[c] = 0.f;
+  // validity of the rows / columns this thread reads (zero padding = skipped loads)
+  bool zok[KZ], yok[3], xok[NCOL];
+#pragma unroll
+  for (int tz = 0; tz < KZ; ++tz) { const int zin = n + tz - g.pz; zok[tz] = (zin >= crop0) && (zin < crop0 + g.zdepth); }
+#pragma unroll
+  for (int ty = 0; ty < 3; ++ty) { const int iy = oy + ty * DXY - g.py; yok[ty] = (iy >= 0) && (iy < g.H); }
+#pragma unroll
+  for (int c = 0; c < NCOL; ++c) { const int ix = ox - g.px + c; xok[c] = valid && (ix >= 0) && (ix < g.W); }
+  for (int ci0 = 0; ci0 < g.Cin; ci0 += CV_CI) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CV_CI * TAPS * CV_CO; i += CV_THREADS) {
+      const int co = i % CV_CO, t = (i / CV_CO) % TAPS, ci = i / (CV_CO * TAPS);
+      float v = 0.f;
+      if (ci0 + ci < g.Cin && co0 + co < g.Cout) v = w[((size_t)(co0 + co) * g.Cin + ci0 + ci) * TAPS + t];
+      s_w[i] = v;
+    }
+    __syncthreads();
+    if (!valid) continue;
+    const int nci = min(CV_CI, g.Cin - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+      const float* xc = x + (size_t)(ci0 + ci) * g.xs_c;
+      const float* wc = s_w + (size_t)ci * TAPS * CV_CO;
+#pragma unroll
+      for (int tz = 0; tz < KZ; ++tz) {
+        if (!zok[tz]) continue;
+        const float* xz = xc + (size_t)(n + tz - g.pz) * g.xs_n;
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty) {
+          if (!yok[ty]) continue;
+          const float* xr = xz + (size_t)(oy + ty * DXY - g.py) * g.W + (ox - g.px);
+          float v[NCOL];
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c) v[c] = 0.f;
+#pragma unroll
+          for (int tx = 0; tx < 3; ++tx) {                 // only the columns a tap lands on (dilation 4: 6 of 10)
+            if (xok[tx * DXY]) v[tx * DXY] = __ldg(xr + tx * DXY);
+            if (xok[tx * DXY + 1]) v[tx * DXY + 1] = __ldg(xr + tx * DXY + 1);
+          }
+#pragma unroll
+          for (int tx = 0; tx < 3; ++tx) {
+            const float a = v[tx * DXY], b = v[tx * DXY + 1];
+            const float4* w4 = reinterpret_cast<const float4*>(wc + ((tz * 3 + ty) * 3 + tx) * CV_CO);
+#pragma unroll
+            for (int k = 0; k < CV_CO / 4; ++k) {
+              const float4 ww = w4[k];
+              acc0[4 * k + 0] = fmaf(a, ww.x, acc0[4 * k + 0]); acc1[4 * k + 0] = fmaf(b, ww.x, acc1[4 * k + 0]);
+              acc0[4 * k + 1] = fmaf(a, ww.y, acc0[4 * k + 1]); acc1[4 * k + 1] = fmaf(b, ww.y, acc1[4 * k + 1]);
+              acc0[4 * k + 2] = fmaf(a, ww.z, acc0[4 * k + 2]); acc1[4 * k + 2] = fmaf(b, ww.z, acc1[4 * k + 2]);
+              acc0[4 * k + 3] = fmaf(a, ww.w, acc0[4 * k + 3]); acc1[4 * k + 3] = fmaf(b, ww.w, acc1[4 * k + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < CV_CO; ++c) {
+    if (co0 + c >= g.Cout) break;
+    float* o = y + (size_t)n * g.ys_n + (size_t)(co0 + c) * g.ys_c + (size_t)oy * g.Wo + ox;
+    const float bv = bias ? bias[co0 + c] : 0.f;
+    float v0 = acc0[c] + bv, v1 = acc1[c] + bv;
+    if (accumulate) { v0 += o[0]; if (valid1) v1 += o[1]; }
+    o[0] = relu ? fmaxf(v0, 0.f) : v0;
+    if (valid1) o[1] = relu ? fmaxf(v1, 0.f) : v1;
+  }
+}
+
 // wt[ci][co][taps-1-t] = w[co][ci][t]: the weights with which a stride-1 conv of dy gives dx
 __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int taps) {
   const size_t total = (size_t)Cout * Cin * taps;
@@ -106,26 +196,36 @@ __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restri
 }
 
 // dw[co][ci][t] += sum_{n,oy,ox} dy[n][co][oy][ox] * x[n + tz*dz - pz][ci][oy*s + ty*dy - py][ox*s + tx*dx - px]
-// One CTA: one co, CI_T input channels, all taps in registers, a chunk of the (n, pixel) range; CTA reduction, atomics.
+// One CTA: CO_T output channels x CI_T input channels, all taps, in registers, over a chunk of the (n, pixel) range;
+// every loaded x value feeds CO_T accumulators, every dy value CI_T * TAPS; CTA reduction, atomics.
 constexpr int WG_THREADS = 256;
-template <int KZ, int KY, int KX, int CI_T>
+template <int KZ, int KY, int KX, int CO_T, int CI_T>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dw, const Geom g, const long long chunk) {
   constexpr int TAPS = KZ * KY * KX;
+  constexpr int NACC = CO_T * CI_T * TAPS;
   const int ncig = ceil_div(g.Cin, CI_T);
-  const int co = blockIdx.x / ncig, ci0 = (blockIdx.x % ncig) * CI_T;
+  const int co0 = (blockIdx.x / ncig) * CO_T, ci0 = (blockIdx.x % ncig) * CI_T;
   const long long hw = (long long)g.Ho * g.Wo, total = (long long)g.N * hw;
   const long long i0 = (long long)blockIdx.y * chunk, i1 = min(total, i0 + chunk);
-  float acc[CI_T][TAPS];
+  float acc[CO_T][CI_T][TAPS];
 #pragma unroll
-  for (int c = 0; c < CI_T; ++c)
+  for (int o = 0; o < CO_T; ++o)
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) acc[c][t] = 0.f;
+    for (int c = 0; c < CI_T; ++c)
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) acc[o][c][t] = 0.f;
   for (long long i = i0 + threadIdx.x; i < i1; i += WG_THREADS) {
     const int n = (int)(i / hw), p = (int)(i - (long long)n * hw);
     const int oy = p / g.Wo, ox = p - oy * g.Wo;
-    const float d = __ldg(dy + (size_t)n * g.ys_n + (size_t)co * g.ys_c + p);
-    if (d == 0.f) continue;                                 // ReLU-masked gradients are exact zeros
+    float d[CO_T];
+    bool any = false;
+#pragma unroll
+    for (int o = 0; o < CO_T; ++o) {
+      d[o] = (co0 + o < g.Cout) ? __ldg(dy + (size_t)n * g.ys_n + (size_t)(co0 + o) * g.ys_c + p) : 0.f;
+      any |= (d[o] != 0.f);
+    }
+    if (!any) continue;                                     // ReLU-masked gradients are exact zeros
     const int crop0 = (n / g.zdepth) * g.zdepth;
 #pragma unroll
     for (int tz = 0; tz < KZ; ++tz) {
@@ -141,31 +241,37 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_f32_kernel(const float* __re
           const int ix = ox * g.stride + tx * g.dx - g.px;
           if (ix < 0 || ix >= g.W) continue;
 #pragma unroll
-          for (int c = 0; c < CI_T; ++c)
-            if (ci0 + c < g.Cin) acc[c][(tz * KY + ty) * KX + tx] = fmaf(d, __ldg(xr + (size_t)(ci0 + c) * g.xs_c + ix), acc[c][(tz * KY + ty) * KX + tx]);
+          for (int c = 0; c < CI_T; ++c) {
+            if (ci0 + c >= g.Cin) continue;
+            const float xv = __ldg(xr + (size_t)(ci0 + c) * g.xs_c + ix);
+#pragma unroll
+            for (int o = 0; o < CO_T; ++o) acc[o][c][(tz * KY + ty) * KX + tx] = fmaf(d[o], xv, acc[o][c][(tz * KY + ty) * KX + tx]);
+          }
         }
       }
     }
   }
-  __shared__ float s_red[WG_THREADS / 32][CI_T * TAPS];
+  __shared__ float s_red[WG_THREADS / 32][NACC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int c = 0; c < CI_T; ++c)
+  for (int o = 0; o < CO_T; ++o)
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) {
-      float v = acc[c][t];
+    for (int c = 0; c < CI_T; ++c)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_red[warp][c * TAPS + t] = v;
-    }
+      for (int t = 0; t < TAPS; ++t) {
+        float v = acc[o][c][t];
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+        if (lane == 0) s_red[warp][(o * CI_T + c) * TAPS + t] = v;
+      }
   __syncthreads();
-  for (int i = threadIdx.x; i < CI_T * TAPS; i += WG_THREADS) {
-    const int c = i / TAPS, t = i - c * TAPS;
-    if (ci0 + c >= g.Cin) continue;
+  for (int i = threadIdx.x; i < NACC; i += WG_THREADS) {
+    const int t = i % TAPS, c = (i / TAPS) % CI_T, o = i / (TAPS * CI_T);
+    if (ci0 + c >= g.Cin || co0 + o >= g.Cout) continue;
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < WG_THREADS / 32; ++k) v += s_red[k][i];
-    if (v != 0.f) atomicAdd(dw + ((size_t)co * g.Cin + ci0 + c) * TAPS + t, v);
+    if (v != 0.f) atomicAdd(dw + ((size_t)(co0 + o) * g.Cin + ci0 + c) * TAPS + t, v);
   }
 }
 
@@ -389,15 +495,17 @@ bool geom_ok(const Geom* g) {
          g->pz >= 0 && g->py >= 0 && g->px >= 0;
 }
 
-template <int KZ, int KY, int KX, int CI_T>
+template <int KZ, int KY, int KX, int CO_T, int CI_T>
 int launch_wgrad(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo;
-  const int groups = g.Cout * ceil_div(g.Cin, CI_T);
-  // enough CTAs to fill the machine a few times over, chunks of at least 4096 (n, pixel) positions
-  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(total, 4096), ceil_div<long long>(8LL * num_sms(), groups)));
+  const int groups = ceil_div(g.Cout, CO_T) * ceil_div(g.Cin, CI_T);
+  // enough CTAs to fill the machine a few times over; chunks of at least 16384 (n, pixel) positions so that the CTA's
+  // reduction of its CO_T * CI_T * TAPS partial sums stays a small share of its work
+  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(total, 16384), ceil_div<long long>(8LL * num_sms(), groups)));
+  splits = std::min<long long>(splits, 65535);
   const long long chunk = ceil_div<long long>(total, splits);
   splits = ceil_div<long long>(total, chunk);
-  wgrad_f32_kernel<KZ, KY, KX, CI_T><<<dim3(groups, (unsigned)splits), WG_THREADS, 0, s>>>(x, dy, dw, g, chunk);
+  wgrad_f32_kernel<KZ, KY, KX, CO_T, CI_T><<<dim3(groups, (unsigned)splits), WG_THREADS, 0, s>>>(x, dy, dw, g, chunk);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }
@@ -415,8 +523,23 @@ extern "C" int cetpick_train_conv_f32(const float* x, const float* w, const floa
   const size_t smem = (size_t)CV_CI * taps * CV_CO * sizeof(float);
   if (smem > 48 * 1024) return CETPICK_ERR_UNSUPPORTED;
   if (g->N > 65535) return CETPICK_ERR_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g->ky == 3 && g->kx == 3 && g->stride == 1 && g->dz == 1 && g->dy == g->dx && g->Ho == g->H && g->Wo == g->W) {
+    // the hot shapes ('same' 3x3 in-plane taps): two pixels per thread, taps unrolled
+    const dim3 grid2(ceil_div(g->Ho * ((g->Wo + 1) / 2), CV_THREADS), g->N, ceil_div(g->Cout, CV_CO));
+    if (g->kz == 1 && g->dy == 1) {
+      conv3x3_f32_kernel<1, 1><<<grid2, CV_THREADS, 0, s>>>(x, w, bias, y, *g, flags);
+      CETPICK_LAUNCH_CHECK();
+      return CETPICK_OK;
+    }
+    if (g->kz == 3 && g->dy == 4) {
+      conv3x3_f32_kernel<3, 4><<<grid2, CV_THREADS, 0, s>>>(x, w, bias, y, *g, flags);
+      CETPICK_LAUNCH_CHECK();
+      return CETPICK_OK;
+    }
+  }
   const dim3 grid(ceil_div(g->Ho * g->Wo, CV_THREADS), g->N, ceil_div(g->Cout, CV_CO));
-  conv_f32_kernel<<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, *g, flags);
+  conv_f32_kernel<<<grid, CV_THREADS, smem, s>>>(x, w, bias, y, *g, flags);
   CETPICK_LAUNCH_CHECK();
   return CETPICK_OK;
 }
@@ -436,12 +559,12 @@ extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, flo
   if (!x || !dy || !dw || !geom_ok(g)) return CETPICK_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int kz = g->kz, ky = g->ky, kx = g->kx;
-  if (kz == 1 && ky == 3 && kx == 3) return launch_wgrad<1, 3, 3, 4>(x, dy, dw, *g, s);
-  if (kz == 3 && ky == 3 && kx == 3) return launch_wgrad<3, 3, 3, 2>(x, dy, dw, *g, s);
-  if (kz == 1 && ky == 7 && kx == 7) return launch_wgrad<1, 7, 7, 1>(x, dy, dw, *g, s);
-  if (kz == 1 && ky == 1 && kx == 1) return launch_wgrad<1, 1, 1, 8>(x, dy, dw, *g, s);
-  if (kz == 3 && ky == 1 && kx == 1) return launch_wgrad<3, 1, 1, 8>(x, dy, dw, *g, s);
-  if (kz == 1 && ky == 2 && kx == 2) return launch_wgrad<1, 2, 2, 8>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 3 && kx == 3) return launch_wgrad<1, 3, 3, 4, 2>(x, dy, dw, *g, s);
+  if (kz == 3 && ky == 3 && kx == 3) return launch_wgrad<3, 3, 3, 2, 1>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 7 && kx == 7) return launch_wgrad<1, 7, 7, 1, 1>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 1 && kx == 1) return launch_wgrad<1, 1, 1, 4, 8>(x, dy, dw, *g, s);
+  if (kz == 3 && ky == 1 && kx == 1) return launch_wgrad<3, 1, 1, 1, 8>(x, dy, dw, *g, s);
+  if (kz == 1 && ky == 2 && kx == 2) return launch_wgrad<1, 2, 2, 4, 4>(x, dy, dw, *g, s);
   return CETPICK_ERR_UNSUPPORTED;
 }
 

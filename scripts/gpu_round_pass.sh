@@ -23,7 +23,7 @@ try:
     print({k: j[k] for k in ("value", "value_w1", "ms_per_step", "gpu_launches")}, "e2e", j["e2e"]["value"])
     print({k: r[k] for k in ("achieved", "frac", "frac_step", "forward_ms", "stem_uint8_input_ms", "conv_ms_all")})
     print(r["layers_ms"])
-    for k in ("e2e_run", "simsiam_config3", "roofline_decode", "torch_cuda_baseline", "tf32_mode", "cpu_baseline", "clocks"):
+    for k in ("e2e_run", "simsiam_config3", "roofline_decode", "train_config5", "torch_cuda_baseline", "tf32_mode", "cpu_baseline", "clocks"):
         print(k, j.get(k))
 except Exception as e:
     print("bench line unreadable:", e)
