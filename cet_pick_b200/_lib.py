@@ -100,6 +100,7 @@ TEST_SIGNATURES = {
     "cetpick_conv_stem_bf16": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "cetpick_decode_set_stop_stage": (_int, [_int]),
     "cetpick_decode_graph_hits": (_i64, []),
+    "cetpick_tmap_cache_stats": (_int, [C.POINTER(_i64), C.POINTER(_i64)]),
     "cetpick_probe_mma_rate": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_probe_mma_rate2": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "cetpick_conv_bf16": (_int, [_int, _vp, _int, _vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _int,

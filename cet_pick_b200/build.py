@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libcetpick_sm100a.so")
 TEST_LIB = os.path.join(PKG, "libcetpick_test_sm100a.so")   # product objects + the hooks of include/cetpick_test.h
 STAMP = LIB + ".stamp"
-SOURCES = ["abi.cu", "decode.cu", "greedy_nms.cu", "preproc.cu", "explore.cu", "conv_tc.cu", "conv_march.cu", "conv_up.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "conv_small.cu", "simsiam.cu", "train.cu", "train_net.cu", "unet.cu", "probe.cu"]
+SOURCES = ["abi.cu", "decode.cu", "greedy_nms.cu", "preproc.cu", "explore.cu", "sort.cu", "conv_tc.cu", "conv_march.cu", "conv_up.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "conv_small.cu", "simsiam.cu", "train.cu", "train_net.cu", "unet.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr"]
 

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <mutex>
+#include <unordered_map>
 
 namespace cetpick {
 
@@ -309,68 +310,100 @@ CUtensorMapSwizzle swizzle_of(int KC) {
 
 }  // namespace
 
-// bf16 tiled tensor map whose innermost box dimension is KC channels (= the swizzle span)
-int tmap_encode_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, int KC) {
+// ---------------------------------------------------------------------------------------------
+// Tensor-map cache.  A CUtensorMap is a pure function of (base pointer, data type, rank, dims, strides, box, swizzle,
+// L2 promotion, out-of-bounds fill); a forward of the same plan on the same buffers and shape asks for the same ~45
+// descriptors every time (the detector loop: same workspace, same input staging buffer), so they are encoded once
+// (cuTensorMapEncodeTiled is a 1-2 us driver call each) and copied from here afterwards.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  int dtype, rank, swizzle, promo, oob, dev;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "hashed as 64-bit words");
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+int64_t g_tmap_hits = 0, g_tmap_misses = 0;
+constexpr size_t TMAP_CACHE_MAX = 4096;
+
+int tmap_encode_any(CUtensorMap* tm, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo,
+                    CUtensorMapFloatOOBfill oob, const char* what) {
+  if (rank < 1 || rank > 5) return CETPICK_ERR_BAD_ARG;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.dtype = (int)dtype; key.rank = rank; key.swizzle = (int)swz; key.promo = (int)promo; key.oob = (int)oob;
+  key.dev = current_device();
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) { *tm = it->second; ++g_tmap_hits; return CETPICK_OK; }
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
   cuuint64_t d[5], st[4];
   cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
+  CUresult r = enc(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, oob);
+  if (r != CUDA_SUCCESS) {
+    g_cuda_err = std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r);
+    return CETPICK_ERR_CUDA;
+  }
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (g_tmaps.size() >= TMAP_CACHE_MAX) g_tmaps.clear();
+  g_tmaps.emplace(key, *tm);
+  ++g_tmap_misses;
   return CETPICK_OK;
+}
+}  // namespace
+
+void tmap_cache_stats(int64_t* hits, int64_t* misses) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (hits) *hits = g_tmap_hits;
+  if (misses) *misses = g_tmap_misses;
+}
+
+// bf16 tiled tensor map whose innermost box dimension is KC channels (= the swizzle span)
+int tmap_encode_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int KC) {
+  return tmap_encode_any(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle_of(KC),
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE, "bf16");
 }
 
 // fp32 tiled tensor map, no swizzle, out-of-bounds elements read as NaN (decode: fmaxf ignores them)
 int tmap_encode_f32_nanfill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                             const uint64_t* strides_bytes, const uint32_t* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
-  cuuint64_t d[5], st[4];
-  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
-  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
-  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(f32) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
-  return CETPICK_OK;
+  return tmap_encode_any(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA, "f32 nan-fill");
 }
 
 // fp32 tiled tensor map, no swizzle, out-of-bounds elements read as zero (stem: the conv's zero padding)
 int tmap_encode_f32_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
-  cuuint64_t d[5], st[4];
-  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
-  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(f32) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
-  return CETPICK_OK;
+  return tmap_encode_any(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE, "f32");
 }
 
 // uint8 tiled tensor map, no swizzle, out-of-bounds elements read as zero (quantised-input stem)
 int tmap_encode_u8_zerofill(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                             const uint64_t* strides_bytes, const uint32_t* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
-  cuuint64_t d[5], st[4];
-  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
-  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), d, st, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { g_cuda_err = "cuTensorMapEncodeTiled(u8) failed: " + std::to_string((int)r); return CETPICK_ERR_CUDA; }
-  return CETPICK_OK;
+  return tmap_encode_any(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE, "u8");
 }
 
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {

@@ -37,6 +37,8 @@ struct ConvLaunch {
 
 // bf16 tiled tensor map (rank <= 5) whose innermost box dimension is KC channels = the swizzle span
 // (KC 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B); out-of-bounds elements read as zero.
+// (hits, misses) of the process-wide tensor-map cache behind the tmap_encode_* helpers
+void tmap_cache_stats(int64_t* hits, int64_t* misses);
 int tmap_encode_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, int KC);
 

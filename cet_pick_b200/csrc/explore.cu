@@ -7,15 +7,13 @@
 // The Gaussians are `cetpick_pre_gauss1d_f64` (preproc.cu).
 //
 // Greedy suppression with double scores: the 64-bit (key,index) composite of the float32 version does not fit, so
-// candidates are compacted IN INDEX ORDER (cub select with a counting iterator), keyed with the monotone 64-bit
+// candidates are compacted IN INDEX ORDER (compact_flagged, sort.cu), keyed with the monotone 64-bit
 // image of the double, and sorted with a STABLE descending radix sort: equal scores keep ascending index order
 // (the canonical tie order of this repo; the reference's is numpy's unstable argsort).  The dependency rounds are
 // those of greedy_nms.cu.  Scores are returned as float32 like the reference's `scores` array (:61,68).
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include "sort.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -177,20 +175,14 @@ struct ExLayout {
 
 ExLayout ex_layout(size_t n_vox, size_t cap) {
   ExLayout L;
-  size_t t1 = 0, t2 = 0, t3 = 0;
-  const int nn = (int)std::min<size_t>(n_vox, 0x7fffffff), nc = (int)std::min<size_t>(cap, 0x7fffffff);
-  cub::CountingInputIterator<uint32_t> it(0u);
-  cub::DeviceSelect::Flagged(nullptr, t1, it, (const uint8_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr, nn);
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, t2, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                            (const uint32_t*)nullptr, (uint32_t*)nullptr, nc);
-  cub::DeviceSelect::Flagged(nullptr, t3, it, (const uint8_t*)nullptr, (uint32_t*)nullptr, (int*)nullptr, nc);
+  const size_t t1 = compact_tmp_bytes(n_vox), t2 = sort_tmp_bytes(cap, true), t3 = compact_tmp_bytes(cap);
   L.tmp_bytes = std::max(t1, std::max(t2, t3));
   size_t o = 0;
   L.off_ctr = o;    o = align_up(o + 64, 256);
   L.off_deltas = o; o = align_up(o + (size_t)EX_MAX_DELTAS * 8, 256);
   L.off_flag = o;   o = align_up(o + n_vox, 256);
   L.off_rank = o;   o = align_up(o + n_vox * 4, 256);
-  L.off_idx = o;    o = align_up(o + n_vox * 4, 256);      // cub select writes up to n entries before the count is known
+  L.off_idx = o;    o = align_up(o + n_vox * 4, 256);      // sized for every voxel: the count is only known on the device
   L.off_idx2 = o;   o = align_up(o + cap * 4, 256);
   L.off_keys = o;   o = align_up(o + cap * 8, 256);
   L.off_keys2 = o;  o = align_up(o + cap * 8, 256);
@@ -286,10 +278,8 @@ extern "C" int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, i
   CETPICK_CUDA(cudaMemcpyAsync(d_deltas, deltas.data(), deltas.size() * 8, cudaMemcpyHostToDevice, s));
   ex_flag_kernel<<<sms * 8, EX_THREADS, 0, s>>>(vol, n, threshold, flag, rank);
   CETPICK_LAUNCH_CHECK();
-  cub::CountingInputIterator<uint32_t> it(0u);
   size_t tb = L.tmp_bytes;
-  CETPICK_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, flag, idx, n_sel, (int)n, s));   // candidates in index order
-  ++g_launches;
+  if (int rc = compact_flagged(flag, (uint32_t)n, nullptr, nullptr, idx, n_sel, tmp, tb, s, nullptr)) return rc;   // candidates in index order
   int nc_i = 0;
   CETPICK_CUDA(cudaMemcpyAsync(&nc_i, n_sel, sizeof(int), cudaMemcpyDeviceToHost, s));
   CETPICK_CUDA(cudaStreamSynchronize(s));
@@ -302,8 +292,7 @@ extern "C" int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, i
   ex_key_kernel<<<gb, EX_THREADS, 0, s>>>(vol, idx, nc, keys);
   CETPICK_LAUNCH_CHECK();
   tb = L.tmp_bytes;
-  CETPICK_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, keys, keys2, idx, idx2, (int)nc, 0, 64, s));   // stable
-  ++g_launches;
+  if (int rc = radix_sort_desc_u64(keys, keys2, idx, idx2, nc, tmp, tb, s, nullptr)) return rc;   // stable
   ex_rank_kernel<<<gb, EX_THREADS, 0, s>>>(idx2, nc, rank, state);
   CETPICK_LAUNCH_CHECK();
   int rounds = 0;
@@ -324,8 +313,7 @@ extern "C" int cetpick_greedy_nms_f64(const double* vol, int64_t D, int64_t H, i
   ex_pickflag_kernel<<<gb, EX_THREADS, 0, s>>>(state, nc, pflag);
   CETPICK_LAUNCH_CHECK();
   tb = L.tmp_bytes;
-  CETPICK_CUDA(cub::DeviceSelect::Flagged(tmp, tb, it, pflag, pos, n_sel + 1, (int)nc, s));
-  ++g_launches;
+  if (int rc = compact_flagged(pflag, nc, nullptr, nullptr, pos, n_sel + 1, tmp, tb, s, nullptr)) return rc;
   ex_write_kernel<<<gb, EX_THREADS, 0, s>>>(pos, n_sel + 1, keys2, idx2, (int)H, (int)W, (long long)max_out, scores, coords);
   CETPICK_LAUNCH_CHECK();
   int np = 0;

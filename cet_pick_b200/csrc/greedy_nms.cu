@@ -17,12 +17,11 @@
 // dependency chains are a few tens of voxels long.
 //
 // Pipeline: compact (score > threshold) voxels into 64-bit composites (monotone key << 32 | ~index)
-// -> cub radix sort descending -> scatter ranks into a dense int32 map -> resolve rounds -> ordered
+// -> stable radix sort descending (sort.cu) -> scatter ranks into a dense int32 map -> resolve rounds -> ordered
 // compaction of the picks -> (score, x, y, z) writer.
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
+#include "sort.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -133,11 +132,7 @@ struct GnLayout {
 
 GnLayout gn_layout(size_t n_vox, size_t cap) {
   GnLayout L;
-  size_t sort_tmp = 0, sel_tmp = 0;
-  cub::DeviceRadixSort::SortKeysDescending(nullptr, sort_tmp, (const unsigned long long*)nullptr,
-                                           (unsigned long long*)nullptr, (int)std::min<size_t>(cap, 0x7fffffff));
-  cub::DeviceSelect::Flagged(nullptr, sel_tmp, (const unsigned long long*)nullptr, (const uint8_t*)nullptr,
-                             (unsigned long long*)nullptr, (int*)nullptr, (int)std::min<size_t>(cap, 0x7fffffff));
+  const size_t sort_tmp = sort_tmp_bytes(cap, false), sel_tmp = compact_tmp_bytes(cap);
   L.tmp_bytes = std::max(sort_tmp, sel_tmp);
   size_t o = 0;
   L.off_ctr = o;    o = align_up(o + sizeof(GnCounters), 256);
@@ -226,8 +221,7 @@ extern "C" int cetpick_greedy_nms_f32(const float* heat, int64_t D, int64_t H, i
   if (nc == 0) return CETPICK_OK;
 
   size_t tb = L.tmp_bytes;
-  CETPICK_CUDA(cub::DeviceRadixSort::SortKeysDescending(tmp, tb, cand, sorted, (int)nc, 0, 64, s));
-  ++g_launches;
+  if (int rc = radix_sort_desc_u64(cand, sorted, nullptr, nullptr, nc, tmp, tb, s, nullptr)) return rc;
   const int gb = (int)ceil_div<uint32_t>(nc, GN_THREADS);
   gn_rank_kernel<<<gb, GN_THREADS, 0, s>>>(sorted, nc, rank, state);
   CETPICK_LAUNCH_CHECK();
@@ -249,8 +243,7 @@ extern "C" int cetpick_greedy_nms_f32(const float* heat, int64_t D, int64_t H, i
   gn_flag_kernel<<<gb, GN_THREADS, 0, s>>>(state, nc, flags);
   CETPICK_LAUNCH_CHECK();
   tb = L.tmp_bytes;
-  CETPICK_CUDA(cub::DeviceSelect::Flagged(tmp, tb, sorted, flags, picks, n_pick, (int)nc, s));
-  ++g_launches;
+  if (int rc = compact_flagged(flags, nc, sorted, picks, nullptr, n_pick, tmp, tb, s, nullptr)) return rc;
   gn_write_kernel<<<gb, GN_THREADS, 0, s>>>(picks, n_pick, (int)H, (int)W, (long long)max_out, scores, coords);
   CETPICK_LAUNCH_CHECK();
   int np = 0;

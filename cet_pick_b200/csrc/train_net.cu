@@ -489,6 +489,108 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
   for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) dx[i] = (y[i] > 0.f) ? dy[i] : 0.f;
 }
 
+
+// Weight gradient as a tiled SGEMM with implicit im2col: dW[co][(tap, ci)] = sum_i dy[co][i] * X[(tap, ci)][i], i running
+// over the (slice, pixel) positions.  CTA tile BM output channels x BN (tap, ci) columns, K chunks of 32 positions staged in
+// shared memory (position-major rows, so a thread reads its 4 + 4 operands of a k step with two 16-byte loads), 4 x 4
+// accumulators per thread, split over the positions (blockIdx.z), fp32 atomics at the end.
+constexpr int GK = 32, G_THREADS = 256;
+template <int BM, int BN>
+__global__ void __launch_bounds__(G_THREADS) wgrad_gemm_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, const Geom g, const long long chunk) {
+  static_assert(BM * BN == 4096, "256 threads x (4 x 4)");
+  constexpr int A_PER = GK * BM / G_THREADS, B_PER = GK * BN / G_THREADS;
+  __shared__ __align__(16) float As[GK][BM + 4];
+  __shared__ __align__(16) float Bs[GK][BN + 4];
+  const int taps = g.kz * g.ky * g.kx, ntot = taps * g.Cin;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const long long hw = (long long)g.Ho * g.Wo, total = (long long)g.N * hw;
+  const long long i0 = (long long)blockIdx.z * chunk, i1 = min(total, i0 + chunk);
+  const int kk = threadIdx.x & 31, r0 = threadIdx.x >> 5;          // this thread stages position kk of every chunk
+  const int tm = threadIdx.x % (BM / 4), tn = threadIdx.x / (BM / 4);
+  // the B columns this thread stages: column -> (tap, ci) -> channel offset and tap displacement (fixed for the kernel)
+  long long coff[B_PER];
+  int cdz[B_PER], cdy[B_PER], cdx[B_PER];
+#pragma unroll
+  for (int j = 0; j < B_PER; ++j) {
+    const int col = n0 + r0 + 8 * j;
+    if (col < ntot) {
+      const int tap = col / g.Cin, ci = col - tap * g.Cin;
+      const int tz = tap / (g.ky * g.kx), ty = (tap / g.kx) % g.ky, tx = tap % g.kx;
+      coff[j] = (long long)ci * g.xs_c;
+      cdz[j] = tz * g.dz - g.pz; cdy[j] = ty * g.dy - g.py; cdx[j] = tx * g.dx - g.px;
+    } else {
+      coff[j] = -1; cdz[j] = cdy[j] = cdx[j] = 0;
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (long long k0 = i0; k0 < i1; k0 += GK) {
+    const long long i = k0 + kk;
+    const bool live = i < i1;
+    const int n = live ? (int)(i / hw) : 0, p = live ? (int)(i - (long long)n * hw) : 0;
+    const int oy = p / g.Wo, ox = p - oy * g.Wo;
+    const int crop0 = (n / g.zdepth) * g.zdepth;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      const int mm = r0 + 8 * j, co = m0 + mm;
+      As[kk][mm] = (live && co < g.Cout) ? __ldg(dy + (size_t)n * g.ys_n + (size_t)co * g.ys_c + p) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      float v = 0.f;
+      if (live && coff[j] >= 0) {
+        const int zin = n + cdz[j], iy = oy * g.stride + cdy[j], ix = ox * g.stride + cdx[j];
+        if (zin >= crop0 && zin < crop0 + g.zdepth && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          v = __ldg(x + (size_t)zin * g.xs_n + coff[j] + (size_t)iy * g.W + ix);
+      }
+      Bs[kk][r0 + 8 * j] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tn * 4]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]); acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]); acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]); acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]); acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int co = m0 + tm * 4 + a;
+    if (co >= g.Cout) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int col = n0 + tn * 4 + b;
+      if (col >= ntot || acc[a][b] == 0.f) continue;
+      const int tap = col / g.Cin, ci = col - tap * g.Cin;
+      atomicAdd(dw + ((size_t)co * g.Cin + ci) * taps + tap, acc[a][b]);
+    }
+  }
+}
+
+template <int BM, int BN>
+int launch_wgrad_gemm(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.Ho * g.Wo;
+  const int ntot = g.kz * g.ky * g.kx * g.Cin;
+  const int tiles = ceil_div(ntot, BN) * ceil_div(g.Cout, BM);
+  // a few waves of CTAs; chunks of at least 2048 positions (64 k steps of 32) per CTA
+  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(total, 2048), ceil_div<long long>(6LL * num_sms(), tiles)));
+  splits = std::min<long long>(splits, 65535);
+  long long chunk = ceil_div<long long>(total, splits);
+  chunk = ceil_div<long long>(chunk, GK) * GK;
+  splits = ceil_div<long long>(total, chunk);
+  wgrad_gemm_kernel<BM, BN><<<dim3(ceil_div(ntot, BN), ceil_div(g.Cout, BM), (unsigned)splits), G_THREADS, 0, s>>>(x, dy, dw, g, chunk);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
 bool geom_ok(const Geom* g) {
   return g && g->N > 0 && g->Cin > 0 && g->Cout > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kz > 0 && g->ky > 0 &&
          g->kx > 0 && g->dz > 0 && g->dy > 0 && g->dx > 0 && g->stride > 0 && g->zdepth > 0 && g->N % g->zdepth == 0 &&
@@ -559,6 +661,9 @@ extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, flo
   if (!x || !dy || !dw || !geom_ok(g)) return CETPICK_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int kz = g->kz, ky = g->ky, kx = g->kx;
+  // wide layers: tiled SGEMM with implicit im2col; the few-channel ends of the network (stem, hm) keep the direct kernel
+  if (g->Cout >= 64 && kz * ky * kx * g->Cin >= 64) return launch_wgrad_gemm<64, 64>(x, dy, dw, *g, s);
+  if (g->Cout >= 32 && kz * ky * kx * g->Cin >= 128) return launch_wgrad_gemm<32, 128>(x, dy, dw, *g, s);
   if (kz == 1 && ky == 3 && kx == 3) return launch_wgrad<1, 3, 3, 4, 2>(x, dy, dw, *g, s);
   if (kz == 3 && ky == 3 && kx == 3) return launch_wgrad<3, 3, 3, 2, 1>(x, dy, dw, *g, s);
   if (kz == 1 && ky == 7 && kx == 7) return launch_wgrad<1, 7, 7, 1, 1>(x, dy, dw, *g, s);

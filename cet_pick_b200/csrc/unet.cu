@@ -956,4 +956,10 @@ extern "C" int cetpick_conv_bf16(int nsrc, const void* src0, int C0, const void*
   return conv_tc_launch(L, static_cast<cudaStream_t>(stream));
 }
 
+// Test hook: counters of the tensor-map cache (conv_tc.cu)
+extern "C" int cetpick_tmap_cache_stats(int64_t* hits, int64_t* misses) {
+  tmap_cache_stats(hits, misses);
+  return CETPICK_OK;
+}
+
 #endif  // CETPICK_TEST_HOOKS

@@ -102,6 +102,10 @@ int cetpick_probe_mma_rate(int N, int KC, int sbo_a, int a_step, int ntap, int n
 int cetpick_probe_mma_rate2(int N, int KC, int sbo_a, int a_step, int ntap, int ndst, int iters,
                             float* out_cycles, int pairs, void* stream);
 
+/* (hits, misses) of the process-wide tensor-map cache: a forward repeated on the same plan, buffers and shape encodes no
+ * new CUtensorMap (csrc/conv_tc.cu). */
+int cetpick_tmap_cache_stats(int64_t* hits, int64_t* misses);
+
 /* Stage timing of the decode (scripts/decode_stages.py): cetpick_decode_f32 returns after stage n of its launch
  * sequence (1 init, 2 sample select, 3 sieve, 4 gated fall-backs + EQ pass, 5 tail kernel); 0 = all. */
 int cetpick_decode_set_stop_stage(int n);

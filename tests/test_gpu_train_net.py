@@ -45,7 +45,8 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("name,cin,cout,shape,zdepth", [
-    ("CONV3", 16, 32, (6, 33, 41), 1), ("CONV3", 64, 24, (3, 17, 20), 1), ("CONV1", 32, 32, (5, 19, 23), 1),
+    ("CONV3", 16, 32, (6, 33, 41), 1), ("CONV3", 64, 24, (3, 17, 20), 1), ("CONV3", 48, 80, (3, 9, 11), 1),
+    ("CONV3", 128, 256, (20, 8, 8), 1), ("CONV1", 32, 32, (5, 19, 23), 1),
     ("STEM", 1, 16, (4, 37, 50), 1), ("HEAD3D", 32, 32, (8, 21, 27), 4), ("HM", 32, 1, (6, 14, 18), 3)])
 def test_conv_forward_dgrad_wgrad(name, cin, cout, shape, zdepth):
     """conv_f32_kernel / flip_weights + conv / wgrad_f32_kernel against F.conv2d / F.conv3d and autograd."""

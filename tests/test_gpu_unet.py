@@ -324,3 +324,31 @@ def test_tf32_mode_medium_vs_oracle_and_bf16():
     again = np.abs(m(x.cuda())[-1]["hm"].cpu().numpy() - ref).max()
     print(f"heat-map max-abs error vs fp32 oracle: bf16 {e_bf16:.3e}, tf32 {e_tf32:.3e}")
     assert e_tf32 <= 1e-4 and e_bf16 <= HM_TOL and again == e_bf16
+
+
+def test_repeated_forward_reuses_cached_tensor_maps():
+    """A second forward of the same plan on the same input buffer and workspace encodes no new CUtensorMap: every
+    descriptor comes from the cache in csrc/conv_tc.cu (counters of the test library, which shares no state with the
+    product library: the forward below goes through the test twin)."""
+    import ctypes as C
+    from cet_pick_b200 import _lib
+    from cet_pick_b200.models.model import create_model
+    T = _lib.test_lib()
+    old = _lib.lib
+    _lib.lib = lambda: T
+    try:
+        m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+        m.load_state_dict(synth.unet_state_dict_torch(5, 4))
+        m = m.cuda().eval()
+        x = synth.tomogram_torch(6, 96, 160, seed=1, device="cuda")[None]
+        h, mi = C.c_int64(0), C.c_int64(0)
+        a = m(x)[-1]["hm"].clone()
+        T.cetpick_tmap_cache_stats(C.byref(h), C.byref(mi))
+        h1, m1 = h.value, mi.value
+        b = m(x)[-1]["hm"]
+        T.cetpick_tmap_cache_stats(C.byref(h), C.byref(mi))
+        assert mi.value == m1 and h.value - h1 >= 20, (h1, m1, h.value, mi.value)
+        assert torch.equal(a, b)
+        m._destroy_plan()
+    finally:
+        _lib.lib = old
