@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   // that step -> phantom slots (SL = S - 2).  COUT = 64: N = 192 UMMAs run at the tensor rate, a split costs nothing
   // in time (two UMMAs of N = 64 + 128) -> plain ring (SL = S) with the window split where it wraps.
   constexpr bool PHANTOM = COUT == 32;
+  // accumulator slots per M-tile and logical ring length: compile-time, so the slot arithmetic below is add / compare /
+  // multiply-shift instead of a runtime division (the issuer warp's scalar chain is what bounds the 32-channel layers)
+  constexpr int S_CT = (TMEM_COLS / (MT * COUT)) < MAX_SLOTS ? (TMEM_COLS / (MT * COUT)) : MAX_SLOTS;
+  constexpr uint32_t SL = PHANTOM ? S_CT - 2 : S_CT;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_afull[MAX_SLOTS], bar_aempty[MAX_SLOTS], bar_w;
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     // a slot is free again when BOTH epilogue groups are through with its row: MT = 2: each group drains its own M-tile;
     // MT = 1: one group drains, the other only observes the phase -- and must arrive too, or the issuer could start the
     // slot's next phase (and the one after) before the observer has looked, which a parity wait cannot tell apart
-    for (int s = 0; s < p.SL; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 8); }
+    for (int s = 0; s < (int)SL; ++s) { ptx::mbar_init(&bar_afull[s], 1); ptx::mbar_init(&bar_aempty[s], 8); }
     ptx::mbar_init(&bar_w, 1);
     ptx::fence_barrier_init();
   }
@@ -172,7 +176,11 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
 
-  const uint32_t SL = (uint32_t)p.SL;
+  // barrier addresses in the shared window, computed once
+  uint32_t a_full = ptx::smem_u32(bar_full), a_empty = ptx::smem_u32(bar_empty);
+  uint32_t a_afull = ptx::smem_u32(bar_afull), a_aempty = ptx::smem_u32(bar_aempty);
+  // (opaque to the compiler from here on: otherwise it re-derives each address -- S2UR SR_CgaCtaId + ULEA -- at every use)
+  asm volatile("" : "+r"(a_full), "+r"(a_empty), "+r"(a_afull), "+r"(a_aempty));
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -189,8 +197,8 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         for (int i = i_lo; i <= i_hi; ++i)
           for (int src = 0; src < p.nsrc; ++src)
             for (int c = 0; c < p.chunks; ++c) {
-              ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
-              ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(G::NBOX * G::BOX_BYTES));
+              ptx::mbar_wait_a(a_empty + 8u * (uint32_t)stage, phase ^ 1u);
+              ptx::mbar_arrive_expect_tx_a(a_full + 8u * (uint32_t)stage, (uint32_t)(G::NBOX * G::BOX_BYTES));
               uint8_t* dst = sA + (size_t)stage * G::STAGE_BYTES;
               if (MODE == MARCH_2D_ROWS)
                 for (int t = 0; t < MT; ++t)
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
     constexpr uint32_t A_HI = ptx::smem_desc_hi(G::SBO_A, G::LAYOUT), B_HI = ptx::smem_desc_hi(G::SBO_B, G::LAYOUT);
     constexpr uint32_t IDESC0 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     const uint32_t sW_lo = ptx::smem_desc_lo(ptx::smem_u32(sW)), sA_lo = ptx::smem_desc_lo(ptx::smem_u32(sA));
-    const uint32_t tile_cols = (uint32_t)(p.S * COUT);
+    constexpr uint32_t tile_cols = (uint32_t)(S_CT * COUT);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t umask = 0;      // bit s: parity of the number of rows that have used logical slot s
@@ -219,17 +227,21 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
       decode_strip<MODE, MT>(p, k, s);
       const int i_lo = max(s.ma - 1, 0), i_hi = min(s.mb, p.L - 1);
       int r_touched = s.ma;
+      // running slots (no division in the row loop): sl_t = slot of row r_touched, sl_p = slot of row i - 1
+      uint32_t sl_t = ((uint32_t)s.ma + org) % SL;
+      uint32_t sl_p = ((uint32_t)i_lo + org + SL - 1u) % SL;
       for (int i = i_lo; i <= i_hi; ++i) {
         const int r_lo = max(s.ma, i - 1), r_hi = min(s.mb - 1, i + 1);
         const int n = r_hi - r_lo + 1;
         for (; r_touched <= r_hi; ++r_touched) {    // rows touched for the first time: slot must be drained
-          const uint32_t sl = ((uint32_t)r_touched + org) % SL;
-          ptx::mbar_wait(&bar_aempty[sl], ((umask >> sl) & 1u) ^ 1u);
-          umask ^= 1u << sl;
+          ptx::mbar_wait_a(a_aempty + 8u * sl_t, ((umask >> sl_t) & 1u) ^ 1u);
+          umask ^= 1u << sl_t;
+          sl_t = (sl_t + 1u == SL) ? 0u : sl_t + 1u;
         }
         // the window starts at the home slot of row i-1 and runs on into the phantom slots: no wrap, and a
         // row's partial sums land in the same places wherever the strip starts
-        const uint32_t s_lo = (((uint32_t)i + org + SL - 1u) % SL + (uint32_t)(r_lo - (i - 1))) % (PHANTOM ? 0xffffffffu : SL);
+        uint32_t s_lo = sl_p + (uint32_t)(r_lo - (i - 1));
+        if (!PHANTOM && s_lo >= SL) s_lo -= SL;
         const int n1 = PHANTOM ? n : min(n, (int)(SL - s_lo)), n2 = n - n1;     // plain ring: the wrap splits the columns
         const uint32_t id1 = IDESC0 | ((uint32_t)(n1 * COUT >> 3) << 17), id2 = IDESC0 | ((uint32_t)(n2 * COUT >> 3) << 17);
         const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
         for (int src = 0; src < p.nsrc; ++src)
           for (int c = 0; c < p.chunks; ++c) {
-            ptx::mbar_wait(&bar_full[stage], phase);
+            ptx::mbar_wait_a(a_full + 8u * (uint32_t)stage, phase);
             ptx::tc_fence_after();
             const uint32_t a_lo = sA_lo + (uint32_t)(stage * (G::STAGE_BYTES >> 4));
             const uint32_t w_lo = sW_lo + (uint32_t)((src * p.chunks + c) * G::T * (G::WBLK >> 4));
@@ -255,17 +267,19 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
                       ptx::umma_bf16_lohi(d2 + t * tile_cols, a_lo + (G::aoff(t, j, kk) >> 4), A_HI,
                                           w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
                   }
-              ptx::umma_commit(&bar_empty[stage]);
+              ptx::umma_commit_a(a_empty + 8u * (uint32_t)stage);
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         // rows that have now seen all three of their input rows
+        const uint32_t sl_i = (sl_p + 1u == SL) ? 0u : sl_p + 1u;     // slot of row i
         if (ptx::elect_one()) {
-          if (i - 1 >= s.ma) ptx::umma_commit(&bar_afull[((uint32_t)(i - 1) + org) % SL]);
-          if (i == p.L - 1 && i < s.mb) ptx::umma_commit(&bar_afull[((uint32_t)i + org) % SL]);
+          if (i - 1 >= s.ma) ptx::umma_commit_a(a_afull + 8u * sl_p);
+          if (i == p.L - 1 && i < s.mb) ptx::umma_commit_a(a_afull + 8u * sl_i);
         }
         __syncwarp();
+        sl_p = sl_i;
       }
     }
   } else if (warp >= 4) {
@@ -292,13 +306,13 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           // (every group observes every phase of a slot's barrier, also for rows / tiles the other group drains:
           // a parity wait only tells the current phase from the one before it, and a group that skipped a phase
           // could run two phases ahead across a strip boundary and take the stale parity for "done")
-          ptx::mbar_wait(&bar_afull[slot], par);
+          ptx::mbar_wait_a(a_afull + 8u * slot, par);
           if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) {
-            if (MT == 1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive(&bar_aempty[slot]); }   // observed: see bar_aempty's init
+            if (MT == 1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive_a(a_aempty + 8u * slot); }   // observed: see bar_aempty's init
             continue;
           }
           ptx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * p.S + (int)slot) * COUT);
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((t * S_CT + (int)slot) * COUT);
           uint32_t v[COUT];
           __syncwarp();
 #pragma unroll
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bar_aempty[slot]);
+          if (lane == 0) ptx::mbar_arrive_a(a_aempty + 8u * slot);
 
           int x, y, z;
           if (MODE == MARCH_2D_ROWS) { x = s.x0 + t * 128 + m; y = r; z = s.img; }
