@@ -1080,7 +1080,10 @@ __global__ void __launch_bounds__(SIEVE_THREADS, CTAS) sieve_kernel(const __grid
 // one kernel whose CTAs are all resident (grid <= SM count) and meet at a counting barrier in the decode state.
 // ---------------------------------------------------------------------------------------------
 constexpr int TAIL_THREADS = 512;
-constexpr int TAIL_DIGITS = 6;
+// select digit: 11 bits a pass.  (14-bit digits -- histogram in the dynamic shared memory of the ordering phase -- were
+// measured: the tie-free map still needs two passes, its K-th refine bin spans 2^15 keys, and a pass got twice as slow.)
+constexpr int TAIL_BITS = 11, TAIL_BINS = 1 << TAIL_BITS;
+constexpr int TAIL_DIGITS = 6;                             // ceil(64 / 11) passes at most
 constexpr int RANK_BINS = 4096;        // buckets of the ordering phase (linear in the composite)
 
 __device__ __forceinline__ void write_pick(unsigned long long c, int r, const float* __restrict__ heat,
@@ -1106,6 +1109,17 @@ __device__ __forceinline__ void write_pick(unsigned long long c, int r, const fl
   if (inds) inds[r] = (long long)idx;
 }
 
+#ifdef CETPICK_TEST_HOOKS
+__device__ __forceinline__ unsigned long long tail_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TAIL_STAMP(var) const unsigned long long var = tail_now()
+#else
+#define TAIL_STAMP(var) const unsigned long long var = 0ull
+#endif
+
 // all CTAs of the grid (co-resident) have arrived `phase` times
 __device__ __forceinline__ void tail_grid_sync(uint32_t* ctr, uint32_t& phase) {
   ++phase;
@@ -1128,6 +1142,30 @@ __device__ __forceinline__ int rank_bin(unsigned long long c, unsigned long long
   return min(RANK_BINS - 1, (int)f);
 }
 
+
+// Block-wide descending scan over nb = PER * TAIL_THREADS bins in shared memory (thread t owns the PER bins just below
+// nb - PER * t): returns the number of elements in bins ABOVE this thread's first bin; s_part needs TAIL_THREADS / 32 words.
+template <int PER>
+__device__ __forceinline__ uint32_t tail_scan_above(const uint32_t* __restrict__ bins, int nb, uint32_t* s_part, uint32_t& mine) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) sum += bins[nb - 1 - (int)threadIdx.x * PER - i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += s_part[w];
+  mine = sum;
+  __syncthreads();
+  return before + incl - sum;
+}
+
 // Phases (every CTA takes the same branches: all decisions come from state written before a barrier):
 //   1. unless the sieve already fixed the selection (fast final select, csel_done == 2): radix select of the K-th
 //      largest composite, 11 bits a pass, starting from the bin the sieve's histogram put the K-th key in when it has
@@ -1138,18 +1176,19 @@ __device__ __forceinline__ int rank_bin(unsigned long long c, unsigned long long
 //      buckets + bucket peers that are greater (one warp per element, 32 lanes over the peers: a bucket swollen by
 //      tied scores is still shared out over the whole grid), and writes the pick row (rank < K).
 __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long long* __restrict__ cand, DecodeState* st,
-                                                            uint32_t* thist /*[TAIL_DIGITS][HIST_BINS], zeroed*/,
+                                                            uint32_t* thist /*[TAIL_DIGITS][TAIL_BINS], zeroed*/,
                                                             unsigned long long* out, uint32_t cap_total, int K, int do_rank,
                                                             const float* __restrict__ heat, const float* __restrict__ reg,
                                                             int D, int H, int W, float* __restrict__ dets,
                                                             long long* __restrict__ inds) {
   extern __shared__ __align__(16) unsigned char tail_smem[];
-  __shared__ uint32_t s_hist[HIST_BINS];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(tail_smem);   // [TAIL_BINS], select phase only
   __shared__ uint32_t s_sel[3];
-  __shared__ unsigned long long s_max;
+  __shared__ uint32_t s_part[TAIL_THREADS / 32];
   uint32_t phase = 0;
   const uint32_t n = min(st->cand_count, cap_total);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TAIL_STAMP(ts0);
   unsigned long long kth;
   uint32_t n_sel;
   if (st->csel_done == 2) {                 // fast final select: every composite with key >= the bin edge
@@ -1168,9 +1207,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
     kth = 0ull;
     int npass = 0;
     for (int d = 0; d < TAIL_DIGITS; ++d) {
-      const int bits = min(11, wl), shift = wl - bits;
-      uint32_t* gh = thist + d * HIST_BINS;
-      for (int i = threadIdx.x; i < HIST_BINS; i += TAIL_THREADS) s_hist[i] = 0;
+      const int bits = min(TAIL_BITS, wl), shift = wl - bits;
+      uint32_t* gh = thist + d * TAIL_BINS;
+      for (int i = threadIdx.x; i < TAIL_BINS; i += TAIL_THREADS) s_hist[i] = 0;
       __syncthreads();
       for (uint32_t i0 = blockIdx.x * TAIL_THREADS; i0 < n; i0 += gridDim.x * TAIL_THREADS) {   // CTA-uniform trip count
         const uint32_t i = i0 + threadIdx.x;
@@ -1188,32 +1227,24 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
         if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
       tail_grid_sync(&st->tail_bar, phase);
       // every CTA resolves the digit itself (same bins, same answer): no second barrier
-      for (int i = threadIdx.x; i < HIST_BINS; i += TAIL_THREADS) s_hist[i] = (i < (1 << bits)) ? __ldcg(&gh[i]) : 0u;
+      for (int i = threadIdx.x; i < TAIL_BINS; i += TAIL_THREADS) s_hist[i] = (i < (1 << bits)) ? __ldcg(&gh[i]) : 0u;
       __syncthreads();
-      if (threadIdx.x < 32) {
-        const int nb = max(32, 1 << bits), per = nb / 32;      // (bins beyond 2^bits are zero)
-        uint32_t sum = 0;
-        for (int i = 0; i < per; ++i) sum += s_hist[nb - 1 - lane * per - i];
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const uint32_t excl = incl - sum;
-        const bool mine = (excl < kleft) && (incl >= kleft);
-        const unsigned who = __ballot_sync(0xffffffffu, mine);
-        if (who == 0) {                       // fewer than kleft elements in the class (cannot happen: K <= candidates)
-          if (lane == 0) { s_sel[0] = 0; s_sel[1] = 0xffffffffu; s_sel[2] = 0; }
-        } else if (lane == __ffs(who) - 1) {
-          uint32_t cum = excl;
-          int b = nb - 1 - lane * per;
-          for (int i = 0; i < per; ++i, --b) {
-            const uint32_t h = s_hist[b];
+      {
+        // all 512 threads: 4 bins each, from the top (bins beyond 2^bits are zero)
+        uint32_t own;
+        const uint32_t above = tail_scan_above<TAIL_BINS / TAIL_THREADS>(s_hist, TAIL_BINS, s_part, own);
+        if (threadIdx.x == 0) { s_sel[0] = 0; s_sel[1] = 0xffffffffu; s_sel[2] = 0; }   // fewer than kleft in the class: cannot happen
+        __syncthreads();
+        if (above < kleft && above + own >= kleft) {
+          uint32_t cum = above;
+          int bb = TAIL_BINS - 1 - (int)threadIdx.x * (TAIL_BINS / TAIL_THREADS);
+          for (int i = 0; i < TAIL_BINS / TAIL_THREADS; ++i, --bb) {
+            const uint32_t h = s_hist[bb];
             if (cum + h >= kleft) break;
             cum += h;
           }
-          s_sel[0] = (uint32_t)b; s_sel[1] = kleft - cum; s_sel[2] = s_hist[b];
+          // bins are stored at their digit's index; the histogram occupies [0, 2^bits): digit = bb
+          s_sel[0] = (uint32_t)bb; s_sel[1] = kleft - cum; s_sel[2] = s_hist[bb];
         }
       }
       __syncthreads();
@@ -1234,6 +1265,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_final = n; st->n_sel = n_sel; st->kth_comp = kth; st->sel_kleft = (uint32_t)npass; }
   }
 
+  TAIL_STAMP(ts1);
   // ---- compaction (order irrelevant: the ordering phase ranks by value) and the maximum
   {
     unsigned long long mx = 0ull;
@@ -1259,6 +1291,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
   }
   if (!do_rank) return;                       // K > RANK_MAX_K: sort_write_kernel orders the K composites
   tail_grid_sync(&st->tail_bar, phase);
+  TAIL_STAMP(ts2);
 
   // ---- ordering by counting
   unsigned long long* s_sorted = reinterpret_cast<unsigned long long*>(tail_smem);            // [RANK_MAX_K]
@@ -1271,19 +1304,13 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < m; i += TAIL_THREADS) atomicAdd(&s_above[rank_bin(__ldcg(&out[i]), kth, scale)], 1u);
   __syncthreads();
-  if (warp == 0) {                            // s_above[b] <- number of elements in buckets above b
-    constexpr int PER = RANK_BINS / 32;
-    uint32_t sum = 0;
-    for (int i = 0; i < PER; ++i) sum += s_above[RANK_BINS - 1 - lane * PER - i];
-    uint32_t incl = sum;
+  {                                           // s_above[b] <- number of elements in buckets above b (all threads, 8 buckets each)
+    constexpr int PER = RANK_BINS / TAIL_THREADS;
+    uint32_t own;
+    uint32_t run = tail_scan_above<PER>(s_above, RANK_BINS, s_part, own);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    uint32_t run = incl - sum;
     for (int i = 0; i < PER; ++i) {
-      const int b = RANK_BINS - 1 - lane * PER - i;
+      const int b = RANK_BINS - 1 - (int)threadIdx.x * PER - i;
       const uint32_t h = s_above[b];
       s_above[b] = run;
       run += h;
@@ -1312,6 +1339,14 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const unsigned long 
     const uint32_t r = lo + g;
     if (lane == 0 && r < (uint32_t)K) write_pick(c, (int)r, heat, reg, n_vox, H * W, W, dets, inds);
   }
+#ifdef CETPICK_TEST_HOOKS
+  // phase times of CTA 0 in ns, into state words that are dead by now (scripts/decode_stages.py reads them)
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long ts3 = tail_now();
+    st->sel_prefix = (uint32_t)(ts1 - ts0); st->n_gt = (uint32_t)(ts2 - ts1); st->hit_total = (uint32_t)(ts3 - ts2);
+  }
+#endif
 }
 
 // One CTA: bitonic sort (descending) of K composites, then the pick writer
@@ -1427,7 +1462,7 @@ WsLayout ws_layout(int64_t D, int64_t H, int64_t W, int K) {
   L.off_rhist = o; o = align_up(o + (size_t)REFINE_BINS * sizeof(uint32_t), 256);
   L.off_cand = o;  o = align_up(o + (size_t)L.cap_total * 8, 256);
   L.off_out = o;   o = align_up(o + (size_t)std::max(npad, RANK_MAX_K) * 8, 256);
-  L.off_thist = o; o = align_up(o + (size_t)TAIL_DIGITS * HIST_BINS * sizeof(uint32_t), 256);
+  L.off_thist = o; o = align_up(o + (size_t)TAIL_DIGITS * TAIL_BINS * sizeof(uint32_t), 256);
   L.total = o;
   return L;
 }
@@ -1512,7 +1547,7 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
 
   uint32_t* thist = reinterpret_cast<uint32_t*>(base + L.off_thist);
   uint32_t* rhist = reinterpret_cast<uint32_t*>(base + L.off_rhist);
-  init_state_kernel<<<ceil_div(std::max(D, HIST_BINS), 256), 256, 0, s>>>(st, hist, eqcnt, D, 0u, thist, TAIL_DIGITS * HIST_BINS, rhist);
+  init_state_kernel<<<std::max(32, ceil_div(std::max(D, HIST_BINS), 256)), 256, 0, s>>>(st, hist, eqcnt, D, 0u, thist, TAIL_DIGITS * TAIL_BINS, rhist);
   CETPICK_LAUNCH_CHECK();
   CETPICK_STAGE(1);
 
@@ -1593,7 +1628,7 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
   CETPICK_STAGE(4);
   {  // exact K-th composite, compaction and (K <= RANK_MAX_K) ordering + pick rows: one launch
     const int do_rank = K <= RANK_MAX_K;
-    const size_t smem = do_rank ? (size_t)RANK_MAX_K * 8 + 2 * (size_t)RANK_BINS * 4 : 0;
+    const size_t smem = std::max<size_t>((size_t)TAIL_BINS * 4, do_rank ? (size_t)RANK_MAX_K * 8 + 2 * (size_t)RANK_BINS * 4 : 0);
     static DeviceOnce attr_once;
     if (attr_once.first()) {
       CETPICK_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -174,5 +174,5 @@ def decode_debug_state(device=None):
     _lib.check(_lib.lib().cetpick_decode_debug_state(ws_ptr, _lib.stream_ptr(), out), "decode_debug_state")
     names = ["t0key", "sel_prefix", "sel_kleft", "flags", "cand_count", "n_gt", "need_fallback", "eq_need",
              "eq_zc", "done_ctr", "csel_kleft", "out_count", "csel_prefix_lo", "csel_prefix_hi", "kth_comp_lo",
-             "kth_comp_hi", "n_final", "csel_done", "n_real", "t_run", "hit_total", "dense", "need_dense", "n_sel"]
+             "kth_comp_hi", "n_final", "csel_done", "n_real", "t_run", "hit_total", "dense", "need_dense", "csel_wl"]
     return {n: int(out[i]) for i, n in enumerate(names)}

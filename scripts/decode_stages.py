@@ -60,6 +60,10 @@ def main():
         print(f"stage {n} {STAGES[n]:32s} cumulative {t * 1e3:8.1f} us   stage {1e3 * (t - prev):8.1f} us")
         prev = t
     print(f"whole decode {full * 1e3:8.1f} us")
+    d = dec.decode_debug_state()
+    print(f"tail kernel, CTA 0 (ns): select {d['sel_prefix']} ({d['sel_kleft']} passes, csel_done {d['csel_done']}), "
+          f"compaction + barrier {d['n_gt']}, ordering + rows {d['hit_total']}; candidates {d['n_final']}; "
+          f"class width 2^{d['csel_wl']}, rank inside {d['csel_kleft']}, t0key {d['t0key']:#x}, kth key {d['kth_comp_hi']:#x}, t_run {d['t_run']:#x}")
     T.cetpick_decode_set_stop_stage(0)
 
 
