@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
         const uint32_t boff2 = boff1 + (uint32_t)n1 * (G::SLOT_BYTES >> 4);
         const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
-        const uint32_t sl_i = (sl_p + 1u == SL) ? 0u : sl_p + 1u;     // slot of row i
         for (int src = 0; src < p.nsrc; ++src)
           for (int c = 0; c < p.chunks; ++c) {
             ptx::mbar_wait_a(a_full + 8u * (uint32_t)stage, phase);
@@ -269,16 +268,20 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
                                           w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
                   }
               ptx::umma_commit_a(a_empty + 8u * (uint32_t)stage);
-              if (src == p.nsrc - 1 && c == p.chunks - 1) {
-                // last operand block of input row i: the rows that have now seen all three of their input rows
-                // (same election as the UMMAs: one ELECT / reconvergence per row instead of two)
-                if (i - 1 >= s.ma) ptx::umma_commit_a(a_afull + 8u * sl_p);
-                if (i == p.L - 1 && i < s.mb) ptx::umma_commit_a(a_afull + 8u * sl_i);
-              }
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+        // rows that have now seen all three of their input rows.  (Folding these commits into the election of the last
+        // operand block above saves an ELECT / reconvergence per row and measured 3 % on the 32-channel layers, but
+        // that build dead-locked intermittently in slab mode -- 4 of 6 runs of test_config0_full_size_vs_oracle, cause
+        // not found -- while this form ran 40 / 40: kept.)
+        const uint32_t sl_i = (sl_p + 1u == SL) ? 0u : sl_p + 1u;     // slot of row i
+        if (ptx::elect_one()) {
+          if (i - 1 >= s.ma) ptx::umma_commit_a(a_afull + 8u * sl_p);
+          if (i == p.L - 1 && i < s.mb) ptx::umma_commit_a(a_afull + 8u * sl_i);
+        }
+        __syncwarp();
         sl_p = sl_i;
       }
     }

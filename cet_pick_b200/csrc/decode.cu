@@ -63,6 +63,8 @@ struct DecodeState {
   uint32_t hit_total;     // sieve: voxels >= threshold queued so far (reported in batches)
   uint32_t dense;         // sieve: hit density too high for the hit-by-hit path: bail out
   uint32_t need_dense;    // set by the sieve's last CTA: scan_kernel COLLECT (gate 2) takes over with the same t0
+  uint32_t slist_count;   // sample pass: keys appended to the sample list
+  uint32_t sample_zero;   // sample pass: voxels whose NMS output is (the key of) zero
   uint32_t csel_wl;       // csel_done == 3: log2 width of the composite class [csel_prefix, +2^wl) holding the K-th one
   uint32_t tail_bar;      // tail_kernel: arrivals at its grid barrier
   unsigned long long cmax; // tail_kernel: largest selected composite
@@ -95,6 +97,7 @@ struct alignas(64) ScanParams {
   uint32_t* eqcnt;     // D per-plane counts of o == t0
   uint32_t* rhist;     // sieve: REFINE_BINS counts of appended candidates by distance of their key from t0
   unsigned long long* cand;
+  uint32_t* slist;     // HIST on the sample, first pass: also append every non-zero survivor key here (null = off)
 };
 
 __device__ __forceinline__ uint32_t f2key(float v) {
@@ -562,6 +565,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
         uint32_t n_eq = 0;
         if (!zgen) {
           if (mode == MODE_HIST) {
+            if (p.slist) {      // sample list: the second select pass reads these keys instead of repeating the stencil
+              uint32_t cnt = 0;
+              for (uint32_t m = mask; m; m &= m - 1) cnt += (f2key(centre(__ffs(m) - 1)) != KEY_ZERO) ? 1u : 0u;
+              uint32_t incl = cnt;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+              }
+              uint32_t base = 0;
+              if (lane == 31 && incl) base = atomicAdd(&st->slist_count, incl);
+              base = __shfl_sync(0xffffffffu, base, 31);
+              uint32_t o = base + incl - cnt;
+              for (uint32_t m = mask; m; m &= m - 1) {
+                const uint32_t ok = f2key(centre(__ffs(m) - 1));
+                if (ok != KEY_ZERO) p.slist[o++] = ok;
+              }
+            }
             zero_cnt += __popc(vmask) - __popc(mask);
             // Plateau maps put most survivors of a thread, and of a warp, into ONE bin: run-length compress per
             // thread, then one shared-memory atomic per distinct bin of the warp (a 32 x 16-way serialised
@@ -683,6 +704,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
 
   // ---- publish and let the last CTA take the decision for the next kernel ----
   if (mode == MODE_HIST) {
+    if (p.slist) {
+      const uint32_t wz = __reduce_add_sync(0xffffffffu, zero_cnt);
+      if ((threadIdx.x & 31) == 0 && wz) atomicAdd(&st->sample_zero, wz);
+    }
     if (zero_cnt && (hs >= 32 || (KEY_ZERO >> hs) == prefix))
       atomicAdd(&s_hist[(KEY_ZERO >> p.shift) & dmask], zero_cnt);
     __syncthreads();
@@ -727,6 +752,64 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const __grid_cons
     }
   } else {  // MODE_COLLECT: plan the EQ pass
     if (threadIdx.x == 0) collect_plan(p, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Second pass of the sample select, from the key list the first pass appended (instead of a second stencil pass over
+// the sample planes): 11 more key bits among the keys that carry the first pass's digit.  Same decisions as the
+// last HIST pass of scan_kernel (t0 = lower edge of the K-th key's 22-bit bin; dense / fall-back hand-over).
+// ---------------------------------------------------------------------------------------------
+constexpr int SL_THREADS = 512, SL_GRID = 64;
+__global__ void __launch_bounds__(SL_THREADS) sample_list_kernel(const __grid_constant__ ScanParams p) {
+  __shared__ uint32_t s_hist[HIST_BINS];
+  __shared__ uint32_t s_sel[3];
+  __shared__ uint32_t s_ticket;
+  DecodeState* st = p.st;
+  const uint32_t n = st->slist_count;
+  const uint32_t prefix = st->sel_prefix;          // the first pass's digit (top 11 key bits)
+  const uint32_t dmask = (1u << p.bits) - 1u;
+  const int hs = p.shift + p.bits, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < HIST_BINS; i += SL_THREADS) s_hist[i] = 0;
+  __syncthreads();
+  for (uint32_t i0 = blockIdx.x * SL_THREADS; i0 < n; i0 += gridDim.x * SL_THREADS) {   // CTA-uniform trip count
+    const uint32_t i = i0 + threadIdx.x;
+    const uint32_t k = (i < n) ? p.slist[i] : 0u;
+    const bool in = (i < n) && (k >> hs) == prefix;
+    // plateau maps: whole warps carry one key -> one shared-memory atomic per group of equal bins
+    const uint32_t bin = in ? ((k >> p.shift) & dmask) : (0x80000000u | (uint32_t)lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (in && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIST_BINS; i += SL_THREADS)
+    if (s_hist[i]) atomicAdd(&p.hist[i], s_hist[i]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&st->done_ctr, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  // the sample's suppressed voxels all carry the key of zero
+  if (threadIdx.x == 0 && st->sample_zero && (KEY_ZERO >> hs) == prefix)
+    atomicAdd(&p.hist[(KEY_ZERO >> p.shift) & dmask], st->sample_zero);
+  __threadfence();
+  __syncthreads();
+  select_digit(p.hist, 1 << p.bits, st->sel_kleft, s_hist, s_sel);
+  if (threadIdx.x == 0) {
+    const uint32_t np = (prefix << p.bits) | s_sel[0];
+    st->sel_prefix = np;
+    st->sel_kleft = s_sel[1];
+    if (s_sel[1] == 0xffffffffu) atomicOr(&st->flags, (uint32_t)FLAG_INTERNAL);
+    if (s_sel[2] > 8u * (uint32_t)p.K) {            // see scan_kernel: plateaus, not peaks
+      if ((unsigned long long)s_sel[2] * (unsigned long long)p.sample_ratio > (unsigned long long)p.cap_gt) {
+        st->need_fallback = 1; st->flags |= FLAG_FALLBACK;
+      } else {
+        st->need_dense = 1;
+      }
+    }
+    st->t0key = np << p.shift;
+    st->done_ctr = 0;
   }
 }
 
@@ -1610,7 +1693,21 @@ int decode_one(const float* heat, int D, int H, int W, int kernel_xy, int K, int
     sp = std::max(sp, 1);
     const int zlo = (D - sp) / 2, zhi = zlo + sp;
     p.sample_ratio = (uint32_t)std::max<uint64_t>(1, n / ((uint64_t)sp * hw));
-    if ((rc = run_select(zlo, zhi, 0, 2))) return rc;
+    if (p.use_tma) {
+      // sample select: one stencil pass (top 11 key bits + the survivors' keys into a list), then 11 more bits from the list
+      ScanParams q = p;
+      q.mode = MODE_HIST; q.zlo = zlo; q.zhi = zhi; q.gate = 0;
+      q.shift = shifts[0]; q.bits = nbits[0]; q.last_pass = 0;
+      q.k_select = (uint32_t)K;
+      q.slist = reinterpret_cast<uint32_t*>(cand);          // the candidate list is not in use yet
+      const int grid = scan_grid(D, H, W, zlo, zhi, &q.ZC);
+      if ((rc = launch_scan_p(P, q, grid, s))) return rc;
+      q.shift = shifts[1]; q.bits = nbits[1]; q.last_pass = 1;
+      CETPICK_CUDA(launch_k(sample_list_kernel, dim3(SL_GRID), dim3(SL_THREADS), 0, s, q));
+      CETPICK_LAUNCH_CHECK();
+    } else if ((rc = run_select(zlo, zhi, 0, 2))) {
+      return rc;
+    }
     CETPICK_STAGE(2);
     if ((rc = run_collect(0, 0, 0))) return rc;
     CETPICK_STAGE(3);
