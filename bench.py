@@ -16,6 +16,7 @@ Legs (all inside one run; the extra ones are rank 0 / N = 1 only so the scaling 
   e2e            host uint8 levels in (pinned, 3 staging buffers) -> H2D -> forward -> decode -> picks D2H
   e2e_run        TomodetDetector.run(): the drop-in call incl. heat-map D2H and the <name>.txt / _hm.mrc files (tmpfs)
   roofline       tcgen05 conv kernels of one forward: median of 5 profiled forwards (+ frac_step at step level)
+  zshard_one_tomogram  (N > 1) one tomogram z-sharded over the ranks: slab forward + local decode + candidate merge
   train_config5    BASELINE.json configs[4]: training step on 128^3 crops (all ranks; gradient all-reduce + Adam)
   roofline_decode  BASELINE.json configs[2]: decode of a 512x1024x1024 map, K = 10 000, with a bit-exact self-check
   simsiam_config3  BASELINE.json configs[3]: SimSiam 3-D encoder embedding inference on 8192 sub-volumes of 32^3
@@ -230,6 +231,70 @@ def leg_roofline_decode(dev, pk, iters=10):
             "launches_per_decode": int(launches), "bit_exact_vs_torch_cuda": exact, "status_flags": int(flags),
             "torch_cuda_decode_ms": torch_ms, "speedup_vs_torch_cuda": torch_ms / mean_ms,
             "peak_source": pk["src"] + " HBM copy bandwidth", "gvoxels_per_sec": D * H * W / (mean_ms * 1e-3) / 1e9}
+
+
+def leg_zshard(dev, rank, world, model, shape, K, nms, iters=3):
+    """ONE tomogram whose z-slabs are spread over the ranks (north_star (3) for a volume that does not fit
+    or must come back fast): every rank forwards its slab with a 4-slice recompute halo, decodes its own core slices, one
+    all_gather of K candidates per rank, merge-select.  Collective: all ranks call this.  Reports the latency of one
+    tomogram (max over ranks) and, on rank 0, whether the picks equal the single-GPU decode of the whole volume."""
+    import torch
+    import torch.distributed as dist
+    import synthdata as synth
+    from cet_pick_b200.models.decode import tomo_decode
+    from cet_pick_b200.shard import decode_z_sharded
+    D, H, W = shape
+    vol = synth.tomogram_torch(D, H, W, seed=4242, device=dev)          # every rank would read only its slab from disk
+    ok = torch.ones(1, device=dev)
+    err = ""
+
+    def fwd(s, lo):
+        model.z_origin = lo
+        try:
+            return model(s[None])[-1]["hm"][0, 0]
+        finally:
+            model.z_origin = 0
+
+    def once():
+        return decode_z_sharded(fwd, lambda a, b: vol[a:b], D, K, nms)
+
+    dets = None
+    try:
+        fwd(vol[:8], 0)                                                 # local warm-up, no collective
+        torch.cuda.synchronize()
+    except Exception as e:
+        ok.zero_()
+        err = f"{type(e).__name__}: {e}"[:200]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) == 0:
+        return {"error": err or "another rank failed"}
+    once()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        dets = once()
+    t1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1) / iters], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out = {"workload": f"one {H}x{W}x{D} tomogram, z-slabs over {world} GPUs: slab forward (+4-slice recompute halo), local "
+                       f"decode of the own core slices, all_gather of K = {K} candidates per rank, merge-select",
+           "ms_per_tomogram": float(ms), "n_gpus": world, "exchange_bytes_per_rank": K * 12}
+    if rank == 0:
+        whole = model(vol[None])[-1]["hm"]
+        ref = tomo_decode(whole, kernel=nms, K=K)
+        t2, t3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t2.record()
+        ref = tomo_decode(model(vol[None])[-1]["hm"], kernel=nms, K=K)
+        t3.record()
+        torch.cuda.synchronize()
+        out["picks_identical_to_one_gpu"] = bool(torch.equal(dets.view(torch.int32), ref.view(torch.int32)))
+        out["one_gpu_ms_per_tomogram"] = t2.elapsed_time(t3)
+        out["speedup_vs_one_gpu"] = out["one_gpu_ms_per_tomogram"] / out["ms_per_tomogram"]
+    return out
 
 
 def leg_train(dev, rank, world, crops_per_rank=2, steps=3, with_torch=False):
@@ -741,6 +806,16 @@ def run_b200(a, rank, world, local_rank):
         finally:
             del our_hm
             torch.cuda.empty_cache()
+    # ---- one tomogram z-sharded over the ranks: collective, world > 1 only
+    if not a.no_extras and world > 1:
+        del pool[:]
+        torch.cuda.empty_cache()
+        try:
+            res = leg_zshard(dev, rank, world, model_w1, (D, H, W), a.K, a.nms)
+        except Exception as e:
+            res = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0:
+            line["zshard_one_tomogram"] = res
     # ---- training step (configs[4]): every rank takes part (the gradient all-reduce is the path's one collective)
     if not a.no_extras:
         del pool[:]

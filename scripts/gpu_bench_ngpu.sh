@@ -7,6 +7,6 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127
 echo "rc=$?"; python - <<PY
 import json
 j = json.loads(open("gpurun_out/${TAG}_bench_c2_${N}gpu.json").read().strip().splitlines()[-1])
-print({k: j[k] for k in ("n_gpus", "value", "value_w1", "ms_per_step")}, "e2e", j["e2e"]["value"], j["clocks"]); print("train_config5", j.get("train_config5"))
+print({k: j[k] for k in ("n_gpus", "value", "value_w1", "ms_per_step")}, "e2e", j["e2e"]["value"], j["clocks"]); print("train_config5", j.get("train_config5")); print("zshard", j.get("zshard_one_tomogram"))
 PY
 tail -3 gpurun_out/${TAG}_bench_${N}gpu.err
