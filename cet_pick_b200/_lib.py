@@ -68,6 +68,7 @@ SIGNATURES = {
     "cetpick_train_conv_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "cetpick_train_flip_weights_f32": (_int, [_vp, _vp, _int, _int, _int, _vp]),
     "cetpick_train_conv_wgrad_f32": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "cetpick_train_set_tf32": (_int, [_int]),
     "cetpick_train_upconv_f32": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "cetpick_train_net_workspace_bytes": (_int, [_int, C.POINTER(_sz)]),
     "cetpick_train_bn_f32": (_int, [_vp, _ll, _ll, _vp, _ll, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, C.c_float,

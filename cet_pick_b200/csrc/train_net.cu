@@ -14,8 +14,8 @@
 // Tensors are fp32 with DENSE rows and explicit (slice, channel) strides, so one buffer serves the 2-D trunk
 // ((D,C,h,w): slice = z) and the 3-D head ((C,D,h,w) read through the same strides): the reference's permutes
 // (unet_small.py:71,83-84) and the channel concat (unet.py:390) are views here, not copies.
-// This is the FIRST correct training path: CUDA-core fp32, gradients within 1e-3 of torch autograd.  The tensor-core
-// kernels of the inference path are not used here.
+// This is the FIRST correct training path: CUDA-core fp32 convolutions, TF32 mma.sync weight gradient (switchable).  The
+// tcgen05 kernels of the inference path are not used here (see DESIGN.md section 4.7 for accuracy and timing).
 #include "common.cuh"
 
 #include <algorithm>
@@ -591,6 +591,147 @@ int launch_wgrad_gemm(const float* x, const float* dy, float* dw, const Geom& g,
   return CETPICK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- TF32 tensor-core variant
+// Same tiling and implicit-im2col staging as wgrad_gemm_kernel, but the 32-position chunk is contracted with
+// mma.sync.m16n8k8 TF32 (fp32 accumulate): operands are rounded to TF32 (cvt.rna) when they are staged -- the arithmetic
+// class of the reference's own training (PyTorch's default cudnn.allow_tf32 = True).  8 warps: 2 x 4 (BM = 64) or 1 x 8
+// (BM = 32) warp tiles of 32 x 16; shared-memory rows are padded to a stride of 8 mod 32 words, so the fragment loads
+// (lane = 4 g + t reads row t / t + 4, column g / g + 8) hit 32 different banks.
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(G_THREADS) wgrad_mma_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dw, const Geom g, const long long chunk) {
+  static_assert(BM * BN == 4096 && (BM == 32 || BM == 64), "8 warps x (32 x 16)");
+  constexpr int A_PER = GK * BM / G_THREADS, B_PER = GK * BN / G_THREADS;
+  constexpr int LDA = BM + 8, LDB = BN + 8;
+  __shared__ __align__(16) uint32_t As[GK][LDA];
+  __shared__ __align__(16) uint32_t Bs[GK][LDB];
+  const int taps = g.kz * g.ky * g.kx, ntot = taps * g.Cin;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const long long hw = (long long)g.Ho * g.Wo, total = (long long)g.N * hw;
+  const long long i0 = (long long)blockIdx.z * chunk, i1 = min(total, i0 + chunk);
+  const int kk = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  constexpr int WM = BM / 32;                          // warps along m
+  const int mw = (warp % WM) * 32, nw = (warp / WM) * 16;
+  // per staged column: channel offset (elements; < 0 = no such column) and the tap displacement packed as three biased bytes
+  int coff[B_PER], dpk[B_PER];
+#pragma unroll
+  for (int j = 0; j < B_PER; ++j) {
+    const int col = n0 + r0 + 8 * j;
+    if (col < ntot) {
+      const int tap = col / g.Cin, ci = col - tap * g.Cin;
+      const int tz = tap / (g.ky * g.kx), ty = (tap / g.kx) % g.ky, tx = tap % g.kx;
+      coff[j] = (int)((long long)ci * g.xs_c);
+      dpk[j] = (tz * g.dz - g.pz + 64) | ((ty * g.dy - g.py + 64) << 8) | ((tx * g.dx - g.px + 64) << 16);
+    } else {
+      coff[j] = -1; dpk[j] = 0;
+    }
+  }
+  float acc[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  // software pipeline: the global loads of chunk k + 1 are in flight while chunk k is contracted
+  float ra[A_PER], rb[B_PER];
+  auto fetch = [&](long long k0) {
+    const long long i = k0 + kk;
+    const bool live = i < i1;
+    const int n = live ? (int)(i / hw) : 0, p = live ? (int)(i - (long long)n * hw) : 0;
+    const int oy = p / g.Wo, ox = p - oy * g.Wo;
+    const int crop0 = (n / g.zdepth) * g.zdepth;
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      const int co = m0 + r0 + 8 * j;
+      ra[j] = (live && co < g.Cout) ? __ldg(dy + (size_t)n * g.ys_n + (size_t)co * g.ys_c + p) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      float v = 0.f;
+      if (live && coff[j] >= 0) {
+        const int zin = n + (dpk[j] & 0xff) - 64, iy = oy * g.stride + ((dpk[j] >> 8) & 0xff) - 64;
+        const int ix = ox * g.stride + ((dpk[j] >> 16) & 0xff) - 64;
+        if (zin >= crop0 && zin < crop0 + g.zdepth && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          v = __ldg(x + (size_t)zin * g.xs_n + (size_t)coff[j] + (size_t)iy * g.W + ix);
+      }
+      rb[j] = v;
+    }
+  };
+  if (i0 < i1) fetch(i0);
+  for (long long k0 = i0; k0 < i1; k0 += GK) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) As[kk][r0 + 8 * j] = to_tf32(ra[j]);
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) Bs[kk][r0 + 8 * j] = to_tf32(rb[j]);
+    __syncthreads();
+    if (k0 + GK < i1) fetch(k0 + GK);
+#pragma unroll
+    for (int k8 = 0; k8 < GK; k8 += 8) {
+      uint32_t af[2][4], bf[2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int m = mw + mi * 16 + gq;
+        af[mi][0] = As[k8 + tq][m];     af[mi][1] = As[k8 + tq][m + 8];
+        af[mi][2] = As[k8 + tq + 4][m]; af[mi][3] = As[k8 + tq + 4][m + 8];
+      }
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int nn = nw + ni * 8 + gq;
+        bf[ni][0] = Bs[k8 + tq][nn]; bf[ni][1] = Bs[k8 + tq + 4][nn];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) mma_tf32(acc[mi][ni], af[mi], bf[ni]);
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int co = m0 + mw + mi * 16 + gq + ((c & 2) ? 8 : 0);
+        const int col = n0 + nw + ni * 8 + 2 * tq + (c & 1);
+        const float v = acc[mi][ni][c];
+        if (co >= g.Cout || col >= ntot || v == 0.f) continue;
+        const int tap = col / g.Cin, ci = col - tap * g.Cin;
+        atomicAdd(dw + ((size_t)co * g.Cin + ci) * taps + tap, v);
+      }
+}
+
+template <int BM, int BN>
+int launch_wgrad_mma(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
+  const long long total = (long long)g.N * g.Ho * g.Wo;
+  const int ntot = g.kz * g.ky * g.kx * g.Cin;
+  const int tiles = ceil_div(ntot, BN) * ceil_div(g.Cout, BM);
+  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(total, 2048), ceil_div<long long>(6LL * num_sms(), tiles)));
+  splits = std::min<long long>(splits, 65535);
+  long long chunk = ceil_div<long long>(total, splits);
+  chunk = ceil_div<long long>(chunk, GK) * GK;
+  splits = ceil_div<long long>(total, chunk);
+  wgrad_mma_kernel<BM, BN><<<dim3(ceil_div(ntot, BN), ceil_div(g.Cout, BM), (unsigned)splits), G_THREADS, 0, s>>>(x, dy, dw, g, chunk);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
+int g_train_tf32 = 1;      // 1: tensor-core (TF32) contraction in the wide layers' weight gradients; 0: fp32 FMA everywhere
+
 bool geom_ok(const Geom* g) {
   return g && g->N > 0 && g->Cin > 0 && g->Cout > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kz > 0 && g->ky > 0 &&
          g->kx > 0 && g->dz > 0 && g->dy > 0 && g->dx > 0 && g->stride > 0 && g->zdepth > 0 && g->N % g->zdepth == 0 &&
@@ -662,8 +803,12 @@ extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int kz = g->kz, ky = g->ky, kx = g->kx;
   // wide layers: tiled SGEMM with implicit im2col; the few-channel ends of the network (stem, hm) keep the direct kernel
-  if (g->Cout >= 64 && kz * ky * kx * g->Cin >= 64) return launch_wgrad_gemm<64, 64>(x, dy, dw, *g, s);
-  if (g->Cout >= 32 && kz * ky * kx * g->Cin >= 128) return launch_wgrad_gemm<32, 128>(x, dy, dw, *g, s);
+  const bool mma_ok = g_train_tf32 && (long long)g->Cin * g->xs_c < 0x7fffffffLL && g->pz < 64 && g->py < 64 && g->px < 64 &&
+                      (kz - 1) * g->dz < 64 && (ky - 1) * g->dy < 64 && (kx - 1) * g->dx < 64;
+  if (g->Cout >= 64 && kz * ky * kx * g->Cin >= 64)
+    return mma_ok ? launch_wgrad_mma<64, 64>(x, dy, dw, *g, s) : launch_wgrad_gemm<64, 64>(x, dy, dw, *g, s);
+  if (g->Cout >= 32 && kz * ky * kx * g->Cin >= 128)
+    return mma_ok ? launch_wgrad_mma<32, 128>(x, dy, dw, *g, s) : launch_wgrad_gemm<32, 128>(x, dy, dw, *g, s);
   if (kz == 1 && ky == 3 && kx == 3) return launch_wgrad<1, 3, 3, 4, 2>(x, dy, dw, *g, s);
   if (kz == 3 && ky == 3 && kx == 3) return launch_wgrad<3, 3, 3, 2, 1>(x, dy, dw, *g, s);
   if (kz == 1 && ky == 7 && kx == 7) return launch_wgrad<1, 7, 7, 1, 1>(x, dy, dw, *g, s);
@@ -671,6 +816,11 @@ extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, flo
   if (kz == 3 && ky == 1 && kx == 1) return launch_wgrad<3, 1, 1, 1, 8>(x, dy, dw, *g, s);
   if (kz == 1 && ky == 2 && kx == 2) return launch_wgrad<1, 2, 2, 4, 4>(x, dy, dw, *g, s);
   return CETPICK_ERR_UNSUPPORTED;
+}
+
+extern "C" int cetpick_train_set_tf32(int on) {
+  g_train_tf32 = on ? 1 : 0;
+  return CETPICK_OK;
 }
 
 extern "C" int cetpick_train_upconv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g,

@@ -292,6 +292,9 @@ int cetpick_train_flip_weights_f32(const float* w, float* wt, int Cout, int Cin,
  * CETPICK_ERR_UNSUPPORTED).  Sums in fp32 with atomics: order, hence the last bits, vary from run to run (like cuDNN's
  * default weight-gradient algorithms). */
 int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, float* dw, const cetpick_conv_geom* g, void* stream);
+/* 1 (default): the wide layers contract on the tensor cores with operands rounded to TF32 and fp32 accumulation -- the
+ * arithmetic of the reference's own training run (PyTorch's default torch.backends.cudnn.allow_tf32 = True); 0: fp32 FMA. */
+int cetpick_train_set_tf32(int on);
 /* ConvTranspose2d(Cin, Cout, 2, stride 2) + bias cropped to (Ho, Wo) <= (2H, 2W) (unet.py:285-292,375-380); w [Cin][Cout][2][2]. */
 int cetpick_train_upconv_f32(const float* x, const float* w, const float* bias, float* y, const cetpick_conv_geom* g, void* stream);
 /* workspace of the reductions below for up to C_max channels (256-byte aligned) */
