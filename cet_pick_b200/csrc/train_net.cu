@@ -591,6 +591,8 @@ int launch_wgrad_gemm(const float* x, const float* dy, float* dw, const Geom& g,
   return CETPICK_OK;
 }
 
+int g_train_tf32 = 1;      // 1: tensor-core (TF32) contraction in the wide layers (3x3 trunk convs, weight gradients); 0: fp32 FMA everywhere
+
 // ---------------------------------------------------------------------------------------------- TF32 tensor-core variant
 // Same tiling and implicit-im2col staging as wgrad_gemm_kernel, but the 32-position chunk is contracted with
 // mma.sync.m16n8k8 TF32 (fp32 accumulate): operands are rounded to TF32 (cvt.rna) when they are staged -- the arithmetic
@@ -715,6 +717,111 @@ __global__ void __launch_bounds__(G_THREADS) wgrad_mma_kernel(const float* __res
       }
 }
 
+// 3 x 3 'same' convolution (2-D trunk layers; also their data gradient on flipped weights) on the tensor cores:
+// CTA = 64 output channels x one 8 x 16 pixel tile of one slice, K loop over chunks of 8 input channels.  Per chunk the
+// 10 x 18 input patch (halo included, zero padding applied while staging) and the 9 x 8 x 64 weights are staged as TF32;
+// each of the 9 taps is then 2 x 4 mma.sync.m16n8k8 per warp (warp tile 32 channels x 32 pixels = 2 tile rows), the B
+// fragments being the patch shifted by the tap -- no im2col copy.  Next chunk's global loads are in flight meanwhile.
+constexpr int CM_TW = 16, CM_TH = 8, CM_CI = 8, CM_CO = 64;
+constexpr int CM_PLANE = 184;                      // 10 x 18 patch, padded: 184 = 24 mod 32 words -> conflict-free B fragments
+constexpr int CM_LDW = CM_CO + 8;                  // 72 = 8 mod 32 words -> conflict-free A fragments
+__global__ void __launch_bounds__(256, 2) conv3x3_mma_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y,
+                                                          const Geom g, const int flags) {
+  __shared__ __align__(16) uint32_t s_p[CM_CI][CM_PLANE];
+  __shared__ __align__(16) uint32_t s_w[9][CM_CI][CM_LDW];
+  const bool accumulate = flags & 1, relu = flags & 2;
+  const int tiles_x = ceil_div(g.W, CM_TW);
+  const int tx0 = (blockIdx.x % tiles_x) * CM_TW, ty0 = (blockIdx.x / tiles_x) * CM_TH;
+  const int n = blockIdx.y, co0 = blockIdx.z * CM_CO;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int mw = (warp & 1) * 32, wn = warp >> 1;          // warp: channels [mw, mw + 32), tile rows 2 wn, 2 wn + 1
+  constexpr int P_PER = (CM_CI * 180 + 255) / 256;         // 6 patch elements per thread
+  constexpr int W_PER = 9 * CM_CI * CM_CO / 256;           // 18 weights per thread
+  float rp[P_PER], rw[W_PER];
+  auto fetch = [&](int ci0) {
+#pragma unroll
+    for (int j = 0; j < P_PER; ++j) {
+      const int e = threadIdx.x + 256 * j;
+      float v = 0.f;
+      if (e < CM_CI * 180) {
+        const int ci = e / 180, r = e - ci * 180, py = r / 18, px = r - py * 18;
+        const int iy = ty0 + py - 1, ix = tx0 + px - 1;
+        if (ci0 + ci < g.Cin && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+          v = __ldg(x + (size_t)n * g.xs_n + (size_t)(ci0 + ci) * g.xs_c + (size_t)iy * g.W + ix);
+      }
+      rp[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < W_PER; ++j) {
+      const int e = threadIdx.x + 256 * j;                 // co-major, then the 72 contiguous (ci, tap) weights of the chunk
+      const int co = e / 72, r = e - co * 72, ci = r / 9;
+      rw[j] = (co0 + co < g.Cout && ci0 + ci < g.Cin) ? __ldg(w + ((size_t)(co0 + co) * g.Cin + ci0) * 9 + r) : 0.f;
+    }
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  fetch(0);
+  for (int ci0 = 0; ci0 < g.Cin; ci0 += CM_CI) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < P_PER; ++j) {
+      const int e = threadIdx.x + 256 * j;
+      if (e < CM_CI * 180) s_p[e / 180][e % 180] = to_tf32(rp[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < W_PER; ++j) {
+      const int e = threadIdx.x + 256 * j;
+      const int co = e / 72, r = e - co * 72, ci = r / 9, tap = r - ci * 9;
+      s_w[tap][ci][co] = to_tf32(rw[j]);
+    }
+    __syncthreads();
+    if (ci0 + CM_CI < g.Cin) fetch(ci0 + CM_CI);
+#pragma unroll 1
+    for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) {
+      const int tap = ty * 3 + tx;
+      uint32_t af[2][4], bf[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int m = mw + mi * 16 + gq;
+        af[mi][0] = s_w[tap][tq][m];     af[mi][1] = s_w[tap][tq][m + 8];
+        af[mi][2] = s_w[tap][tq + 4][m]; af[mi][3] = s_w[tap][tq + 4][m + 8];
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int prow = 2 * wn + (ni >> 1) + ty, pcol = (ni & 1) * 8 + gq + tx;
+        bf[ni][0] = s_p[tq][prow * 18 + pcol]; bf[ni][1] = s_p[tq + 4][prow * 18 + pcol];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) mma_tf32(acc[mi][ni], af[mi], bf[ni]);
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int co = co0 + mw + mi * 16 + gq + ((c & 2) ? 8 : 0);
+        const int oy = ty0 + 2 * wn + (ni >> 1), ox = tx0 + (ni & 1) * 8 + 2 * tq + (c & 1);
+        if (co >= g.Cout || oy >= g.H || ox >= g.W) continue;
+        float* o = y + (size_t)n * g.ys_n + (size_t)co * g.ys_c + (size_t)oy * g.W + ox;
+        float v = acc[mi][ni][c] + (bias ? bias[co] : 0.f);
+        if (accumulate) v += *o;
+        *o = relu ? fmaxf(v, 0.f) : v;
+      }
+}
+
 template <int BM, int BN>
 int launch_wgrad_mma(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo;
@@ -730,7 +837,6 @@ int launch_wgrad_mma(const float* x, const float* dy, float* dw, const Geom& g, 
   return CETPICK_OK;
 }
 
-int g_train_tf32 = 1;      // 1: tensor-core (TF32) contraction in the wide layers' weight gradients; 0: fp32 FMA everywhere
 
 bool geom_ok(const Geom* g) {
   return g && g->N > 0 && g->Cin > 0 && g->Cout > 0 && g->H > 0 && g->W > 0 && g->Ho > 0 && g->Wo > 0 && g->kz > 0 && g->ky > 0 &&
@@ -770,6 +876,12 @@ extern "C" int cetpick_train_conv_f32(const float* x, const float* w, const floa
   if (g->ky == 3 && g->kx == 3 && g->stride == 1 && g->dz == 1 && g->dy == g->dx && g->Ho == g->H && g->Wo == g->W) {
     // the hot shapes ('same' 3x3 in-plane taps): two pixels per thread, taps unrolled
     const dim3 grid2(ceil_div(g->Ho * ((g->Wo + 1) / 2), CV_THREADS), g->N, ceil_div(g->Cout, CV_CO));
+    if (g->kz == 1 && g->dy == 1 && g_train_tf32 && g->Cout >= 32 && g->Cin >= 8 && g->py == 1 && g->px == 1) {
+      const dim3 gm(ceil_div(g->W, CM_TW) * ceil_div(g->H, CM_TH), g->N, ceil_div(g->Cout, CM_CO));
+      conv3x3_mma_kernel<<<gm, 256, 0, s>>>(x, w, bias, y, *g, flags);
+      CETPICK_LAUNCH_CHECK();
+      return CETPICK_OK;
+    }
     if (g->kz == 1 && g->dy == 1) {
       conv3x3_f32_kernel<1, 1><<<grid2, CV_THREADS, 0, s>>>(x, w, bias, y, *g, flags);
       CETPICK_LAUNCH_CHECK();

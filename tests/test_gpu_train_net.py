@@ -7,7 +7,9 @@ largest gradient, within max(5e-3, 3 x the error torch's OWN fp32 path makes aga
 above 5e-2.  The backward of this network through ~20 batch-statistics BatchNorms amplifies fp32 rounding (a few ReLU
 masks of near-zero activations flip): at 128^3 the error grows from 1e-7 at the head to ~2e-2 in the bottom block for
 torch-fp32/cuDNN and for these kernels alike (measured: ours <= torch's on 55 of 62 tensors), so a fixed 1e-3 against
-float64 is not reachable in fp32 by either.
+float64 is not reachable in fp32 by either.  In the default TF32 mode (tensor-core 3x3 convolutions and weight gradients,
+the arithmetic of the reference's own run) the same amplification gives 0.3-0.4 in the bottom block for torch-TF32/cuDNN and
+for these kernels alike, so there the only yardstick is torch-TF32's own error against float64 (no absolute cap).
 The single layers are compared with torch's fp32 ops at 1e-4 .. 2e-5.
 SURVEY.md 8f-4; BASELINE.json configs[4] names 128^3 crops: `test_training_step_128_cube`.
 """
@@ -62,8 +64,8 @@ def rel(a, b):
 @pytest.mark.parametrize("tf32", [False, True])
 def test_conv_forward_dgrad_wgrad(name, cin, cout, shape, zdepth, tf32):
     """conv_f32_kernel / flip_weights + conv / weight-gradient kernels against F.conv2d / F.conv3d and autograd.
-    tf32 = False: fp32 FMA everywhere (1e-4); True: the wide layers' weight gradient contracts on the tensor cores with
-    TF32 operands (2e-3 of the largest gradient: 10-bit mantissas, fp32 accumulation)."""
+    tf32 = False: fp32 FMA everywhere (2e-5 / 1e-4); True: the wide 3x3 layers and the wide weight gradients contract on
+    the tensor cores with TF32 operands (2e-3 of the largest value: 10-bit mantissas, fp32 accumulation)."""
     E, o = _ops(tf32)
     spec = getattr(E, name)
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -81,14 +83,14 @@ def test_conv_forward_dgrad_wgrad(name, cin, cout, shape, zdepth, tf32):
     ref.backward(gy)
     y = E.new_view(N, cout, ref.shape[2], ref.shape[3], x.device)
     o.conv(_view(E, x.detach()), w.detach(), None, y, spec, zdepth)
-    assert rel(y.t, ref.detach()) <= 2e-5
+    assert rel(y.t, ref.detach()) <= (2e-3 if tf32 else 2e-5)
     dw = torch.zeros_like(w)
     o.wgrad(_view(E, x.detach()), _view(E, gy), dw, spec, zdepth)
     assert rel(dw, w.grad) <= (2e-3 if tf32 else 1e-4)
     if spec.stride == 1:
         dx = E.new_view(N, cin, H, W, x.device)
         o.dgrad(_view(E, gy), w.detach(), dx, spec, zdepth)
-        assert rel(dx.t, x.grad) <= 2e-5
+        assert rel(dx.t, x.grad) <= (2e-3 if tf32 else 2e-5)
 
 
 @pytest.mark.parametrize("cin,cout,shape,crop", [(64, 32, (5, 9, 11), (18, 22)), (32, 16, (3, 10, 7), (19, 13))])
@@ -183,10 +185,12 @@ def _labels(b, d, h, w, seed):
     return torch.from_numpy(gt)
 
 
-def _step_vs_oracle(b, d, h, w, tau, tol, with_aug=False):
+def _step_vs_oracle(b, d, h, w, tau, tol, with_aug=False, tf32=False):
     from oracle import train_oracle as to
     from cet_pick_b200.models.model import create_model
     from cet_pick_b200.trains.engine import DetectorTrainer
+    from cet_pick_b200 import _lib
+    _lib.check(_lib.lib().cetpick_train_set_tf32(int(tf32)), "cetpick_train_set_tf32")
     sd = {k: v.cuda() for k, v in synth.unet_state_dict_torch(41, 4).items()}
     m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
     m.load_state_dict(sd)
@@ -203,8 +207,9 @@ def _step_vs_oracle(b, d, h, w, tau, tol, with_aug=False):
         from oracle import unet_oracle as uo
         with torch.no_grad():
             uo.forward(x_aug.double(), sdo, want_proj=False, train=True)        # moves the running statistics only
-    assert abs(float(loss) - float(oloss)) <= 1e-5 * max(1.0, abs(float(oloss)))
-    assert float((logits - ohm.view_as(logits)).abs().max()) <= 1e-4 * max(1.0, float(ohm.abs().max()))
+    # TF32 mode: forward and backward round their tensor-core operands to 10-bit mantissas, like the reference's own run
+    assert abs(float(loss) - float(oloss)) <= (2e-3 if tf32 else 1e-5) * max(1.0, abs(float(oloss)))
+    assert float((logits - ohm.view_as(logits)).abs().max()) <= (1e-2 if tf32 else 1e-4) * max(1.0, float(ohm.abs().max()))
     # a bias in front of a batch-statistics BatchNorm (the transposed convs') has NO gradient mathematically: both sides
     # hold rounding noise there, so the error of a tensor is taken relative to max(its own largest gradient, 1e-4 of the
     # largest gradient of the whole model)
@@ -223,32 +228,38 @@ def _step_vs_oracle(b, d, h, w, tau, tol, with_aug=False):
     errs = errors(lambda k, p: p.grad.double())
     msg = (f"training step {b}x{d}x{h}x{w}: loss {float(loss):.6f}, worst gradient errors vs float64 "
            f"{[(k, f'{e:.1e}') for e, k in errs[:3]]}, largest gradient {gmax:.3e}, {tr.stats['launches']} launches")
+    # torch's own path in the same arithmetic class (fp32 / TF32 cuDNN) against the same float64 oracle: the co-reference
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     _, g32, _ = to.training_step(x, gt, {k: v.clone() for k, v in sd.items()}, tau)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
     e32 = errors(lambda k, p: g32[k].double())
-    msg += f"; torch fp32 (cuDNN, TF32 off) by the same measure: {[(k, f'{e:.1e}') for e, k in e32[:3]]}"
+    msg += f"; torch {'TF32' if tf32 else 'fp32 (TF32 off)'} (cuDNN) by the same measure: {[(k, f'{e:.1e}') for e, k in e32[:3]]}"
     print(msg)
     t32 = {k: e for e, k in e32}
     for e, k in errs:
-        assert e <= max(tol, 3.0 * t32[k]) and e <= 5e-2, (k, e, t32[k])
+        assert e <= max(tol, 3.0 * t32[k]) and (tf32 or e <= 5e-2), (k, e, t32[k])
     for k, v in m.named_buffers():
         if "running" in k:
-            assert rel(v.double(), sdo[k]) <= 1e-4, k
+            assert rel(v.double(), sdo[k]) <= (5e-3 if tf32 else 1e-4), k     # running statistics of TF32 conv outputs
     return tr, m, x, gt
 
 
+@pytest.mark.parametrize("tf32", [False, True])
 @pytest.mark.parametrize("b,d,h,w,aug", [(1, 6, 32, 48, False), (2, 5, 38, 42, True)])
-def test_training_step_small_vs_autograd(b, d, h, w, aug):
+def test_training_step_small_vs_autograd(b, d, h, w, aug, tf32):
     """Even and odd (ceil-mode pool + autocrop) sizes, one crop (b == 1 branch) and two (b > 1 branch, 3-D taps must not
     cross crops), optionally the second train-mode forward of the augmented view."""
-    _step_vs_oracle(b, d, h, w, 0.02, 5e-3, aug)
+    _step_vs_oracle(b, d, h, w, 0.02, 2e-2 if tf32 else 5e-3, aug, tf32=tf32)
 
 
-def test_training_step_128_cube():
-    """BASELINE.json configs[4]'s crop: one 128^3 crop, forward + backward, gradients against torch autograd."""
+@pytest.mark.parametrize("tf32", [False, True])
+def test_training_step_128_cube(tf32):
+    """BASELINE.json configs[4]'s crop: one 128^3 crop, forward + backward, gradients against torch autograd, in the
+    fp32 mode and in the default TF32 tensor-core mode (co-reference: torch with cudnn.allow_tf32 as in the reference)."""
     free, _ = torch.cuda.mem_get_info()
     if free < 30 << 30:
         pytest.skip("needs ~30 GB of free device memory")
-    _step_vs_oracle(1, 128, 128, 128, 0.01, 5e-3)
+    _step_vs_oracle(1, 128, 128, 128, 0.01, 2e-2 if tf32 else 5e-3, tf32=tf32)
 
 
 def test_adam_steps_follow_torch_optimizer():
@@ -257,7 +268,7 @@ def test_adam_steps_follow_torch_optimizer():
     either direction, so the bound is 2 * lr per step at worst and 5 % of that on average; the inference plan is rebuilt
     from the new weights."""
     from oracle import train_oracle as to
-    tr, m, x, gt = _step_vs_oracle(1, 4, 32, 32, 0.02, 5e-3)
+    tr, m, x, gt = _step_vs_oracle(1, 4, 32, 32, 0.02, 5e-3, tf32=False)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     names = [k for k, _ in m.named_parameters()]
     ref_params = [sd[k].clone().requires_grad_(True) for k in names]
