@@ -370,7 +370,7 @@ def leg_train(dev, rank, world, crops_per_rank=2, steps=3, with_torch=False):
     ar = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
     flops = 3 * 214.6e9 * crops_per_rank * world
     out = {"workload": f"refinement training step, {crops_per_rank} x 128^3 crops per rank, unet_4, PULoss, Adam (configs[4]; "
-                       "fp32 CUDA-core layers, batch-statistics BatchNorm per crop)",
+                       "TF32 mma.sync 3x3 convolutions and weight gradients, fp32 elsewhere, batch-statistics BatchNorm per crop)",
            "ms_per_step": ms, "crops_per_s": world * crops_per_rank / (ms * 1e-3), "n_gpus": world,
            "allreduce_ms": ar if world > 1 else 0.0, "gradient_bucket_bytes": int(tr.bucket.numel * 4),
            "model_tflops": flops / (ms * 1e-3) / 1e12, "launches_per_crop": int(tr.stats.get("launches", 0)),
