@@ -513,7 +513,7 @@ def leg_simsiam(dev, pk, B=8192):
     return res
 
 
-def leg_e2e_run(dev, a, shape, n_tomo, host_q):
+def leg_e2e_run(dev, a, shape, n_tomo, host_q, threads=8):
     """The drop-in call: TomodetDetector.run(volume, meta) per tomogram, from page-locked host levels to the
     `<name>.txt` pick file and the `<name>_hm.mrc` heat-map on tmpfs (H2D, forward, decode, 268 MB heat-map D2H and
     both file writes inside the timed region)."""
@@ -534,7 +534,7 @@ def leg_e2e_run(dev, a, shape, n_tomo, host_q):
                            "--out_id", "out", "--exp_id", "bench"])
         opt.out_path = os.path.join(work, "out")
         det = detector_factory[opt.task](opt)
-        det.set_async_write(True, threads=8)       # heat-map files are written by 8 threads under the next tomograms
+        det.set_async_write(True, threads=threads)  # heat-map files are written by these threads under the next tomograms
         meta = lambda i: {"name": [f"tomo{i:03d}"], "zdim": D, "level_values": None}
         det.run(host_q[0][None], meta(0))
         det.flush()
@@ -566,7 +566,7 @@ def leg_e2e_run(dev, a, shape, n_tomo, host_q):
                 "files": "pick list + float32 heat-map MRC per tomogram on " + tmp,
                 "stage_ms_median": {k: 1e3 * median([s[k] for s in stats]) for k in ("net", "dec", "tot_time")},
                 "note": "uint8 levels staged H2D on a copy stream one tomogram ahead; heat-map D2H on a copy stream into "
-                        "pooled page-locked buffers; 8 writer threads (AsyncWriter) put the MRC + pick files on tmpfs; "
+                        f"pooled page-locked buffers; {threads} writer threads (AsyncWriter) put the MRC + pick files on tmpfs; "
                         "flush() inside the timed region"}
     finally:
         shutil.rmtree(work, ignore_errors=True)
@@ -772,7 +772,7 @@ def run_b200(a, rank, world, local_rank):
             del pool[:]
             torch.cuda.empty_cache()
             try:
-                line["e2e_run"] = leg_e2e_run(dev, a, (D, H, W), 16, host_q)
+                line["e2e_run"] = leg_e2e_run(dev, a, (D, H, W), 48, host_q, threads=12)
             except Exception as e:
                 line["e2e_run"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
