@@ -772,7 +772,7 @@ def run_b200(a, rank, world, local_rank):
             del pool[:]
             torch.cuda.empty_cache()
             try:
-                line["e2e_run"] = leg_e2e_run(dev, a, (D, H, W), 48, host_q, threads=12)
+                line["e2e_run"] = leg_e2e_run(dev, a, (D, H, W), 48, host_q, threads=8)
             except Exception as e:
                 line["e2e_run"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
