@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         const uint32_t boff1 = (uint32_t)(r_lo - (i - 1)) * (G::SLOT_BYTES >> 4);
         const uint32_t boff2 = boff1 + (uint32_t)n1 * (G::SLOT_BYTES >> 4);
         const uint32_t d1 = tmem_base + s_lo * COUT, d2 = tmem_base;
+        const uint32_t sl_i = (sl_p + 1u == SL) ? 0u : sl_p + 1u;     // slot of row i
         for (int src = 0; src < p.nsrc; ++src)
           for (int c = 0; c < p.chunks; ++c) {
             ptx::mbar_wait_a(a_full + 8u * (uint32_t)stage, phase);
@@ -268,20 +269,16 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
                                           w_lo + boff2 + ((j * G::WBLK + kk * 32) >> 4), B_HI, id2);
                   }
               ptx::umma_commit_a(a_empty + 8u * (uint32_t)stage);
+              if (src == p.nsrc - 1 && c == p.chunks - 1) {
+                // last operand block of input row i: the rows that have now seen all three of their input rows
+                // (same election as the UMMAs: one ELECT / reconvergence per row instead of two)
+                if (i - 1 >= s.ma) ptx::umma_commit_a(a_afull + 8u * sl_p);
+                if (i == p.L - 1 && i < s.mb) ptx::umma_commit_a(a_afull + 8u * sl_i);
+              }
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-        // rows that have now seen all three of their input rows.  (Folding these commits into the election of the last
-        // operand block above saves an ELECT / reconvergence per row and measured 3 % on the 32-channel layers, but
-        // that build dead-locked intermittently in slab mode -- 4 of 6 runs of test_config0_full_size_vs_oracle, cause
-        // not found -- while this form ran 40 / 40: kept.)
-        const uint32_t sl_i = (sl_p + 1u == SL) ? 0u : sl_p + 1u;     // slot of row i
-        if (ptx::elect_one()) {
-          if (i - 1 >= s.ma) ptx::umma_commit_a(a_afull + 8u * sl_p);
-          if (i == p.L - 1 && i < s.mb) ptx::umma_commit_a(a_afull + 8u * sl_i);
-        }
-        __syncwarp();
         sl_p = sl_i;
       }
     }
@@ -306,9 +303,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, 1) conv_march_kernel(const __gr
         for (int t = 0; t < MT; ++t) {
           // one epilogue group per (row, M-tile); with the fused pool a group keeps both rows of a pair
           // (MT = 2: group = M-tile; MT = 1: groups alternate row PAIRS; strips start on even rows)
-          // (every group observes every phase of a slot's barrier, also for rows / tiles the other group drains:
-          // a parity wait only tells the current phase from the one before it, and a group that skipped a phase
-          // could run two phases ahead across a strip boundary and take the stale parity for "done")
+          // A warp waits for a phase of a slot's barrier EXACTLY ONCE and arrives on the slot-free barrier afterwards:
+          //  * it must observe every phase (a parity wait only tells the current phase from the one before it; a group
+          //    that skipped a phase could run two phases ahead across a strip boundary and take the stale parity for
+          //    "done") -- MT = 1: the group that does not drain a row still waits, then arrives as an observer;
+          //  * it must never wait for a phase AGAIN after its arrival: the issuer may then reuse the slot, and a warp that
+          //    is held up for two phases between its arrival and a second wait takes the parity of the phase two ahead
+          //    for the one it wants and blocks on a phase that needs its own next arrival -- a dead-lock seen about once
+          //    in ten slab-mode forwards when MT = 2 groups also "observed" the other group's tile (found with a wait
+          //    recorder).  MT = 2: each group drains its own tile of EVERY row, so it skips the
+          //    other tile without waiting.
+          if (MT == 2 && t != eg) continue;
           ptx::mbar_wait_a(a_afull + 8u * slot, par);
           if ((pool && MT == 1) ? (((r >> 1) & 1) != eg) : ((int)((q * (uint32_t)MT + (uint32_t)t) & 1u) != eg)) {
             if (MT == 1) { __syncwarp(); if (lane == 0) ptx::mbar_arrive_a(a_aempty + 8u * slot); }   // observed: see bar_aempty's init
