@@ -352,3 +352,22 @@ def test_repeated_forward_reuses_cached_tensor_maps():
         m._destroy_plan()
     finally:
         _lib.lib = old
+
+
+def test_slab_mode_repeated_forwards_stay_identical_and_do_not_hang():
+    """Regression for the marching kernel's epilogue dead-lock (a warp waiting for a slot barrier a second time after its
+    arrival could be lapped by two phases; it showed in about one of ten slab-mode forwards of this size once the UMMA
+    issuer got faster): 40 slab-mode forwards of a 128 x 512 x 512 volume, all bit-identical to the
+    whole-volume heat-map.  A protocol bug traps after 4 s instead of hanging the GPU."""
+    from cet_pick_b200.models.model import create_model
+    m = create_model("unet_4", {"hm": 1, "proj": 32}, 32, last_k=3)
+    m.load_state_dict(synth.unet_state_dict_torch(317, 4))
+    m = m.cuda().eval()
+    m.compute_proj, m.fuse_sigmoid = False, True
+    x = synth.tomogram_torch(128, 512, 512, seed=0, device="cuda")[None]
+    hm = m(x)[-1]["hm"].clone()
+    m.slab_z = 48
+    for _ in range(40):
+        hm2 = m(x)[-1]["hm"]
+        assert float((hm2 - hm).abs().max()) <= 2e-7
+    torch.cuda.synchronize()
