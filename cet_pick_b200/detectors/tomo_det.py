@@ -138,19 +138,21 @@ class TomodetDetector(BaseDetector):
         if o.fiber or o.spike:
             raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
                                       "(utils/post_process.py:31-106; DESIGN.md)")
-        lines = []
-        for k, v in dets.items():
-            for c in v:
-                x, y, z, score = int(np.floor(c[0])), int(np.floor(c[1])), int(np.floor(c[2])), float(c[3])
-                if (score > o.out_thresh and z >= o.cutoff_z and z <= max_z - o.cutoff_z
-                        and 20 < x < max_x - 20 and 20 < y < max_y - 20):
-                    if o.compress:
-                        z = int(z) * 2
-                    if not o.with_score:
-                        lines.append(str(x) + "\t" + str(z) + "\t" + str(y))
-                    else:
-                        lines.append(str(x) + "\t" + str(z) + "\t" + str(y) + "\t" + str(score))
-        return lines
+        from itertools import chain
+        rows = list(chain.from_iterable(dets.values()))           # dict order = ascending z, rows in top-K order
+        if not rows:
+            return []
+        a = np.asarray(rows, dtype=np.float64)                    # the float32 values, exactly (float(c[3]) in the reference)
+        x, y, z = (np.floor(a[:, j]).astype(np.int64) for j in range(3))
+        score = a[:, 3]
+        keep = (score > o.out_thresh) & (z >= o.cutoff_z) & (z <= max_z - o.cutoff_z) & (x > 20) & (x < max_x - 20) \
+            & (y > 20) & (y < max_y - 20)
+        if o.compress:
+            z = z * 2
+        xs, ys, zs = x[keep].tolist(), y[keep].tolist(), z[keep].tolist()
+        if not o.with_score:
+            return ["%d\t%d\t%d" % t for t in zip(xs, zs, ys)]
+        return ["%d\t%d\t%d\t%s" % (xx, zz, yy, str(sc)) for xx, zz, yy, sc in zip(xs, zs, ys, score[keep].tolist())]
 
     def _pinned_like(self, t):
         """page-locked staging buffer for the heat-map copy, kept across tomograms"""

@@ -14,12 +14,15 @@ def tomo_post_process(dets, z_dim_tot=128):
     for i in range(dets.shape[0]):
         top_preds = {}
         z = dets[i, :, 2]
-        order = np.argsort(z, kind="stable")
+        order = np.argsort(z, kind="stable")          # rows of one plane stay in top-K order (stable)
         zs = z[order]
-        # rows whose z is an integer plane index in [0, z_dim_tot): one pass instead of one mask per plane
-        for j in np.unique(zs):
-            if j < 0 or j >= z_dim_tot or j != np.floor(j):
-                continue
-            lo, hi = np.searchsorted(zs, j, "left"), np.searchsorted(zs, j, "right")
-            top_preds[int(j)] = dets[i, np.sort(order[lo:hi]), :].astype(np.float32).tolist()
+        ok = (zs >= 0) & (zs < z_dim_tot) & (zs == np.floor(zs))     # integer plane index in [0, z_dim_tot)
+        order, zs = order[ok], zs[ok]
+        if zs.size == 0:
+            continue
+        rows = dets[i, order, :].astype(np.float32).tolist()        # one conversion for all K rows (host-side cost of run())
+        starts = np.flatnonzero(np.r_[True, zs[1:] != zs[:-1]]).tolist() + [int(zs.size)]
+        keys = zs[starts[:-1]].astype(np.int64).tolist()
+        for k, a, b in zip(keys, starts[:-1], starts[1:]):
+            top_preds[k] = rows[a:b]
     return [top_preds]
