@@ -10,7 +10,7 @@ import torch
 
 from ..models.decode import decode_status, tomo_decode
 from ..utils.mrcio import write_mrc
-from ..utils.post_process import tomo_post_process
+from ..utils.post_process import graph_pick_lines, tomo_post_process
 from .base_detector import BaseDetector
 
 
@@ -133,26 +133,26 @@ class TomodetDetector(BaseDetector):
                 print(ln, file=f)
 
     def _pick_lines(self, dets, max_z, max_x, max_y):
-        """tomo_det.py:69-83: one `x\tz\ty[\tscore]` line per pick that passes the score / z-cutoff / 20-px border filter"""
+        """tomo_det.py:69-95: one `x\tz\ty[\tscore]` line per pick that passes the score / z-cutoff / 20-px border filter;
+        with --fiber / --spike the kept picks go through the graph post-processing of utils/post_process.py instead.
+        --spike without --fiber follows TomoClassdetDetector.save_detection (tomo_det_classify.py:196-214): here the
+        reference fills its candidate list only under --fiber and then indexes the empty list (IndexError)."""
         o = self.opt
-        if o.fiber or o.spike:
-            raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
-                                      "(utils/post_process.py:31-106; DESIGN.md)")
         from itertools import chain
         rows = list(chain.from_iterable(dets.values()))           # dict order = ascending z, rows in top-K order
-        if not rows:
-            return []
-        a = np.asarray(rows, dtype=np.float64)                    # the float32 values, exactly (float(c[3]) in the reference)
+        a = np.asarray(rows, dtype=np.float64).reshape(-1, 5)     # the float32 values, exactly (float(c[3]) in the reference)
         x, y, z = (np.floor(a[:, j]).astype(np.int64) for j in range(3))
         score = a[:, 3]
         keep = (score > o.out_thresh) & (z >= o.cutoff_z) & (z <= max_z - o.cutoff_z) & (x > 20) & (x < max_x - 20) \
             & (y > 20) & (y < max_y - 20)
         if o.compress:
             z = z * 2
-        xs, ys, zs = x[keep].tolist(), y[keep].tolist(), z[keep].tolist()
+        xs, ys, zs, sc = x[keep].tolist(), y[keep].tolist(), z[keep].tolist(), score[keep].tolist()
+        if o.fiber or o.spike:
+            return graph_pick_lines(o, xs, ys, zs, sc, scale=o.distance_scale)
         if not o.with_score:
             return ["%d\t%d\t%d" % t for t in zip(xs, zs, ys)]
-        return ["%d\t%d\t%d\t%s" % (xx, zz, yy, str(sc)) for xx, zz, yy, sc in zip(xs, zs, ys, score[keep].tolist())]
+        return ["%d\t%d\t%d\t%s" % (xx, zz, yy, str(s)) for xx, zz, yy, s in zip(xs, zs, ys, sc)]
 
     def _pinned_like(self, t):
         """page-locked staging buffer for the heat-map copy, kept across tomograms"""

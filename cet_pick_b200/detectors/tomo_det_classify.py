@@ -17,6 +17,7 @@ import torch
 from ..models.decode import tomo_decode_classify
 from ..models.utils import _sigmoid
 from ..utils.mrcio import write_mrc
+from ..utils.post_process import graph_pick_lines
 from .base_detector import BaseDetector
 
 
@@ -115,28 +116,34 @@ class TomoClassdetDetector(BaseDetector):
         return dets, meta["name"][0]
 
     def save_detection(self, hm, dets, path, meta, prefix="", name=""):
-        """:173-214 (plain and --with_score lines; the fiber / spike graph post-processing of the
-        reference is host-side Python outside this path)."""
+        """:173-214: heat-map MRC, then plain / --with_score lines, or the --fiber / --spike graph post-processing of
+        the kept picks (utils/post_process.py; the fiber re-sampling step is the reference's default of 2 here)."""
         os.makedirs(path, exist_ok=True)            # every rank of a torchrun job writes into the same directory
-        if getattr(self.opt, "fiber", False) or getattr(self.opt, "spike", False):
-            raise NotImplementedError("fiber/spike graph post-processing is outside the hot path "
-                                      "(utils/post_process.py:31-106; DESIGN.md)")
         hm = hm.detach().cpu().numpy()[0][0]
         max_z, max_y, max_x = hm.shape
         if np.isnan(hm).any():
             raise ValueError("Output contains NaN values")
         write_mrc(os.path.join(path, "{}_hm.mrc".format(name)), np.float32(np.swapaxes(hm, 1, 0)))
+        o = self.opt
+        graph = getattr(o, "fiber", False) or getattr(o, "spike", False)
+        kept = ([], [], [], [])
         with open(os.path.join(path, "{}.txt".format(name)), "w+") as out_detect:
             for c in np.asarray(dets):
                 x, y, z, score = int(np.floor(c[0])), int(np.floor(c[1])), int(np.floor(c[2])), float(c[3])
-                if (score > self.opt.out_thresh and z >= self.opt.cutoff_z and z <= max_z - self.opt.cutoff_z
+                if (score > o.out_thresh and z >= o.cutoff_z and z <= max_z - o.cutoff_z
                         and x > 20 and x < max_x - 20 and y > 20 and y < max_y - 20):
-                    if self.opt.compress:
+                    if o.compress:
                         z = int(z) * 2
-                    if not self.opt.with_score:
+                    if graph:
+                        for lst, v in zip(kept, (x, y, z, score)):
+                            lst.append(v)
+                    elif not o.with_score:
                         print(str(x) + "\t" + str(z) + "\t" + str(y), file=out_detect)
                     else:
                         print(str(x) + "\t" + str(z) + "\t" + str(y) + "\t" + str(score), file=out_detect)
+            if graph:
+                for ln in graph_pick_lines(o, *kept, scale=2):
+                    print(ln, file=out_detect)
 
     def debug(self, debugger, images, dets, output, scale=1):
         pass
