@@ -55,6 +55,7 @@ SIGNATURES = {
     "cetpick_unet_forward_u8": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_unet_forward_slab": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _int, _vp, _vp, _sz, _vp]),
     "cetpick_simsiam_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _int]),
+    "cetpick_simsiam_create_2d": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _int, _int]),
     "cetpick_simsiam_destroy": (None, [_vp]),
     "cetpick_simsiam_set_param": (_int, [_vp, C.c_char_p, _vp, _i64]),
     "cetpick_simsiam_finalize": (_int, [_vp]),

@@ -3,7 +3,8 @@
 // :181-215 3-D feature layer and MLP heads, :325-366 forward_test), whose per-slice maps are 8x8, 4x4 and 2x2 pixels.
 //
 // GEMM view: M = 128 output pixels = TZ whole maps of TH x TW pixels (TW*TH*TZ = 128; the 3-D layer takes one
-// 2x2x32 sub-volume per tile, a Linear layer 128 rows), N = output channels (<= 256), K = taps x input channels.
+// 2x2x32 sub-volume per tile, a Linear layer 128 rows) or, for the 32x32 / 16x16 maps of the 2-D exploration network
+// (simsiam_model_2d.py:617-774), a band of 128 / TW full rows of one map, N = output channels (<= 256), K = taps x input channels.
 // The activation tensor is a rank-5 TMA tensor (C, W, H, Z, B); for every (tap, 64-channel chunk) ONE box load shifted
 // by the tap offset brings the [128][64] K-major A tile, TMA's out-of-bounds zero fill is the zero padding (in x, y
 // and, for the 3-D layer, z), and the traversal stride of the tensor map (elementStrides) is the convolution stride
@@ -30,9 +31,9 @@ struct alignas(64) SmallParams {
   int chunks, ntaps, KC, nkb;
   int N;                         // GEMM N = output channels (one tile of N columns)
   int Wo, Ho, Z, NBATCH;         // output map size, maps per batch element, batch elements
-  int TW, TH, TZ, tiles_z;
+  int TW, TH, TZ, tiles_z, tiles_y;     // a tile = TW x TH x TZ output pixels = 128; tiles_y row bands per map
   long long total_tiles;
-  int stages, a_sub, b_sub, layout_type;
+  int stages, a_sub, b_sub, layout_type, stride;
   int relu, out_f32;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -89,12 +90,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int z0 = (int)(t % p.tiles_z) * p.TZ, nb = (int)(t / p.tiles_z);
+        const int ty = (int)(t % p.tiles_y);
+        const long long tq = t / p.tiles_y;
+        const int z0 = (int)(tq % p.tiles_z) * p.TZ, nb = (int)(tq / p.tiles_z);
+        const int yin0 = ty * p.TH * p.stride;               // first input row of the band (before the tap offset)
         for (int kb = 0; kb < p.nkb; ++kb) {
           const int tap = kb / p.chunks, chunk = kb - tap * p.chunks;
           ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
           ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)(p.a_sub + p.b_sub));
-          tma_load_5d(sA + (size_t)stage * p.a_sub, &p.tmA, &bar_full[stage], chunk * p.KC, p.tdx[tap], p.tdy[tap],
+          tma_load_5d(sA + (size_t)stage * p.a_sub, &p.tmA, &bar_full[stage], chunk * p.KC, p.tdx[tap], yin0 + p.tdy[tap],
                       z0 + p.tdz[tap], nb);
           ptx::tma_load_2d(sB + (size_t)stage * p.b_sub, &p.tmB, &bar_full[stage], 0, kb * p.N);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -140,10 +144,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int z0 = (int)(t % p.tiles_z) * p.TZ, nb = (int)(t / p.tiles_z);
+      const int ty = (int)(t % p.tiles_y);
+      const long long tq = t / p.tiles_y;
+      const int z0 = (int)(tq % p.tiles_z) * p.TZ, nb = (int)(tq / p.tiles_z);
       const int z = z0 + pz;
       const bool valid = z < p.Z;
-      const size_t pix = (((size_t)nb * p.Z + z) * p.Ho + py) * p.Wo + px;
+      const size_t pix = (((size_t)nb * p.Z + z) * p.Ho + ty * p.TH + py) * p.Wo + px;
       ptx::mbar_wait(&bar_tfull[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride;
@@ -241,8 +247,11 @@ int conv_small_launch(const SmallLaunch& L, cudaStream_t stream) {
   if (!L.src || !L.wpk || !L.out || L.C <= 0 || (L.C % 64) || L.N < 16 || L.N > 256 || (L.N % 16)) return CETPICK_ERR_BAD_ARG;
   if (L.ntaps < 1 || L.ntaps > 27 || (L.stride != 1 && L.stride != 2) || L.Wo < 1 || L.Ho < 1 || L.Z < 1 || L.B < 1)
     return CETPICK_ERR_BAD_ARG;
-  const int pix = L.Wo * L.Ho;
-  if (pix > 128 || (128 % pix)) return CETPICK_ERR_UNSUPPORTED;     // whole maps per tile: Wo*Ho must divide 128
+  // a tile is TH full rows of TZ maps: small maps go whole (Wo*Ho divides 128), larger ones in bands of 128 / Wo rows
+  if (L.Wo > 128 || (128 % L.Wo)) return CETPICK_ERR_UNSUPPORTED;
+  const int TH = std::min(L.Ho, 128 / L.Wo);
+  if ((L.Ho % TH) || (128 % (L.Wo * TH))) return CETPICK_ERR_UNSUPPORTED;
+  const int pix = L.Wo * TH;
   EncodeTiledFn enc = encode_fn();
   if (!enc) { g_cuda_err = "cuTensorMapEncodeTiled not available"; return CETPICK_ERR_CUDA; }
 
@@ -250,9 +259,10 @@ int conv_small_launch(const SmallLaunch& L, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.KC = 64; p.chunks = L.C / 64; p.ntaps = L.ntaps; p.nkb = L.ntaps * p.chunks; p.N = L.N;
   p.Wo = L.Wo; p.Ho = L.Ho; p.Z = L.Z; p.NBATCH = L.B;
-  p.TW = L.Wo; p.TH = L.Ho; p.TZ = 128 / pix;
+  p.TW = L.Wo; p.TH = TH; p.TZ = 128 / pix; p.stride = L.stride;
+  p.tiles_y = L.Ho / TH;
   p.tiles_z = ceil_div(L.Z, p.TZ);
-  p.total_tiles = (long long)p.tiles_z * L.B;
+  p.total_tiles = (long long)p.tiles_y * p.tiles_z * L.B;
   p.a_sub = 128 * 64 * 2;
   p.b_sub = L.N * 64 * 2;
   p.layout_type = 2;

@@ -14,7 +14,8 @@ struct SmallLaunch {
   int B = 1, Z = 1;              // batch elements, maps per batch element (taps may move in z inside one element)
   int Hin = 1, Win = 1;
   int stride = 1;                // 1 or 2 (in x and y)
-  int Ho = 1, Wo = 1;            // output map size; Wo*Ho must divide 128
+  int Ho = 1, Wo = 1;            // output map size: Wo*Ho divides 128 (whole maps per tile), or Wo divides 128 and
+                                 // Ho is a multiple of 128 / Wo (row bands of one map per tile)
   const void* wpk = nullptr;     // device, layout of small_pack_weights()
   int N = 0;                     // output channels, multiple of 16, <= 256
   int ntaps = 1;

@@ -11,6 +11,13 @@
 //     conv_small_kernel every 3x3 / 1x1 conv of the BasicBlocks (stride 1 / 2, residual add + ReLU in the epilogue),
 //                       the Conv3d(256,256,3) feature layer (one 2x2xD sub-volume per M-tile) and the Linear layers
 //     avgpool_kernel    AdaptiveAvgPool3d((1,1,1))
+//
+// 2-D variant (cetpick_simsiam_create_2d): TomoResClassifier2D.forward_test of
+// cet_pick/models/networks/simsiam_model_2d.py:617-774 (arch `simsiam2d_18`): conv1 is 3x3 stride 1 without a max-pool,
+// the three stages run on the full / half / quarter resolution of a 2-D patch (32x32 -> 16x16 -> 8x8), then
+// AdaptiveAvgPool2d, fc: 256 -> head_conv, and the proj / pred MLPs of width head_conv.
+//     stem2d_kernel     conv 3x3 s1 p1 (1 -> 64) + BN + ReLU (CUDA cores)
+//     conv_small_kernel the BasicBlocks in row bands of 128 pixels, the Linear layers
 #include "common.cuh"
 #include "conv_small.cuh"
 
@@ -102,7 +109,56 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict_
   }
 }
 
-// AdaptiveAvgPool3d((1,1,1)): bf16 [B][P][C] -> bf16 [B][C] (fp32 sum); one CTA per batch element, C = 256 threads
+// 2-D variant: conv1 3x3 s1 p1 (1 -> 64) + BN + ReLU (simsiam_model_2d.py:625-627, 755-757), fp32 patch in, bf16 NHWC out.
+// One CTA per patch; thread = (pixel lane, 8-channel group): its 9 x 8 folded weights live in registers, the patch with
+// a zero frame in shared memory; 8 neighbouring threads write the 128 B of one pixel.
+__global__ void __launch_bounds__(256) stem2d_kernel(const float* __restrict__ in, long long npatch, int HW,
+                                                     const float* __restrict__ wgt /*[9][64], BN scale folded*/,
+                                                     const float* __restrict__ shift /*[64]*/,
+                                                     __nv_bfloat16* __restrict__ out /*[npatch][HW][HW][64]*/) {
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  float* s_in = reinterpret_cast<float*>(stem_smem);          // [(HW+2)][(HW+2)]
+  const int IP = HW + 2, tid = threadIdx.x, cg = tid & 7, lane_px = tid >> 3;
+  float w[9][8], sh[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) w[t][c] = __ldg(wgt + t * 64 + cg * 8 + c);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) sh[c] = __ldg(shift + cg * 8 + c);
+  for (long long s = blockIdx.x; s < npatch; s += gridDim.x) {
+    __syncthreads();
+    const float* src = in + (size_t)s * HW * HW;
+    for (int i = tid; i < IP * IP; i += 256) {
+      const int r = i / IP, c = i - r * IP, y = r - 1, x = c - 1;
+      s_in[i] = (y >= 0 && y < HW && x >= 0 && x < HW) ? __ldg(src + y * HW + x) : 0.f;
+    }
+    __syncthreads();
+    for (int px = lane_px; px < HW * HW; px += 32) {
+      const int y = px / HW, x = px - y * HW;
+      float acc[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = sh[c];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = s_in[(y + ky) * IP + x + kx];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, w[ky * 3 + kx][c], acc[c]);
+        }
+      uint4 o;
+      __nv_bfloat162 h;
+      h = __floats2bfloat162_rn(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)); o.x = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)); o.y = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f)); o.z = *reinterpret_cast<uint32_t*>(&h);
+      h = __floats2bfloat162_rn(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f)); o.w = *reinterpret_cast<uint32_t*>(&h);
+      *reinterpret_cast<uint4*>(out + ((size_t)s * HW * HW + px) * 64 + cg * 8) = o;
+    }
+  }
+}
+
+// AdaptiveAvgPool3d((1,1,1)) / AdaptiveAvgPool2d((1,1)): bf16 [B][P][C] -> bf16 [B][C] (fp32 sum); one CTA per batch element, C = 256 threads
 __global__ void __launch_bounds__(256) avgpool_kernel(const __nv_bfloat16* __restrict__ in, int B, int P, int C,
                                                       __nv_bfloat16* __restrict__ out) {
   for (int b = blockIdx.x; b < B; b += gridDim.x)
@@ -123,6 +179,8 @@ using namespace cetpick;
 
 struct cetpick_simsiam {
   int layers[3];
+  int two_d = 0;            // 1: TomoResClassifier2D (simsiam_model_2d.py:617-774)
+  int out_dim = 256;        // width of fc and the heads (head_conv in the 2-D variant)
   bool has_proj, has_pred;
   std::map<std::string, std::vector<float>> params;
   bool finalized = false;
@@ -192,6 +250,17 @@ bool geometry(int64_t H, int64_t W, Geo& g) {
   return g.h2 >= 2;
 }
 
+// 2-D variant: no stride in conv1 and no max-pool, the stages see H, H/2, H/4 (simsiam_model_2d.py:755-762)
+bool geometry_2d(int64_t D, int64_t H, int64_t W, Geo& g) {
+  if (D != 1 || H != W || (H != 8 && H != 16 && H != 32 && H != 64)) return false;
+  g.h0 = g.h1 = (int)H; g.h2 = g.h1 / 2; g.h3 = g.h2 / 2;
+  return true;
+}
+
+bool geometry_of(const cetpick_simsiam* m, int64_t D, int64_t H, int64_t W, Geo& g) {
+  return m->two_d ? geometry_2d(D, H, W, g) : geometry(H, W, g);
+}
+
 size_t ws_bytes_for(const cetpick_simsiam* m, int64_t B, int64_t D, const Geo& g) {
   (void)m;
   const size_t n = (size_t)B * D;
@@ -232,6 +301,16 @@ extern "C" int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int b
   return CETPICK_OK;
 }
 
+extern "C" int cetpick_simsiam_create_2d(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int out_dim,
+                                         int has_proj, int has_pred) {
+  if (out_dim < 64 || out_dim > 256 || (out_dim % 64)) return plan ? CETPICK_ERR_UNSUPPORTED : CETPICK_ERR_BAD_ARG;
+  const int rc = cetpick_simsiam_create(plan, blocks1, blocks2, blocks3, has_proj, has_pred);
+  if (rc != CETPICK_OK) return rc;
+  (*plan)->two_d = 1;
+  (*plan)->out_dim = out_dim;
+  return CETPICK_OK;
+}
+
 extern "C" void cetpick_simsiam_destroy(cetpick_simsiam* m) {
   if (!m) return;
   if (m->d_blob) cudaFree(m->d_blob);
@@ -253,14 +332,15 @@ extern "C" int cetpick_simsiam_finalize(cetpick_simsiam* m) {
   m->blocks.clear();
   Fold f;
   {
-    auto w = m->get("conv1.weight", 64 * 49);
+    const int kk = m->two_d ? 9 : 49;                       // conv1: 3x3 s1 (2-D variant) or 7x7 s2
+    auto w = m->get("conv1.weight", (size_t)64 * kk);
     if (!w || !bn_fold(m, "bn1", 64, true, f)) return CETPICK_ERR_STATE;
-    m->stem_w = balloc(m, 49 * 64 * 4);
+    m->stem_w = balloc(m, (size_t)kk * 64 * 4);
     m->stem_b = balloc(m, 64 * 4);
     float* sw = reinterpret_cast<float*>(m->blob.data() + m->stem_w);
     float* sb = reinterpret_cast<float*>(m->blob.data() + m->stem_b);
     for (int c = 0; c < 64; ++c) {
-      for (int t = 0; t < 49; ++t) sw[t * 64 + c] = (float)((double)(*w)[c * 49 + t] * f.scale[c]);
+      for (int t = 0; t < kk; ++t) sw[t * 64 + c] = (float)((double)(*w)[c * kk + t] * f.scale[c]);
       sb[c] = (float)f.shift[c];
     }
   }
@@ -279,20 +359,23 @@ extern "C" int cetpick_simsiam_finalize(cetpick_simsiam* m) {
       m->blocks.push_back(blk);
       inpl = pl;
     }
-  if (!bn_fold(m, "feature_3d.1", 256, true, f) || !pack(m, "feature_3d.0.weight", 256, 256, 27, 1, &f, nullptr, m->f3d)) return CETPICK_ERR_STATE;
+  if (!m->two_d &&
+      (!bn_fold(m, "feature_3d.1", 256, true, f) || !pack(m, "feature_3d.0.weight", 256, 256, 27, 1, &f, nullptr, m->f3d)))
+    return CETPICK_ERR_STATE;
+  const int od = m->out_dim;                                // 256, or head_conv in the 2-D variant (simsiam_model_2d.py:639-640)
   {
-    auto b = m->get("fc.bias", 256);
-    if (!b || !pack(m, "fc.weight", 256, 256, 1, 1, nullptr, b, m->fc)) return CETPICK_ERR_STATE;
+    auto b = m->get("fc.bias", od);
+    if (!b || !pack(m, "fc.weight", od, 256, 1, 1, nullptr, b, m->fc)) return CETPICK_ERR_STATE;
   }
   if (m->has_proj) {
-    if (!bn_fold(m, "proj.1", 256, true, f) || !pack(m, "proj.0.weight", 256, 256, 1, 1, &f, nullptr, m->proj0)) return CETPICK_ERR_STATE;
-    if (!bn_fold(m, "proj.4", 256, true, f) || !pack(m, "proj.3.weight", 256, 256, 1, 1, &f, nullptr, m->proj3)) return CETPICK_ERR_STATE;
-    if (!bn_fold(m, "proj.7", 256, false, f) || !pack(m, "proj.6.weight", 256, 256, 1, 1, &f, nullptr, m->proj6)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.1", od, true, f) || !pack(m, "proj.0.weight", od, od, 1, 1, &f, nullptr, m->proj0)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.4", od, true, f) || !pack(m, "proj.3.weight", od, od, 1, 1, &f, nullptr, m->proj3)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.7", od, false, f) || !pack(m, "proj.6.weight", od, od, 1, 1, &f, nullptr, m->proj6)) return CETPICK_ERR_STATE;
   }
   if (m->has_pred) {
-    auto b = m->get("pred.3.bias", 256);
-    if (!bn_fold(m, "pred.1", 256, true, f) || !pack(m, "pred.0.weight", 256, 256, 1, 1, &f, nullptr, m->pred0)) return CETPICK_ERR_STATE;
-    if (!b || !pack(m, "pred.3.weight", 256, 256, 1, 1, nullptr, b, m->pred3)) return CETPICK_ERR_STATE;
+    auto b = m->get("pred.3.bias", od);
+    if (!bn_fold(m, "pred.1", od, true, f) || !pack(m, "pred.0.weight", od, od, 1, 1, &f, nullptr, m->pred0)) return CETPICK_ERR_STATE;
+    if (!b || !pack(m, "pred.3.weight", od, od, 1, 1, nullptr, b, m->pred3)) return CETPICK_ERR_STATE;
   }
   if (m->d_blob) { cudaFree(m->d_blob); m->d_blob = nullptr; }
   CETPICK_CUDA(cudaMalloc(&m->d_blob, m->blob.size()));
@@ -305,7 +388,7 @@ extern "C" int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* m, int64_t
                                                size_t* bytes) {
   Geo g;
   if (!m || !bytes || B <= 0 || D <= 0) return CETPICK_ERR_BAD_ARG;
-  if (!geometry(H, W, g)) return CETPICK_ERR_UNSUPPORTED;
+  if (!geometry_of(m, D, H, W, g)) return CETPICK_ERR_UNSUPPORTED;
   *bytes = ws_bytes_for(m, B, D, g);
   return CETPICK_OK;
 }
@@ -317,7 +400,7 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
   if (!m->finalized) return CETPICK_ERR_STATE;
   if ((proj && !m->has_proj) || (pred && !m->has_pred) || (!proj && !pred)) return CETPICK_ERR_BAD_ARG;
   Geo g;
-  if (!geometry(H, W, g)) return CETPICK_ERR_UNSUPPORTED;
+  if (!geometry_of(m, D64, H, W, g)) return CETPICK_ERR_UNSUPPORTED;
   const int B = (int)B64, D = (int)D64;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   if (!ws || ws_bytes < ws_bytes_for(m, B, D, g)) return CETPICK_ERR_WORKSPACE;
@@ -332,7 +415,13 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
   const uint8_t* blob = static_cast<const uint8_t*>(m->d_blob);
   int rc;
 
-  {  // conv1 + bn1 + relu + maxpool -> buf[0]: (n, h1, h1, 64)
+  if (m->two_d) {  // conv1 3x3 + bn1 + relu -> buf[0]: (n, H, H, 64)
+    const int grid = (int)std::min<long long>(n, (long long)num_sms() * 4);
+    const size_t smem = (size_t)(H + 2) * (H + 2) * 4;
+    stem2d_kernel<<<grid, 256, smem, st>>>(x, n, (int)H, reinterpret_cast<const float*>(blob + m->stem_w),
+                                           reinterpret_cast<const float*>(blob + m->stem_b), buf[0]);
+    CETPICK_LAUNCH_CHECK();
+  } else {  // conv1 + bn1 + relu + maxpool -> buf[0]: (n, h1, h1, 64)
     const int grid = (int)std::min<long long>(n, (long long)num_sms() * 8);
     const float* sw = reinterpret_cast<const float*>(blob + m->stem_w);
     const float* sb = reinterpret_cast<const float*>(blob + m->stem_b);
@@ -366,13 +455,19 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
       cur = blk.has_ds ? cur : t2;
       hin = hout;
     }
-  // (B, D, h, w, 256) -> Conv3d 3x3x3 pad 1 + BN3d + ReLU (:348-354); one sub-volume (D*h*w positions) per M-tile
   const int P = D * hin * hin;
-  if (P != 128) return CETPICK_ERR_UNSUPPORTED;            // 32 slices of 2x2 (or 16x... ) must fill one 128-row tile
-  const int t1 = (cur + 1) % 3;
-  if ((rc = run(m, m->f3d, buf[cur], B, D, hin, hin, hin, hin, true, nullptr, 1, 0, buf[t1], st))) return rc;
-  avgpool_kernel<<<std::min(B, num_sms() * 8), 256, 0, st>>>(buf[t1], B, P, 256, vec[0]);
-  CETPICK_LAUNCH_CHECK();
+  if (m->two_d) {
+    // AdaptiveAvgPool2d((1,1)) over the last stage's map (simsiam_model_2d.py:764-765)
+    avgpool_kernel<<<std::min(B, num_sms() * 8), 256, 0, st>>>(buf[cur], B, P, 256, vec[0]);
+    CETPICK_LAUNCH_CHECK();
+  } else {
+    // (B, D, h, w, 256) -> Conv3d 3x3x3 pad 1 + BN3d + ReLU (:348-354); one sub-volume (D*h*w positions) per M-tile
+    if (P != 128) return CETPICK_ERR_UNSUPPORTED;            // 32 slices of 2x2 (or 16x... ) must fill one 128-row tile
+    const int t1 = (cur + 1) % 3;
+    if ((rc = run(m, m->f3d, buf[cur], B, D, hin, hin, hin, hin, true, nullptr, 1, 0, buf[t1], st))) return rc;
+    avgpool_kernel<<<std::min(B, num_sms() * 8), 256, 0, st>>>(buf[t1], B, P, 256, vec[0]);
+    CETPICK_LAUNCH_CHECK();
+  }
   // fc, then the heads: Linear (+ folded BatchNorm1d) (+ ReLU) as 1x1 "convolutions" over the batch axis
   if ((rc = run(m, m->fc, vec[0], 1, B, 1, 1, 1, 1, false, nullptr, 0, 0, vec[1], st))) return rc;
   if (m->has_proj) {

@@ -1,17 +1,19 @@
 """Mirror of cet_pick/models/model.py for the hot path: create_model (:65-70), load_model
 (:195-251), save_model (:283-296).  The default detector family ('unet_N') and the exploration-step embedding
-network ('simsiam_N' / 'simsiam3d_N') are built; the other arch keys of the reference factory are out of scope (SURVEY.md section 2, rows 10 / Surprise 3)."""
+networks ('simsiam_N' / 'simsiam3d_N', 'simsiam2d_N') are built; the other arch keys of the reference factory are out of scope (SURVEY.md section 2, rows 10 / Surprise 3)."""
 from __future__ import annotations
 
 import torch
 
 from .networks.simsiam_model import get_simsiam_net_small
+from .networks.simsiam_model_2d import get_simsiam2d_net_small
 from .networks.unet_small import get_tomo_unet_small
 
 _model_factory = {
     "unet": get_tomo_unet_small,
     "simsiam": get_simsiam_net_small,        # model.py:42-43: 'simsiam' and 'simsiam3d' are the same factory
     "simsiam3d": get_simsiam_net_small,
+    "simsiam2d": get_simsiam2d_net_small,    # model.py:45
 }
 
 
@@ -19,7 +21,7 @@ def create_model(arch, heads, head_conv, last_k=0, local_path=None):
     num_layers = int(arch[arch.find("_") + 1:]) if "_" in arch else 0
     arch = arch[:arch.find("_")] if "_" in arch else arch
     if arch not in _model_factory:
-        raise KeyError(f"arch '{arch}' is outside cet_pick_b200's hot path (unet_N and simsiam[3d]_N are built)")
+        raise KeyError(f"arch '{arch}' is outside cet_pick_b200's hot path (unet_N, simsiam[3d]_N and simsiam2d_N are built)")
     get_model = _model_factory[arch]
     return get_model(num_layers=num_layers, heads=heads, head_conv=head_conv, last_k=last_k,
                      local_path=local_path)

@@ -103,8 +103,7 @@ class TomoResClassifier(nn.Module):
         h = C.c_void_p()
         has_proj = any("proj" in k for k in self.heads)
         has_pred = any("pred" in k for k in self.heads)
-        _lib.check(L.cetpick_simsiam_create(C.byref(h), *self.layers_spec, int(has_proj), int(has_pred)),
-                   "cetpick_simsiam_create")
+        self._create_plan(L, h, int(has_proj), int(has_pred))
         for k, v in self.state_dict().items():
             if k.endswith("num_batches_tracked"):
                 continue
@@ -113,6 +112,11 @@ class TomoResClassifier(nn.Module):
         _lib.check(L.cetpick_simsiam_finalize(h), "cetpick_simsiam_finalize")
         self._plan, self._plan_key = h, key
         return h
+
+    out_dim = 256
+
+    def _create_plan(self, L, h, has_proj, has_pred):
+        _lib.check(L.cetpick_simsiam_create(C.byref(h), *self.layers_spec, has_proj, has_pred), "cetpick_simsiam_create")
 
     # ------------------------------------------------------------------ forward
     def forward_test(self, x1):
@@ -133,9 +137,9 @@ class TomoResClassifier(nn.Module):
         proj = pred = None
         for head in self.heads:
             if "proj" in head:
-                proj = ret[head] = torch.empty((b, 256), dtype=torch.float32, device=x1.device)
+                proj = ret[head] = torch.empty((b, self.out_dim), dtype=torch.float32, device=x1.device)
             if "pred" in head:
-                pred = ret[head] = torch.empty((b, 256), dtype=torch.float32, device=x1.device)
+                pred = ret[head] = torch.empty((b, self.out_dim), dtype=torch.float32, device=x1.device)
         _lib.check(L.cetpick_simsiam_forward(plan, x1.data_ptr(), b, d, h, w,
                                              proj.data_ptr() if proj is not None else None,
                                              pred.data_ptr() if pred is not None else None,

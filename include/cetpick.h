@@ -229,6 +229,11 @@ typedef struct cetpick_simsiam cetpick_simsiam;
 
 /* blocks1..3: BasicBlocks per stage (2,2,2 for *_18; 3,4,6 for *_34).  has_proj / has_pred: which heads exist. */
 int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int has_proj, int has_pred);
+/* 2-D exploration variant: TomoResClassifier2D.forward_test (cet_pick/models/networks/simsiam_model_2d.py:617-774, arch
+ * simsiam2d_18; conv1 3x3 stride 1, no max-pool, AdaptiveAvgPool2d, fc 256 -> out_dim, heads of width out_dim).
+ * out_dim = the reference's head_conv (128 by default for this task, opts.py:207-209); 64, 128, 192 or 256 here. */
+int cetpick_simsiam_create_2d(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int out_dim,
+                              int has_proj, int has_pred);
 void cetpick_simsiam_destroy(cetpick_simsiam* plan);
 /* one tensor of the reference state_dict by its key, host float32, PyTorch layout */
 int cetpick_simsiam_set_param(cetpick_simsiam* plan, const char* key, const float* data_host, int64_t numel);
@@ -236,7 +241,8 @@ int cetpick_simsiam_finalize(cetpick_simsiam* plan);
 int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* plan, int64_t B, int64_t D, int64_t H, int64_t W, size_t* bytes);
 /* x: (B,D,H,W) float32 device sub-volumes (H = W = 32 with D = 32, or H = W = 16 with D = 128: the trunk's final
  * 2x2xD (1x1xD) map fills one 128-row tile; other sizes return CETPICK_ERR_UNSUPPORTED).
- * proj / pred: (B,256) float32 device out, either may be NULL. */
+ * A 2-D plan takes (B,1,H,W) patches, D = 1, H = W in {8, 16, 32, 64}.
+ * proj / pred: (B,256) float32 device out ((B,out_dim) for a 2-D plan), either may be NULL. */
 int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, int64_t D, int64_t H, int64_t W,
                             float* proj, float* pred, void* ws, size_t ws_bytes, void* stream);
 

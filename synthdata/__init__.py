@@ -249,10 +249,12 @@ def fullres_stub_model():
 
 
 # --------------------------------------------------------------------------- SimSiam 3-D encoder (oracle groundwork)
-def simsiam3d_param_shapes(layers=(2, 2, 2), heads=("proj", "pred")):
+def simsiam3d_param_shapes(layers=(2, 2, 2), heads=("proj", "pred"), two_d=False, out_dim=256):
     """state_dict keys and shapes of cet_pick/models/networks/simsiam_model.py:159-235 `TomoResClassifier`
-    (BasicBlock, three stages; arch `simsiam3d_18` / `simsiam_18`), in registration order."""
+    (BasicBlock, three stages; arch `simsiam3d_18` / `simsiam_18`), in registration order; with two_d, of
+    simsiam_model_2d.py:617-664 `TomoResClassifier2D` (arch `simsiam2d_18`: 3x3 conv1, no 3-D layer, width out_dim)."""
     sh = OrderedDict()
+    od = out_dim if two_d else 256
 
     def bn(prefix, c, affine=True):
         if affine:
@@ -262,7 +264,7 @@ def simsiam3d_param_shapes(layers=(2, 2, 2), heads=("proj", "pred")):
         sh[prefix + ".running_var"] = (c,)
         sh[prefix + ".num_batches_tracked"] = ()
 
-    sh["conv1.weight"] = (64, 1, 7, 7)
+    sh["conv1.weight"] = (64, 1, 3, 3) if two_d else (64, 1, 7, 7)
     bn("bn1", 64)
     inpl = 64
     for li, (planes, nblk) in enumerate(zip((64, 128, 256), layers), start=1):
@@ -276,26 +278,32 @@ def simsiam3d_param_shapes(layers=(2, 2, 2), heads=("proj", "pred")):
             if stride_or_widen:
                 sh[p + ".downsample.0.weight"] = (planes, inpl, 1, 1)
         inpl = planes
-    sh["feature_3d.0.weight"] = (256, 256, 3, 3, 3)
-    bn("feature_3d.1", 256)
-    sh["fc.weight"] = (256, 256)
-    sh["fc.bias"] = (256,)
+    if not two_d:
+        sh["feature_3d.0.weight"] = (256, 256, 3, 3, 3)
+        bn("feature_3d.1", 256)
+    sh["fc.weight"] = (od, 256)
+    sh["fc.bias"] = (od,)
     if "proj" in heads:
         for i in (0, 3, 6):
-            sh[f"proj.{i}.weight"] = (256, 256)
-            bn(f"proj.{i + 1}", 256, affine=(i != 6))
+            sh[f"proj.{i}.weight"] = (od, od)
+            bn(f"proj.{i + 1}", od, affine=(i != 6))
     if "pred" in heads:
-        sh["pred.0.weight"] = (256, 256)
-        bn("pred.1", 256)
-        sh["pred.3.weight"] = (256, 256)
-        sh["pred.3.bias"] = (256,)
+        sh["pred.0.weight"] = (od, od)
+        bn("pred.1", od)
+        sh["pred.3.weight"] = (od, od)
+        sh["pred.3.bias"] = (od,)
     return sh
 
 
-def simsiam3d_state_dict_torch(seed: int = 5, layers=(2, 2, 2), heads=("proj", "pred")):
+def simsiam2d_state_dict_torch(seed: int = 6, layers=(2, 2, 2), heads=("proj", "pred"), out_dim=128):
+    """Seeded weights of `TomoResClassifier2D` (simsiam_model_2d.py:617-664), head width out_dim = head_conv."""
+    return simsiam3d_state_dict_torch(seed, layers, heads, two_d=True, out_dim=out_dim)
+
+
+def simsiam3d_state_dict_torch(seed: int = 5, layers=(2, 2, 2), heads=("proj", "pred"), two_d=False, out_dim=256):
     """Seeded non-degenerate weights for the shapes above (BN statistics away from identity), as torch tensors."""
     import torch
-    shapes = simsiam3d_param_shapes(layers, heads)
+    shapes = simsiam3d_param_shapes(layers, heads, two_d, out_dim)
     sd, off = OrderedDict(), 0
     for name, shape in shapes.items():
         n = int(np.prod(shape)) if shape else 1

@@ -129,3 +129,75 @@ def test_forward_test_vs_oracle_batch():
     a, b = out["proj"].cpu().numpy(), ref["proj"].numpy()
     cos = lambda v: (v / np.linalg.norm(v, axis=1, keepdims=True)) @ (v / np.linalg.norm(v, axis=1, keepdims=True)).T
     assert np.abs(cos(a) - cos(b)).max() <= 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D exploration variant (simsiam_model_2d.py:617-774, arch simsiam2d_18): maps of 32x32 / 16x16 / 8x8 pixels; the
+# small-map kernel takes the larger maps in row bands of 128 pixels
+@pytest.mark.parametrize("hw,cin,cout,n", [(32, 64, 64, 5), (16, 128, 128, 9), (64, 64, 64, 2), (16, 64, 128, 3)])
+def test_small_conv3x3_row_bands(L, hw, cin, cout, n):
+    g = torch.Generator(device="cuda").manual_seed(hw + cin + n)
+    x = torch.randn(1, n, hw, hw, cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g) * 0.2
+    res = torch.randn(1, n, hw, hw, cout, device="cuda", generator=g).bfloat16()
+    out = run_small(L, x, w.reshape(cout, cin, 9), 1, hw, hw, TAPS9, b, res, True)
+    ref = F.conv2d(x[0].float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1) + res[0].float()
+    ref = F.relu(ref)
+    assert (out[0].float() - ref).abs().max().item() <= 3e-2
+
+
+@pytest.mark.parametrize("hin,cin,cout,n", [(32, 64, 128, 7), (16, 128, 256, 11), (64, 64, 128, 2)])
+def test_small_conv_stride2_row_bands(L, hin, cin, cout, n):
+    g = torch.Generator(device="cuda").manual_seed(hin + cin)
+    x = torch.randn(1, n, hin, hin, cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (3 * cin ** 0.5)).bfloat16()
+    ho = hin // 2
+    out = run_small(L, x, w.reshape(cout, cin, 9), 2, ho, ho, TAPS9, None, None, True)
+    ref = F.relu(F.conv2d(x[0].float().permute(0, 3, 1, 2), w.float(), None, stride=2, padding=1)).permute(0, 2, 3, 1)
+    assert (out[0].float() - ref).abs().max().item() <= 3e-2
+    w1 = (torch.randn(cout, cin, 1, 1, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+    out1 = run_small(L, x, w1.reshape(cout, cin, 1), 2, ho, ho, [(0, 0, 0)])
+    ref1 = F.conv2d(x[0].float().permute(0, 3, 1, 2), w1.float(), None, stride=2).permute(0, 2, 3, 1)
+    assert (out1[0].float() - ref1).abs().max().item() <= 3e-2
+
+
+def build_model_2d(seed_w=6, out_dim=128):
+    from cet_pick_b200.models.model import create_model
+    m = create_model("simsiam2d_18", {"proj": out_dim, "pred": out_dim}, out_dim)
+    m.load_state_dict(synth.simsiam2d_state_dict_torch(seed_w, out_dim=out_dim))
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["simsiam2d_small", "simsiam2d_hw16"])
+def test_forward_test_2d_vs_reference_golden(golden, name):
+    g = golden(name)
+    hw, od = int(g["hw"]), int(g["out_dim"])
+    m = build_model_2d(int(g["seed_w"]), od)
+    x = torch.from_numpy(np.stack([synth.tomogram_np(1, hw, hw, int(s)) for s in g["seeds"]])).cuda()
+    out = m.forward_test(x)
+    torch.cuda.synchronize()
+    for k in ("proj", "pred"):
+        got, ref = out[k].cpu().numpy(), g[k]
+        e_abs, e_rel = float(np.abs(got - ref).max()), rel_err(got, ref)
+        print(f"{name} {k}: max-abs err {e_abs:.3e} (|ref| max {np.abs(ref).max():.3f}), relative L2 err {e_rel:.3e}")
+        assert got.shape == ref.shape
+        assert e_rel <= 1e-2 and e_abs <= 2e-2      # BF16 operands through 17 layers
+
+
+def test_forward_test_2d_vs_oracle_batch():
+    """a batch that spans many tiles in every layer, given as the 5-D tensor a dataset would hand over"""
+    from oracle import simsiam_oracle as so
+    B = 37
+    sd = synth.simsiam2d_state_dict_torch(6, out_dim=128)
+    m = build_model_2d(6, 128)
+    x = torch.from_numpy(np.stack([synth.tomogram_np(1, 32, 32, 200 + s) for s in range(B)]))
+    with torch.no_grad():
+        ref = so.forward_test_2d(x, sd)
+    out = m.forward_test(x[:, None].cuda())
+    for k in ("proj", "pred"):
+        got, r = out[k].cpu().numpy(), ref[k].numpy()
+        print(f"simsiam2d batch {k}: max-abs {np.abs(got - r).max():.3e}, relative L2 {rel_err(got, r):.3e}")
+        assert rel_err(got, r) <= 1e-2
+    with pytest.raises(RuntimeError):
+        m.forward_test(torch.zeros(2, 3, 32, 32, device="cuda"))        # conv1 has ONE input channel
