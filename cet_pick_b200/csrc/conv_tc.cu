@@ -65,6 +65,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
+// (lo, hi) descriptor words, accumulate flag as an operand; kind::tf32 or kind::f16 (warp-uniform choice)
+__device__ __forceinline__ void umma_lohi(bool tf32, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if (tf32) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .pred p;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    ptx::umma_bf16_lohi_acc(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  }
+}
+
 __device__ __forceinline__ void decode_tile(const ConvParams& p, long long t, int& img, int& y0,
                                             int& x0, int& nb) {
   nb = (int)(t % p.n_nb);
@@ -113,16 +133,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int kb_src0 = p.ntaps * p.chunks0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        int img, y0, x0, nb;
-        decode_tile(p, t, img, y0, x0, nb);
-        for (int kb = 0; kb < p.nkb; kb += p.NKB) {
-          const int nvalid = min(p.NKB, p.nkb - kb);
-          ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
+    // Producer and issuer run their loops on the WHOLE warp with warp-uniform values and elect one lane for the
+    // asynchronous instructions: issued from inside an `if (lane == 0)` region, every UTMALDG / UTCHMMA is wrapped in a
+    // lane-serialising loop (the operands must be in uniform registers) and the issuer's scalar chain bounds the kernel.
+    int stage = 0;
+    uint32_t phase = 0;
+    const int kb_src0 = p.ntaps * p.chunks0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int img, y0, x0, nb;
+      decode_tile(p, t, img, y0, x0, nb);
+      for (int kb = 0; kb < p.nkb; kb += p.NKB) {
+        const int nvalid = min(p.NKB, p.nkb - kb);
+        ptx::mbar_wait(&bar_empty[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&bar_full[stage], (uint32_t)nvalid * (uint32_t)(p.a_sub + p.b_sub));
           for (int j = 0; j < nvalid; ++j) {
             const int k = kb + j;
@@ -135,49 +158,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             ptx::tma_load_2d(sB + (size_t)stage * b_stage + (size_t)j * p.b_sub, &p.tmB,
                              &bar_full[stage], 0, k * p.Ntot + nb * p.NB);
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      // kind::tf32: a_format = b_format = 2 (TF32) in bits [7,10) / [10,13), c_format = 1 (F32)
-      const uint32_t idesc = p.tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24))
-                                    : ptx::make_idesc_bf16(TILE_M, p.NB);
-      const uint32_t esz = p.tf32 ? 4u : 2u;
-      const uint32_t sbo = 8u * esz * (uint32_t)p.KC;     // 8 rows x (KC * element bytes)
-      const int k16s = (int)(p.KC * esz / 32u);           // one UMMA consumes 32 bytes of K per row
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
+    // kind::tf32: a_format = b_format = 2 (TF32) in bits [7,10) / [10,13), c_format = 1 (F32)
+    const bool tf32 = p.tf32 != 0;
+    const uint32_t idesc = tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24))
+                                : ptx::make_idesc_bf16(TILE_M, p.NB);
+    const uint32_t esz = tf32 ? 4u : 2u;
+    const uint32_t sbo = 8u * esz * (uint32_t)p.KC;     // 8 rows x (KC * element bytes)
+    const int k16s = (int)(p.KC * esz / 32u);           // one UMMA consumes 32 bytes of K per row
+    const uint32_t D_HI = ptx::smem_desc_hi(sbo, (uint32_t)p.layout_type);
+    const uint32_t sA_lo = ptx::smem_desc_lo(ptx::smem_u32(sA)), sB_lo = ptx::smem_desc_lo(ptx::smem_u32(sB));
+    const uint32_t a_stage16 = (uint32_t)a_stage >> 4, b_stage16 = (uint32_t)b_stage >> 4;
+    const uint32_t a_sub16 = (uint32_t)p.a_sub >> 4, b_sub16 = (uint32_t)p.b_sub >> 4;
+    const uint32_t a_full = ptx::smem_u32(&bar_full[0]), a_empty = ptx::smem_u32(&bar_empty[0]);
+    const uint32_t a_tfull = ptx::smem_u32(&bar_tfull[0]), a_tempty = ptx::smem_u32(&bar_tempty[0]);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      ptx::mbar_wait_a(a_tempty + 8u * acc, acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.NB;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < p.nkb; kb += p.NKB) {
+        const int nvalid = min(p.NKB, p.nkb - kb);
+        ptx::mbar_wait_a(a_full + 8u * stage, phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NB);
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < p.nkb; kb += p.NKB) {
-          const int nvalid = min(p.NKB, p.nkb - kb);
-          ptx::mbar_wait(&bar_full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t a0 = ptx::smem_u32(sA + (size_t)stage * a_stage);
-          const uint32_t b0 = ptx::smem_u32(sB + (size_t)stage * b_stage);
-          for (int j = 0; j < nvalid; ++j) {
+        const uint32_t a_lo = sA_lo + stage * a_stage16, b_lo = sB_lo + stage * b_stage16;
+        if (ptx::elect_one()) {
+          for (int j = 0; j < nvalid; ++j)
             for (int k = 0; k < k16s; ++k) {
-              const uint64_t da = ptx::make_smem_desc(a0 + j * p.a_sub + k * 32, sbo, p.layout_type);
-              const uint64_t db = ptx::make_smem_desc(b0 + j * p.b_sub + k * 32, sbo, p.layout_type);
-              if (p.tf32) umma_tf32(d_tmem, da, db, idesc, accumulate);
-              else ptx::umma_bf16(d_tmem, da, db, idesc, accumulate);
+              umma_lohi(tf32, d_tmem, a_lo + (uint32_t)j * a_sub16 + 2u * k, D_HI, b_lo + (uint32_t)j * b_sub16 + 2u * k, D_HI,
+                        idesc, accumulate);
               accumulate = 1;
             }
-          }
-          ptx::umma_commit(&bar_empty[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          ptx::umma_commit_a(a_empty + 8u * stage);   // frees the smem slot when these MMAs retire
         }
-        ptx::umma_commit(&bar_tfull[acc]);       // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
       }
+      if (ptx::elect_one()) ptx::umma_commit_a(a_tfull + 8u * acc);       // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue ====================================

@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -102,6 +103,141 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float* __restrict_
           if (x < 0 || x >= CW) continue;
           m0 = fmaxf(m0, __bfloat162float(s_map[y * CW + x][2 * c2]));
           m1 = fmaxf(m1, __bfloat162float(s_map[y * CW + x][2 * c2 + 1]));
+        }
+      }
+      reinterpret_cast<__nv_bfloat162*>(out + ((size_t)s * PW * PW + pp) * 64)[c2] = __floats2bfloat162_rn(m0, m1);
+    }
+  }
+}
+
+// The same stem on the legacy tensor path (mma.sync m16n8k8, TF32 operands, fp32 accumulation) for H = W = 32: per slice
+// an implicit GEMM  [256 conv pixels] x [49 taps, padded to 56] x [64 channels].  The A fragments are gathered straight
+// from the zero-framed input patch in shared memory (element (pixel, tap) = patch[2*oy + ky][2*ox + kx]), the folded
+// weights sit in shared memory as TF32 (72-word rows: conflict-free B fragments); warp w owns conv rows 2w, 2w+1 and
+// all 64 channels.  Shift + ReLU + bf16 into the shared conv map (72-element rows: conflict-free C stores), pooled as
+// in stem_pool_kernel.  The fp32 CUDA-core version above spent 11.7 ms of the 39 ms configs[3] batch here.
+__device__ __forceinline__ uint32_t f2tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int SM_IP = 38, SM_IPP = 39, SM_KP = 56, SM_LDW = 72, SM_LDM = 72;
+constexpr int SM_SMEM = SM_KP * SM_LDW * 4 + ((SM_IP * SM_IPP * 4 + 15) & ~15) + 256 * SM_LDM * 2;
+
+__global__ void __launch_bounds__(256) stem_pool_mma_kernel(const float* __restrict__ in, long long nslices,
+                                                            const float* __restrict__ wgt /*[49][64], BN scale folded*/,
+                                                            const float* __restrict__ shift /*[64]*/,
+                                                            __nv_bfloat16* __restrict__ out /*[nslices][8][8][64]*/) {
+  constexpr int HW = 32, CW = 16, PW = 8;
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  uint32_t (*s_w)[SM_LDW] = reinterpret_cast<uint32_t (*)[SM_LDW]>(stem_smem);                          // [56][72] tf32
+  uint32_t* s_in = reinterpret_cast<uint32_t*>(stem_smem + SM_KP * SM_LDW * 4);                        // [38][39] tf32
+  __nv_bfloat16 (*s_map)[SM_LDM] =
+      reinterpret_cast<__nv_bfloat16 (*)[SM_LDM]>(stem_smem + SM_KP * SM_LDW * 4 + ((SM_IP * SM_IPP * 4 + 15) & ~15));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  // rows 49 / 50 of the padded K axis carry the BatchNorm shift (split into two TF32 terms, so it stays exact to ~2^-22);
+  // the A operand has 1.0 in those two columns: the accumulator comes out with the shift already added
+  for (int i = tid; i < SM_KP * 64; i += 256) {
+    const int k = i >> 6, c = i & 63;
+    uint32_t v = 0u;
+    if (k < 49) v = f2tf32(__ldg(wgt + k * 64 + c));
+    else if (k == 49) v = f2tf32(__ldg(shift + c));
+    else if (k == 50) { const float sv = __ldg(shift + c); v = f2tf32(sv - __uint_as_float(f2tf32(sv))); }
+    s_w[k][c] = v;
+  }
+  // this thread's elements of the zero-framed 38 x 38 patch: (patch offset, source offset or -1 for the frame)
+  constexpr int NPRE = (SM_IP * SM_IP + 255) / 256;
+  float pre[NPRE];                                      // the NEXT slice's values, in flight during this slice's MMAs
+  auto fetch = [&](long long s) {
+    const float* src = in + (size_t)s * HW * HW;
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + 256 * j;
+      const int r = i / SM_IP, c = i - r * SM_IP, y = r - 3, x = c - 3;
+      pre[j] = (i < SM_IP * SM_IP && y >= 0 && y < HW && x >= 0 && x < HW) ? __ldg(src + y * HW + x) : 0.f;
+    }
+  };
+  if ((long long)blockIdx.x < nslices) fetch(blockIdx.x);
+  for (long long s = blockIdx.x; s < nslices; s += gridDim.x) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + 256 * j;
+      const int r = i / SM_IP, c = i - r * SM_IP;
+      if (i < SM_IP * SM_IP) s_in[r * SM_IPP + c] = f2tf32(pre[j]);
+    }
+    __syncthreads();
+    if (s + gridDim.x < nslices) fetch(s + gridDim.x);
+    float acc[2][8][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[mi][ni][c] = 0.f;
+#pragma unroll
+    for (int k8 = 0; k8 < 7; ++k8) {
+      // patch offsets of this thread's two taps of the step (tap t -> row t / 7, column t % 7); columns 49 / 50 = 1.0
+      const int t0 = k8 * 8 + tq, t1 = t0 + 4;
+      const int o0 = (t0 / 7) * SM_IPP + (t0 % 7), o1 = (t1 / 7) * SM_IPP + (t1 % 7);
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        // conv row oy = 2 * warp + mi, pixels ox = gq and gq + 8: patch origin (2 * oy, 2 * ox)
+        const int base = (2 * (2 * warp + mi)) * SM_IPP + 2 * gq;
+        if (k8 < 6) {
+          a[mi][0] = s_in[base + o0];      a[mi][1] = s_in[base + 16 + o0];
+          a[mi][2] = s_in[base + o1];      a[mi][3] = s_in[base + 16 + o1];
+        } else {
+          const uint32_t one = 0x3f800000u;
+          a[mi][0] = t0 == 48 ? s_in[base + o0] : (t0 <= 50 ? one : 0u);
+          a[mi][1] = t0 == 48 ? s_in[base + 16 + o0] : (t0 <= 50 ? one : 0u);
+          a[mi][2] = 0u; a[mi][3] = 0u;
+        }
+      }
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) {
+        uint32_t b[2];
+        b[0] = s_w[k8 * 8 + tq][ni * 8 + gq];
+        b[1] = s_w[k8 * 8 + tq + 4][ni * 8 + gq];
+        mma_m16n8k8_tf32(acc[0][ni], a[0], b);
+        mma_m16n8k8_tf32(acc[1][ni], a[1], b);
+      }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int p = (2 * warp + mi) * CW + gq;
+#pragma unroll
+      for (int ni = 0; ni < 8; ++ni) {
+        const int c = ni * 8 + 2 * tq;
+        *reinterpret_cast<__nv_bfloat162*>(&s_map[p][c]) =
+            __floats2bfloat162_rn(fmaxf(acc[mi][ni][0], 0.f), fmaxf(acc[mi][ni][1], 0.f));
+        *reinterpret_cast<__nv_bfloat162*>(&s_map[p + 8][c]) =
+            __floats2bfloat162_rn(fmaxf(acc[mi][ni][2], 0.f), fmaxf(acc[mi][ni][3], 0.f));
+      }
+    }
+    __syncthreads();
+    // MaxPool2d(3, stride 2, pad 1) on the 16 x 16 map -> 8 x 8
+    for (int o = tid; o < PW * PW * 32; o += 256) {
+      const int c2 = o & 31, pp = o >> 5, py = pp / PW, px = pp % PW;
+      float m0 = 0.f, m1 = 0.f;                         // post-ReLU values: 0 is a safe identity
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = 2 * py + dy;
+        if (y < 0 || y >= CW) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = 2 * px + dx;
+          if (x < 0 || x >= CW) continue;
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&s_map[y * CW + x][2 * c2]));
+          m0 = fmaxf(m0, v.x);
+          m1 = fmaxf(m1, v.y);
         }
       }
       reinterpret_cast<__nv_bfloat162*>(out + ((size_t)s * PW * PW + pp) * 64)[c2] = __floats2bfloat162_rn(m0, m1);
@@ -431,7 +567,14 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
       CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(32)));
       CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(16)));
     }
-    if (H == 32) stem_pool_kernel<32><<<grid, 256, smem_of(32), st>>>(x, n, sw, sb, buf[0]);
+    static DeviceOnce mma_once;
+    if (mma_once.first())
+      CETPICK_CUDA(cudaFuncSetAttribute(stem_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM));
+    static const bool fp32_stem = getenv("CETPICK_SIMSIAM_FP32_STEM") != nullptr;     // A/B switch for the profiles
+    if (H == 32 && !fp32_stem) {
+      const int gm = (int)std::min<long long>(n, (long long)num_sms() * 3);
+      stem_pool_mma_kernel<<<gm, 256, SM_SMEM, st>>>(x, n, sw, sb, buf[0]);
+    } else if (H == 32) stem_pool_kernel<32><<<grid, 256, smem_of(32), st>>>(x, n, sw, sb, buf[0]);
     else stem_pool_kernel<16><<<grid, 256, smem_of(16), st>>>(x, n, sw, sb, buf[0]);
     CETPICK_LAUNCH_CHECK();
   }
