@@ -496,20 +496,61 @@ def leg_simsiam(dev, pk, B=8192):
     try:
         nb = B // 8
         sdd = {k: v.to(dev) for k, v in sd.items()}
-        with torch.no_grad():
-            ref = so.forward_test(x[:nb], sdd)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ref = so.forward_test(x[:nb], sdd)
-            e1.record()
-            torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) * 8
-        res["torch_cuda_fp32_ms_scaled_to_batch"] = t
-        res["speedup_vs_torch_cuda_fp32"] = t / ms
+
+        def torch_arm(fn, xin, tf32, autocast):
+            prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+            try:
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    r = fn(xin)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = fn(xin)
+                    e1.record()
+                    torch.cuda.synchronize()
+                return r, e0.elapsed_time(e1)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+
+        ref, t = torch_arm(lambda v: so.forward_test(v, sdd), x[:nb], False, False)
+        res["torch_cuda_fp32_ms_scaled_to_batch"] = t * 8
+        res["speedup_vs_torch_cuda_fp32"] = t * 8 / ms
         res["rel_l2_err_vs_torch_fp32"] = float(((out["proj"][:nb] - ref["proj"]).norm() / ref["proj"].norm()))
+        # the reference's own arithmetic on this GPU: PyTorch's default cudnn.allow_tf32 = True; and bf16 autocast
+        _, t = torch_arm(lambda v: so.forward_test(v, sdd), x[:nb], True, False)
+        res["torch_cuda_tf32_ms_scaled_to_batch"] = t * 8
+        res["speedup_vs_torch_cuda_tf32"] = t * 8 / ms
+        _, t = torch_arm(lambda v: so.forward_test(v, sdd), x[:nb], True, True)
+        res["torch_cuda_bf16_autocast_ms_scaled_to_batch"] = t * 8
+        res["speedup_vs_torch_cuda_bf16_autocast"] = t * 8 / ms
     except Exception as e:
         res["torch_cuda_error"] = f"{type(e).__name__}: {e}"[:200]
+    try:
+        # 2-D exploration variant (arch simsiam2d_18, TomoResClassifier2D.forward_test): 0.84 GFLOP per 32^2 patch
+        sd2 = synth.simsiam2d_state_dict_torch(6, out_dim=128)
+        m2 = create_model("simsiam2d_18", {"proj": 128, "pred": 128}, 128)
+        m2.load_state_dict(sd2)
+        m2 = m2.to(dev).eval()
+        x2 = x.view(-1)[:B * 1024].view(B, 1, 32, 32)
+        for _ in range(2):
+            out2 = m2.forward_test(x2)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        for i in range(3):
+            out2 = m2.forward_test(x2)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms2 = median([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+        sdd2 = {k: v.to(dev) for k, v in sd2.items()}
+        ref2, t2 = torch_arm(lambda v: so.forward_test_2d(v, sdd2), x2[:B // 8], True, False)
+        res["simsiam2d_18"] = {"workload": f"{B} patches of 32^2, head width 128", "ms": ms2, "patches_per_sec": B / (ms2 * 1e-3),
+                               "achieved_tflops": 0.84e9 * B / (ms2 * 1e-3) / 1e12, "launches": int(m2.last_launches),
+                               "torch_cuda_tf32_ms_scaled_to_batch": t2 * 8, "speedup_vs_torch_cuda_tf32": t2 * 8 / ms2,
+                               "rel_l2_err_vs_torch": float(((out2["proj"][:B // 8] - ref2["proj"]).norm() / ref2["proj"].norm()))}
+    except Exception as e:
+        res["simsiam2d_18"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     return res
 
 
