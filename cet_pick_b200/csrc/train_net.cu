@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace cetpick {
 namespace {
@@ -822,6 +823,100 @@ __global__ void __launch_bounds__(256, 2) conv3x3_mma_kernel(const float* __rest
       }
 }
 
+// Weight gradient of a 3 x 3 'same' convolution (the 2-D trunk) on tiles: CTA = 32 output channels x 32 input channels x
+// all 9 taps, looping over its share of the 128-pixel tiles (8 x 16 pixels of one slice, or 8 x 8 of two slices for the
+// 8-pixel-wide bottom level).  Per tile the dy tile [32 co][128 px] and the input patch with its halo [32 ci][10 x 18]
+// are staged once as TF32 and serve all 9 taps: dW[co][ci][tap] += sum_px dy[co][px] * x[ci][px shifted by the tap]
+// = 9 x mma.sync.m16n8k8 per warp and K step (A = dy, rows = co; B = the patch shifted by the tap, columns = ci), with
+// the 9 x 16 x 8 accumulators in registers for the whole tile range and one atomicAdd per (co, ci, tap) at the end.
+// The im2col form (wgrad_mma_kernel) re-gathers every input element once per tap column with its bounds arithmetic.
+constexpr int WT_PLANE = 228;                      // >= 200 (two 10 x 10 patches), = 4 mod 32 words: conflict-free B fragments
+constexpr int WT_LDY = 132;                        // 128 + 4: conflict-free A fragments
+template <bool TW8>
+__global__ void __launch_bounds__(256, 2) wgrad3x3_tile_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, const Geom g, const int ci_blocks,
+                                                               const long long ntiles, const long long tiles_per_cta) {
+  __shared__ __align__(16) uint32_t s_x[32][WT_PLANE];
+  __shared__ __align__(16) uint32_t s_dy[32][WT_LDY];
+  constexpr int PW = TW8 ? 10 : 18, PSZ = TW8 ? 200 : 180;
+  const int co0 = (blockIdx.x / ci_blocks) * 32, ci0 = (blockIdx.x % ci_blocks) * 32;
+  const long long t_begin = (long long)blockIdx.y * tiles_per_cta, t_end = min(ntiles, t_begin + tiles_per_cta);
+  const int tiles_x = TW8 ? 1 : ceil_div(g.W, 16), tiles_y = ceil_div(g.H, 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gq = lane >> 2, tq = lane & 3;
+  const int mi = warp & 1, nj = warp >> 1;             // warp: co rows [16 mi, 16 mi + 16), ci columns [8 nj, 8 nj + 8)
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+  for (long long T = t_begin; T < t_end; ++T) {
+    const int tx = (int)(T % tiles_x), ty = (int)((T / tiles_x) % tiles_y);
+    const int nn = (int)(T / ((long long)tiles_x * tiles_y)) * (TW8 ? 2 : 1);      // first slice of the tile
+    const int y0 = ty * 8, x0 = tx * 16;
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 128; e += 256) {
+      const int co = e >> 7, pos = e & 127;
+      const int zz = TW8 ? pos >> 6 : 0, row = TW8 ? (pos >> 3) & 7 : pos >> 4, col = TW8 ? pos & 7 : pos & 15;
+      const int oy = y0 + row, ox = x0 + col, n = nn + zz;
+      float v = 0.f;
+      if (co0 + co < g.Cout && n < g.N && oy < g.H && ox < g.W)
+        v = __ldg(dy + (size_t)n * g.ys_n + (size_t)(co0 + co) * g.ys_c + (size_t)oy * g.W + ox);
+      s_dy[co][pos] = to_tf32(v);
+    }
+    for (int e = threadIdx.x; e < 32 * PSZ; e += 256) {
+      const int ci = e / PSZ, r = e - ci * PSZ;
+      const int zz = TW8 ? r / 100 : 0, r2 = TW8 ? r - zz * 100 : r, py = r2 / PW, px = r2 - py * PW;
+      const int iy = y0 + py - 1, ix = x0 + px - 1, n = nn + zz;
+      float v = 0.f;
+      if (ci0 + ci < g.Cin && n < g.N && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+        v = __ldg(x + (size_t)n * g.xs_n + (size_t)(ci0 + ci) * g.xs_c + (size_t)iy * g.W + ix);
+      s_x[ci][r] = to_tf32(v);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int ks = 0; ks < 16; ++ks) {
+      // the 8 pixels of this K step lie in one tile row: patch index of the first one at tap (0, 0)
+      const int pb = TW8 ? (ks >> 3) * 100 + (ks & 7) * 10 : (ks >> 1) * 18 + (ks & 1) * 8;
+      uint32_t af[4];
+      af[0] = s_dy[mi * 16 + gq][ks * 8 + tq];     af[1] = s_dy[mi * 16 + gq + 8][ks * 8 + tq];
+      af[2] = s_dy[mi * 16 + gq][ks * 8 + tq + 4]; af[3] = s_dy[mi * 16 + gq + 8][ks * 8 + tq + 4];
+      const uint32_t* xr = &s_x[nj * 8 + gq][pb + tq];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int off = (t / 3) * PW + (t % 3);
+        uint32_t bf[2] = {xr[off], xr[off + 4]};
+        mma_tf32(acc[t], af, bf);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int co = co0 + mi * 16 + gq + ((c & 2) ? 8 : 0), ci = ci0 + nj * 8 + 2 * tq + (c & 1);
+      const float v = acc[t][c];
+      if (co < g.Cout && ci < g.Cin && v != 0.f) atomicAdd(dw + ((size_t)co * g.Cin + ci) * 9 + t, v);
+    }
+}
+
+int launch_wgrad3x3_tile(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
+  const bool tw8 = g.W <= 8;
+  const int co_blocks = ceil_div(g.Cout, 32), ci_blocks = ceil_div(g.Cin, 32);
+  const long long ntiles = tw8 ? (long long)ceil_div(g.N, 2) * ceil_div(g.H, 8)
+                               : (long long)g.N * ceil_div(g.H, 8) * ceil_div(g.W, 16);
+  // enough CTAs to fill the machine a few times over, at least 4 tiles each (the 288 atomics per thread are paid once per CTA)
+  long long splits = std::max<long long>(1, std::min<long long>(ceil_div<long long>(ntiles, 4),
+                                                                 ceil_div<long long>(6LL * num_sms(), co_blocks * ci_blocks)));
+  splits = std::min<long long>(splits, 65535);
+  const long long per = ceil_div<long long>(ntiles, splits);
+  splits = ceil_div<long long>(ntiles, per);
+  const dim3 grid(co_blocks * ci_blocks, (unsigned)splits);
+  if (tw8) wgrad3x3_tile_kernel<true><<<grid, 256, 0, s>>>(x, dy, dw, g, ci_blocks, ntiles, per);
+  else wgrad3x3_tile_kernel<false><<<grid, 256, 0, s>>>(x, dy, dw, g, ci_blocks, ntiles, per);
+  CETPICK_LAUNCH_CHECK();
+  return CETPICK_OK;
+}
+
 template <int BM, int BN>
 int launch_wgrad_mma(const float* x, const float* dy, float* dw, const Geom& g, cudaStream_t s) {
   const long long total = (long long)g.N * g.Ho * g.Wo;
@@ -917,6 +1012,10 @@ extern "C" int cetpick_train_conv_wgrad_f32(const float* x, const float* dy, flo
   // wide layers: tiled SGEMM with implicit im2col; the few-channel ends of the network (stem, hm) keep the direct kernel
   const bool mma_ok = g_train_tf32 && (long long)g->Cin * g->xs_c < 0x7fffffffLL && g->pz < 64 && g->py < 64 && g->px < 64 &&
                       (kz - 1) * g->dz < 64 && (ky - 1) * g->dy < 64 && (kx - 1) * g->dx < 64;
+  static const bool tile_off = getenv("CETPICK_WGRAD_NO_TILE") != nullptr;            // A/B switch for the profiles
+  if (g_train_tf32 && !tile_off && kz == 1 && ky == 3 && kx == 3 && g->dy == 1 && g->dx == 1 && g->py == 1 && g->px == 1 &&
+      g->stride == 1 && g->Ho == g->H && g->Wo == g->W && g->Cout >= 32 && g->Cin >= 16)
+    return launch_wgrad3x3_tile(x, dy, dw, *g, s);
   if (g->Cout >= 64 && kz * ky * kx * g->Cin >= 64)
     return mma_ok ? launch_wgrad_mma<64, 64>(x, dy, dw, *g, s) : launch_wgrad_gemm<64, 64>(x, dy, dw, *g, s);
   if (g->Cout >= 32 && kz * ky * kx * g->Cin >= 128)
