@@ -10,7 +10,7 @@
 // and, for the 3-D layer, z), and the traversal stride of the tensor map (elementStrides) is the convolution stride
 // (2 for the first conv and the 1x1 shortcut of a down-sampling BasicBlock).  fp32 accumulators in TMEM, double
 // buffered; epilogue = bias (folded BatchNorm) + optional residual add + optional ReLU, bf16 or fp32 out.
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: epilogue
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7, 8-11: two epilogue groups
 #include "conv_small.cuh"
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -24,7 +24,7 @@ namespace cetpick {
 
 namespace {
 
-constexpr int SM_THREADS = 256;
+constexpr int SM_THREADS = 384;          // warps 0-2: producer, issuer, TMEM allocator; 4-7 and 8-11: two epilogue groups
 constexpr int MAX_STAGES = 8;
 
 struct alignas(64) SmallParams {
@@ -210,9 +210,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const __grid_
     // halo mode orders the M rows (y, map, x): row group g = 2 * y + map
     const int px = p.halo ? (m & 7) : m % p.TW, py = p.halo ? (m >> 4) : (m / p.TW) % p.TH,
               pz = p.halo ? ((m >> 3) & 1) : m / (p.TW * p.TH);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    // two epilogue groups, one per TMEM accumulator: group g drains the CTA's tiles g, g + 2, g + 4, ... so each has two
+    // mainloop periods per tile (with one group the epilogue bounded the N = 64 / 128 layers, r10h)
+    const int grp = (warp - 4) >> 2;
+    const int acc = grp;
+    long long it = 0;
+    for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      if ((int)(it & 1) != grp) continue;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int ty = (int)(t % p.tiles_y);
       const long long tq = t / p.tiles_y;
       const int z0 = (int)(tq % p.tiles_z) * p.TZ, nb = (int)(tq / p.tiles_z);
@@ -294,7 +299,6 @@ __global__ void __launch_bounds__(SM_THREADS, 1) conv_small_kernel(const __grid_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar_tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 

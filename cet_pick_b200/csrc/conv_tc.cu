@@ -53,18 +53,7 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 x TF32 -> FP32 (K = 8 per instruction)
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 x TF32 -> FP32 (K = 8 per instruction) or BF16 (K = 16):
 // (lo, hi) descriptor words, accumulate flag as an operand; kind::tf32 or kind::f16 (warp-uniform choice)
 __device__ __forceinline__ void umma_lohi(bool tf32, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                           uint32_t idesc, uint32_t accumulate) {
