@@ -357,10 +357,37 @@ bool bn_fold(const cetpick_simsiam* m, const std::string& p, int C, bool affine,
 }
 
 // conv / Linear weight (Cout, Cin, taps) with an optional BatchNorm behind it and an optional bias of its own
+// CoutP / CinP >= Cout / Cin: the layer is built CoutP x CinP wide with zero weights, zero bias in the padding (head widths
+// that are not multiples of 64 in the 2-D variant: padded activations are exactly 0 through Linear, BatchNorm and ReLU)
 bool pack(cetpick_simsiam* m, const std::string& wkey, int Cout, int Cin, int ntaps, int stride, const Fold* fold,
-          const std::vector<float>* own_bias, cetpick_simsiam::Conv& c) {
-  auto w = m->get(wkey, (size_t)Cout * Cin * ntaps);
-  if (!w || (Cin % 64)) return false;
+          const std::vector<float>* own_bias, cetpick_simsiam::Conv& c, int CoutP = 0, int CinP = 0) {
+  auto w0 = m->get(wkey, (size_t)Cout * Cin * ntaps);
+  if (CoutP < Cout) CoutP = Cout;
+  if (CinP < Cin) CinP = Cin;
+  if (!w0 || (CinP % 64)) return false;
+  std::vector<float> wpad;
+  std::vector<double> spad;
+  std::vector<float> bpad;
+  Fold fpad;
+  const std::vector<float>* w = w0;
+  if (CoutP != Cout || CinP != Cin) {
+    wpad.assign((size_t)CoutP * CinP * ntaps, 0.f);
+    for (int n = 0; n < Cout; ++n)
+      for (int k = 0; k < Cin; ++k)
+        for (int t = 0; t < ntaps; ++t) wpad[((size_t)n * CinP + k) * ntaps + t] = (*w0)[((size_t)n * Cin + k) * ntaps + t];
+    w = &wpad;
+    if (fold) {
+      fpad.scale.assign(CoutP, 1.0); fpad.shift.assign(CoutP, 0.0);
+      for (int n = 0; n < Cout; ++n) { fpad.scale[n] = fold->scale[n]; fpad.shift[n] = fold->shift[n]; }
+      fold = &fpad;
+    }
+    if (own_bias) {
+      bpad.assign(CoutP, 0.f);
+      for (int n = 0; n < Cout; ++n) bpad[n] = (*own_bias)[n];
+      own_bias = &bpad;
+    }
+    Cout = CoutP; Cin = CinP;
+  }
   const std::vector<uint16_t> pk = small_pack_weights(w->data(), Cout, Cin, ntaps, fold ? fold->scale.data() : nullptr);
   c.w_off = balloc(m, pk.size() * 2);
   memcpy(m->blob.data() + c.w_off, pk.data(), pk.size() * 2);
@@ -401,7 +428,7 @@ size_t ws_bytes_for(const cetpick_simsiam* m, int64_t B, int64_t D, const Geo& g
   (void)m;
   const size_t n = (size_t)B * D;
   const size_t a1 = align_up(n * g.h1 * g.h1 * 64 * 2, 1024);       // layer1 maps (three rotating buffers)
-  return 3 * a1 + 1024 + align_up((size_t)B * 256 * 2, 1024) * 4;
+  return 3 * a1 + 1024 + align_up((size_t)B * 256 * 2, 1024) * 4 + align_up((size_t)B * 256 * 4, 1024) * 2;
 }
 
 int run(const cetpick_simsiam* m, const cetpick_simsiam::Conv& c, const void* src, int B, int Z, int Hin, int Win, int Ho,
@@ -439,7 +466,7 @@ extern "C" int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int b
 
 extern "C" int cetpick_simsiam_create_2d(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int out_dim,
                                          int has_proj, int has_pred) {
-  if (out_dim < 64 || out_dim > 256 || (out_dim % 64)) return plan ? CETPICK_ERR_UNSUPPORTED : CETPICK_ERR_BAD_ARG;
+  if (out_dim < 1 || out_dim > 256) return plan ? CETPICK_ERR_UNSUPPORTED : CETPICK_ERR_BAD_ARG;
   const int rc = cetpick_simsiam_create(plan, blocks1, blocks2, blocks3, has_proj, has_pred);
   if (rc != CETPICK_OK) return rc;
   (*plan)->two_d = 1;
@@ -499,19 +526,20 @@ extern "C" int cetpick_simsiam_finalize(cetpick_simsiam* m) {
       (!bn_fold(m, "feature_3d.1", 256, true, f) || !pack(m, "feature_3d.0.weight", 256, 256, 27, 1, &f, nullptr, m->f3d)))
     return CETPICK_ERR_STATE;
   const int od = m->out_dim;                                // 256, or head_conv in the 2-D variant (simsiam_model_2d.py:639-640)
+  const int op = (od + 63) / 64 * 64;                       // width the head layers are built with
   {
     auto b = m->get("fc.bias", od);
-    if (!b || !pack(m, "fc.weight", od, 256, 1, 1, nullptr, b, m->fc)) return CETPICK_ERR_STATE;
+    if (!b || !pack(m, "fc.weight", od, 256, 1, 1, nullptr, b, m->fc, op, 256)) return CETPICK_ERR_STATE;
   }
   if (m->has_proj) {
-    if (!bn_fold(m, "proj.1", od, true, f) || !pack(m, "proj.0.weight", od, od, 1, 1, &f, nullptr, m->proj0)) return CETPICK_ERR_STATE;
-    if (!bn_fold(m, "proj.4", od, true, f) || !pack(m, "proj.3.weight", od, od, 1, 1, &f, nullptr, m->proj3)) return CETPICK_ERR_STATE;
-    if (!bn_fold(m, "proj.7", od, false, f) || !pack(m, "proj.6.weight", od, od, 1, 1, &f, nullptr, m->proj6)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.1", od, true, f) || !pack(m, "proj.0.weight", od, od, 1, 1, &f, nullptr, m->proj0, op, op)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.4", od, true, f) || !pack(m, "proj.3.weight", od, od, 1, 1, &f, nullptr, m->proj3, op, op)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "proj.7", od, false, f) || !pack(m, "proj.6.weight", od, od, 1, 1, &f, nullptr, m->proj6, op, op)) return CETPICK_ERR_STATE;
   }
   if (m->has_pred) {
     auto b = m->get("pred.3.bias", od);
-    if (!bn_fold(m, "pred.1", od, true, f) || !pack(m, "pred.0.weight", od, od, 1, 1, &f, nullptr, m->pred0)) return CETPICK_ERR_STATE;
-    if (!b || !pack(m, "pred.3.weight", od, od, 1, 1, nullptr, b, m->pred3)) return CETPICK_ERR_STATE;
+    if (!bn_fold(m, "pred.1", od, true, f) || !pack(m, "pred.0.weight", od, od, 1, 1, &f, nullptr, m->pred0, op, op)) return CETPICK_ERR_STATE;
+    if (!b || !pack(m, "pred.3.weight", od, od, 1, 1, nullptr, b, m->pred3, op, op)) return CETPICK_ERR_STATE;
   }
   if (m->d_blob) { cudaFree(m->d_blob); m->d_blob = nullptr; }
   CETPICK_CUDA(cudaMalloc(&m->d_blob, m->blob.size()));
@@ -617,11 +645,23 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
     if ((rc = run(m, m->proj0, vec[1], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[2], st))) return rc;
     if ((rc = run(m, m->proj3, vec[2], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[3], st))) return rc;
     // proj.6 + BN(affine=False): fp32 out for the caller, bf16 copy as the input of 'pred'
-    if (proj && (rc = run(m, m->proj6, vec[3], 1, B, 1, 1, 1, 1, false, nullptr, 0, 1, proj, st))) return rc;
+    // head widths that are not multiples of 64 are computed 64-padded into a staging buffer and copied out row by row
+    const int od = m->out_dim, op = m->proj6.Cout;
+    float* stage_f32[2] = {reinterpret_cast<float*>(base + 3 * a1 + 4 * v1),
+                           reinterpret_cast<float*>(base + 3 * a1 + 4 * v1 + align_up((size_t)B * 256 * 4, 1024))};
+    auto emit = [&](const cetpick_simsiam::Conv& c, const void* src, float* dst, int which) -> int {
+      float* o = op == od ? dst : stage_f32[which];
+      const int r = run(m, c, src, 1, B, 1, 1, 1, 1, false, nullptr, 0, 1, o, st);
+      if (r) return r;
+      if (op != od)
+        CETPICK_CUDA(cudaMemcpy2DAsync(dst, (size_t)od * 4, o, (size_t)op * 4, (size_t)od * 4, (size_t)B, cudaMemcpyDeviceToDevice, st));
+      return CETPICK_OK;
+    };
+    if (proj && (rc = emit(m->proj6, vec[3], proj, 0))) return rc;
     if (pred) {
       if ((rc = run(m, m->proj6, vec[3], 1, B, 1, 1, 1, 1, false, nullptr, 0, 0, vec[2], st))) return rc;
       if ((rc = run(m, m->pred0, vec[2], 1, B, 1, 1, 1, 1, false, nullptr, 1, 0, vec[0], st))) return rc;
-      if ((rc = run(m, m->pred3, vec[0], 1, B, 1, 1, 1, 1, false, nullptr, 0, 1, pred, st))) return rc;
+      if ((rc = emit(m->pred3, vec[0], pred, 1))) return rc;
     }
   }
   return CETPICK_OK;

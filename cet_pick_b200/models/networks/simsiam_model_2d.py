@@ -19,9 +19,9 @@ class TomoResClassifier2D(TomoResClassifier):
 
     def __init__(self, layers, heads, head_conv):
         nn.Module.__init__(self)
-        if head_conv not in (64, 128, 192, 256):
-            raise NotImplementedError(f"TomoResClassifier2D head_conv={head_conv}: widths 64, 128, 192, 256 are built "
-                                      "(the reference's default for the exploration task is 128, opts.py:207-209)")
+        if not 1 <= head_conv <= 256:
+            raise NotImplementedError(f"TomoResClassifier2D head_conv={head_conv}: widths 1 ... 256 are built (the "
+                                      "reference's default for the exploration task is 128, opts.py:207-209)")
         self.heads = heads
         self.layers_spec = list(layers[:3])
         self.inplanes = 64

@@ -231,7 +231,8 @@ typedef struct cetpick_simsiam cetpick_simsiam;
 int cetpick_simsiam_create(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int has_proj, int has_pred);
 /* 2-D exploration variant: TomoResClassifier2D.forward_test (cet_pick/models/networks/simsiam_model_2d.py:617-774, arch
  * simsiam2d_18; conv1 3x3 stride 1, no max-pool, AdaptiveAvgPool2d, fc 256 -> out_dim, heads of width out_dim).
- * out_dim = the reference's head_conv (128 by default for this task, opts.py:207-209); 64, 128, 192 or 256 here. */
+ * out_dim = the reference's head_conv (128 by default for this task, opts.py:207-209; 32 by default in the factory's
+ * signature), 1 ... 256; widths that are not multiples of 64 are computed zero-padded. */
 int cetpick_simsiam_create_2d(cetpick_simsiam** plan, int blocks1, int blocks2, int blocks3, int out_dim,
                               int has_proj, int has_pred);
 void cetpick_simsiam_destroy(cetpick_simsiam* plan);

@@ -169,7 +169,7 @@ def build_model_2d(seed_w=6, out_dim=128):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("name", ["simsiam2d_small", "simsiam2d_hw16"])
+@pytest.mark.parametrize("name", ["simsiam2d_small", "simsiam2d_hw16", "simsiam2d_hc32"])
 def test_forward_test_2d_vs_reference_golden(golden, name):
     g = golden(name)
     hw, od = int(g["hw"]), int(g["out_dim"])
