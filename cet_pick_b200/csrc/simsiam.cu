@@ -633,7 +633,9 @@ extern "C" int cetpick_simsiam_forward(cetpick_simsiam* m, const float* x, int64
     CETPICK_LAUNCH_CHECK();
   } else {
     // (B, D, h, w, 256) -> Conv3d 3x3x3 pad 1 + BN3d + ReLU (:348-354); one sub-volume (D*h*w positions) per M-tile
-    if (P != 128) return CETPICK_ERR_UNSUPPORTED;            // 32 slices of 2x2 (or 16x... ) must fill one 128-row tile
+    // an M-tile holds up to 128 / (h*w) slices of one sub-volume (a 32^3 sub-volume fills it exactly; shallower ones, like the
+    // D = 1 slab sums of the reference's own exploration dataset, leave rows idle; deeper ones span several tiles)
+    if (hin * hin > 128) return CETPICK_ERR_UNSUPPORTED;
     const int t1 = (cur + 1) % 3;
     if ((rc = run(m, m->f3d, buf[cur], B, D, hin, hin, hin, hin, true, nullptr, 1, 0, buf[t1], st))) return rc;
     avgpool_kernel<<<std::min(B, num_sms() * 8), 256, 0, st>>>(buf[t1], B, P, 256, vec[0]);

@@ -73,6 +73,8 @@ _DATASETS = {
     "tomo": ([512, 512], 1), "cr": ([64, 64], 1), "semi": ([64, 64], 1), "semiclass": ([64, 64], 1),
     "semi3d": ([64, 64], 1), "fs": ([128, 128], 1), "simsiam": ([24, 24], 256), "scan": ([24, 24], 256),
     "denoise": ([64, 64], 256), "moco": ([32, 32], 256),
+    # the exploration datasets' class attributes (datasets/tomo_pre_proj_angle_select_new3d_vol.py:26-27, ..._new2d3d.py:26-27)
+    "simsiam3d": ([256, 256], 1), "simsiam2d3d": ([256, 256], 1),
 }
 
 

@@ -240,8 +240,9 @@ void cetpick_simsiam_destroy(cetpick_simsiam* plan);
 int cetpick_simsiam_set_param(cetpick_simsiam* plan, const char* key, const float* data_host, int64_t numel);
 int cetpick_simsiam_finalize(cetpick_simsiam* plan);
 int cetpick_simsiam_workspace_bytes(const cetpick_simsiam* plan, int64_t B, int64_t D, int64_t H, int64_t W, size_t* bytes);
-/* x: (B,D,H,W) float32 device sub-volumes (H = W = 32 with D = 32, or H = W = 16 with D = 128: the trunk's final
- * 2x2xD (1x1xD) map fills one 128-row tile; other sizes return CETPICK_ERR_UNSUPPORTED).
+/* x: (B,D,H,W) float32 device sub-volumes, H = W = 32 or 16, any depth D <= 4096 (D = 32 at H = 32 fills the Conv3d
+ * layer's 128-row tile exactly; the reference's exploration dataset feeds D = 1 slab sums); other H, W return
+ * CETPICK_ERR_UNSUPPORTED.
  * A 2-D plan takes (B,1,H,W) patches, D = 1, H = W in {8, 16, 32, 64}.
  * proj / pred: (B,256) float32 device out ((B,out_dim) for a 2-D plan), either may be NULL. */
 int cetpick_simsiam_forward(cetpick_simsiam* plan, const float* x, int64_t B, int64_t D, int64_t H, int64_t W,

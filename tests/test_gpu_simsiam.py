@@ -97,10 +97,12 @@ def rel_err(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
 
 
-def test_forward_test_vs_reference_golden(golden):
-    g = golden("simsiam3d_small")
+@pytest.mark.parametrize("name", ["simsiam3d_small", "simsiam3d_d1", "simsiam3d_d5"])
+def test_forward_test_vs_reference_golden(golden, name):
+    g = golden(name)
     m = build_model(int(g["seed_w"]))
-    x = torch.from_numpy(np.stack([synth.tomogram_np(32, 32, 32, int(s)) for s in g["seeds"]])).cuda()
+    D, H, W = [int(v) for v in g["shape"]]
+    x = torch.from_numpy(np.stack([synth.tomogram_np(D, H, W, int(s)) for s in g["seeds"]])).cuda()
     out = m.forward_test(x)
     torch.cuda.synchronize()
     for k in ("proj", "pred"):
