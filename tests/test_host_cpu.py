@@ -88,3 +88,21 @@ def test_load_model_contract(tmp_path, capsys):
     m3, opt3, ep = load_model(m, p, optimizer=torch.optim.Adam(m.parameters(), lr=1.0), resume=True, lr=1e-3,
                               lr_step=[200, 400, 600])
     assert ep == 450 and abs(opt3.param_groups[0]["lr"] - 1e-5) < 1e-12
+
+
+def test_exploration_driver_host_logic():
+    """cet_pick_b200/simsiam_test_hm_3d.py: the patch normalisation is torchvision's ToPILImage -> ToTensor -> Normalize of
+    PrefetchDatasetProj (simsiam_test_hm_3d.py:44-51) bit for bit; the border filter is the dataset's (:207)."""
+    import torch
+    import torchvision.transforms as T
+    from cet_pick_b200 import simsiam_test_hm_3d as drv
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(7, 1, 32, 32, generator=g)
+    p[0, 0, 0, 0], p[0, 0, 0, 1] = 1.0, 0.0               # the min-max normalised patches contain both ends
+    mean, std = p.mean(), p.std()
+    tr = T.Compose([T.ToPILImage(), T.ToTensor(), T.Normalize((mean), (std))])
+    ref = torch.stack([tr(x) for x in p])
+    assert torch.equal(drv.normalise_patches(p.clone(), mean, std), ref)
+    pos = np.array([[17, 17, 12], [18, 17, 12], [18, 18, 12], [46, 50, 12], [47, 46, 12], [45, 47, 12], [30, 47, 12]])
+    assert drv.keep_candidates(pos, (30, 64, 64), 32).tolist() == [[18, 17, 12], [18, 18, 12], [45, 47, 12], [30, 47, 12]]
+    assert drv.keep_candidates(np.zeros((0, 3), int), (30, 64, 64), 32).shape == (0, 3)
