@@ -8,8 +8,14 @@
 // The activation tensor is a rank-5 TMA tensor (C, W, H, Z, B); for every (tap, 64-channel chunk) ONE box load shifted
 // by the tap offset brings the [128][64] K-major A tile, TMA's out-of-bounds zero fill is the zero padding (in x, y
 // and, for the 3-D layer, z), and the traversal stride of the tensor map (elementStrides) is the convolution stride
-// (2 for the first conv and the 1x1 shortcut of a down-sampling BasicBlock).  fp32 accumulators in TMEM, double
-// buffered; epilogue = bias (folded BatchNorm) + optional residual add + optional ReLU, bf16 or fp32 out.
+// (2 for the first conv and the 1x1 shortcut of a down-sampling BasicBlock).  Two refinements on top of that scheme:
+//   * weights that fit beside the A ring stay RESIDENT in shared memory for the CTA's lifetime (one fetch per CTA);
+//   * HALO mode (8x8 maps, 3x3 stride 1): one zero-framed box [y 0..9][map 0..1][x 0..9][64 ch] per (tile, chunk) -- the
+//     tensor-map dimensions are ordered (C, W, Z, H, B) for that -- and every tap is a shifted descriptor into it
+//     (the 16 eight-pixel row groups of the M-tile are 1280 B apart), instead of nine tap-shifted boxes.
+// fp32 accumulators in TMEM, double buffered, one epilogue group per accumulator; epilogue = bias (folded BatchNorm,
+// from shared memory) + optional residual add (row preloaded into registers) + optional ReLU, bf16 or fp32 out.
+// Producer and issuer run warp-uniform and elect one lane for the asynchronous instructions.
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7, 8-11: two epilogue groups
 #include "conv_small.cuh"
 #include "common.cuh"
