@@ -125,25 +125,22 @@ class TomoClassdetDetector(BaseDetector):
             raise ValueError("Output contains NaN values")
         write_mrc(os.path.join(path, "{}_hm.mrc".format(name)), np.float32(np.swapaxes(hm, 1, 0)))
         o = self.opt
-        graph = getattr(o, "fiber", False) or getattr(o, "spike", False)
-        kept = ([], [], [], [])
+        a = np.asarray(dets, dtype=np.float64).reshape(-1, np.asarray(dets).shape[-1] if len(dets) else 4)
+        x, y, z = (np.floor(a[:, j]).astype(np.int64) for j in range(3))      # rows [x, y, z, score] at the INPUT resolution
+        score = a[:, 3]                                                       # the float32 values, exactly (:191)
+        keep = (score > o.out_thresh) & (z >= o.cutoff_z) & (z <= max_z - o.cutoff_z) & (x > 20) & (x < max_x - 20) \
+            & (y > 20) & (y < max_y - 20)                                     # no x2 here: the map is full resolution (:180)
+        if o.compress:
+            z = z * 2
+        xs, ys, zs, sc = x[keep].tolist(), y[keep].tolist(), z[keep].tolist(), score[keep].tolist()
+        if getattr(o, "fiber", False) or getattr(o, "spike", False):
+            lines = graph_pick_lines(o, xs, ys, zs, sc, scale=2)
+        elif not o.with_score:
+            lines = ["%d\t%d\t%d" % t for t in zip(xs, zs, ys)]
+        else:
+            lines = ["%d\t%d\t%d\t%s" % (xx, zz, yy, str(s)) for xx, zz, yy, s in zip(xs, zs, ys, sc)]
         with open(os.path.join(path, "{}.txt".format(name)), "w+") as out_detect:
-            for c in np.asarray(dets):
-                x, y, z, score = int(np.floor(c[0])), int(np.floor(c[1])), int(np.floor(c[2])), float(c[3])
-                if (score > o.out_thresh and z >= o.cutoff_z and z <= max_z - o.cutoff_z
-                        and x > 20 and x < max_x - 20 and y > 20 and y < max_y - 20):
-                    if o.compress:
-                        z = int(z) * 2
-                    if graph:
-                        for lst, v in zip(kept, (x, y, z, score)):
-                            lst.append(v)
-                    elif not o.with_score:
-                        print(str(x) + "\t" + str(z) + "\t" + str(y), file=out_detect)
-                    else:
-                        print(str(x) + "\t" + str(z) + "\t" + str(y) + "\t" + str(score), file=out_detect)
-            if graph:
-                for ln in graph_pick_lines(o, *kept, scale=2):
-                    print(ln, file=out_detect)
+            out_detect.write("".join(ln + "\n" for ln in lines))
 
     def debug(self, debugger, images, dets, output, scale=1):
         pass

@@ -65,7 +65,10 @@ CASES = {"fiber": (TomodetDetector, dict(fiber=True)),
          "cls_fiber": (TomoClassdetDetector, dict(fiber=True)),
          "cls_spike": (TomoClassdetDetector, dict(spike=True)),
          "cls_spike_score": (TomoClassdetDetector, dict(spike=True, with_score=True, distance_cutoff=9.0)),
-         "cls_fiber_spike": (TomoClassdetDetector, dict(fiber=True, spike=True))}
+         "cls_fiber_spike": (TomoClassdetDetector, dict(fiber=True, spike=True)),
+         "cls_plain": (TomoClassdetDetector, dict()),
+         "cls_score": (TomoClassdetDetector, dict(with_score=True)),
+         "cls_compress": (TomoClassdetDetector, dict(compress=True, out_thresh=0.6))}
 # TomodetDetector with --spike cannot be pinned: tomo_det.py never imports tomo_group_postprocess (NameError at :90).
 rows4 = np.concatenate([pts.astype(np.float32) + 0.5, scores[:, None]], 1).astype(np.float32)
 for tag, (cls, kw) in CASES.items():

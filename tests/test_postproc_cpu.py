@@ -114,7 +114,9 @@ def test_tomodet_spike_follows_the_classify_writer(golden, tmp_path):
 
 @pytest.mark.parametrize("tag,kw", [("cls_fiber", dict(fiber=True)), ("cls_spike", dict(spike=True)),
                                     ("cls_spike_score", dict(spike=True, with_score=True, distance_cutoff=9.0)),
-                                    ("cls_fiber_spike", dict(fiber=True, spike=True))])
+                                    ("cls_fiber_spike", dict(fiber=True, spike=True)),
+                                    ("cls_plain", dict()), ("cls_score", dict(with_score=True)),
+                                    ("cls_compress", dict(compress=True, out_thresh=0.6))])
 def test_classdet_save_detection_graph_files(golden, tmp_path, tag, kw):
     from cet_pick_b200.detectors.tomo_det_classify import TomoClassdetDetector
     g = golden("postproc_file")
