@@ -14,6 +14,10 @@ CASES = [
     ["semi"],
     ["semiclass", "--nms", "5", "--out_thresh", "0.4", "--cutoff_z", "7", "--gpus", "0"],
     ["semi", "--arch", "unet_5", "--fiber", "--exp_id", "abc", "--down_ratio", "2", "--order", "zxy"],
+    # the exploration step (simsiam_test_hm_3d.py): head width 128 by default, DoG sigmas, candidate box
+    ["simsiam3d", "--arch", "simsiam3d_18", "--load_model", "e.pth", "--bbox", "32", "--dog", "2.5,5", "--gauss", "0.8",
+     "--compress", "--test_img_txt", "t.txt", "--exp_id", "explore"],
+    ["simsiam", "--arch", "simsiam2d_18", "--bbox", "24", "--spike", "--distance_cutoff", "12"],
 ]
 
 
