@@ -1,4 +1,5 @@
 """Host-side pieces that need no GPU: MRC I/O, Gaussian taps, post-processing buckets, error paths."""
+import os
 import struct
 
 import numpy as np
@@ -106,3 +107,64 @@ def test_exploration_driver_host_logic():
     pos = np.array([[17, 17, 12], [18, 17, 12], [18, 18, 12], [46, 50, 12], [47, 46, 12], [45, 47, 12], [30, 47, 12]])
     assert drv.keep_candidates(pos, (30, 64, 64), 32).tolist() == [[18, 17, 12], [18, 18, 12], [45, 47, 12], [30, 47, 12]]
     assert drv.keep_candidates(np.zeros((0, 3), int), (30, 64, 64), 32).shape == (0, 3)
+
+
+def test_mrc_byte_order_mode12_extended_header_and_truncation(tmp_path):
+    """read_mrc like mrcfile.open(path, permissive=True): big-endian files (machine stamp 0x11), mode 12 (float16), an
+    extended header before the data, and a clear error for a file shorter than its header says."""
+    from cet_pick_b200.utils import mrcio
+    rng = np.random.default_rng(1)
+    data = rng.standard_normal((3, 4, 5)).astype(np.float32)
+    h = bytearray(1024)
+    struct.pack_into(">4i", h, 0, 5, 4, 3, 2)
+    h[212:216] = bytes([0x11, 0x11, 0, 0])
+    p = str(tmp_path / "be.mrc")
+    open(p, "wb").write(bytes(h) + data.astype(">f4").tobytes())
+    out = mrcio.read_mrc(p)
+    assert out.dtype == np.float32 and out.dtype.byteorder in "=<" and np.array_equal(out, data)
+    half = data.astype(np.float16)
+    h = bytearray(1024)
+    struct.pack_into("<4i", h, 0, 5, 4, 3, 12)
+    struct.pack_into("<i", h, 92, 160)                               # nsymbt: 160 bytes of extended header
+    h[212:216] = bytes([0x44, 0x44, 0, 0])
+    p = str(tmp_path / "f16.mrc")
+    open(p, "wb").write(bytes(h) + b"\x07" * 160 + half.tobytes())
+    out = mrcio.read_mrc(p)
+    assert out.dtype == np.float16 and np.array_equal(out, half)
+    p = str(tmp_path / "short.mrc")
+    open(p, "wb").write(bytes(h) + b"\x07" * 160 + half.tobytes()[:-10])
+    with pytest.raises(ValueError, match="truncated"):
+        mrcio.read_mrc(p)
+    h2 = bytearray(1024)                                              # no machine stamp at all: the sane order wins
+    struct.pack_into(">4i", h2, 0, 5, 4, 3, 1)
+    p = str(tmp_path / "nostamp.mrc")
+    ints = rng.integers(-50, 50, size=(3, 4, 5)).astype(np.int16)
+    open(p, "wb").write(bytes(h2) + ints.astype(">i2").tobytes())
+    assert np.array_equal(mrcio.read_mrc(p), ints)
+
+
+def _write_many(args):
+    """worker of the test below: one 'rank' writing its tomograms into the shared output directory"""
+    rank, path = args
+    import types
+    import torch
+    from cet_pick_b200.detectors.tomo_det import TomodetDetector
+    det = TomodetDetector.__new__(TomodetDetector)
+    det.opt = types.SimpleNamespace(down_ratio=2, out_thresh=0.25, cutoff_z=1, compress=False, fiber=False, spike=False,
+                                    with_score=False, nms=3)
+    hm = torch.rand(1, 1, 6, 40, 44)
+    dets = {2: [[50.5, 40.5, 2.0, 0.9, 0.9]], 3: [[30.5, 44.5, 3.0, 0.7, 0.7]]}
+    for i in range(12):
+        det.save_detection(hm, dets, path, None, name=f"r{rank}_t{i}")
+    return rank
+
+
+def test_two_ranks_write_into_the_same_new_directory(tmp_path):
+    """torchrun ranks share <save_dir>/<out_id>: none may die on the directory another one is creating (round-1 advice)"""
+    import multiprocessing as mp
+    out = str(tmp_path / "exp" / "out")                               # neither level exists yet
+    with mp.get_context("spawn").Pool(2) as pool:
+        assert sorted(pool.map(_write_many, [(0, out), (1, out)])) == [0, 1]
+    names = sorted(os.listdir(out))
+    assert len(names) == 48 and "r0_t0.txt" in names and "r1_t11_hm.mrc" in names
+    assert open(os.path.join(out, "r1_t3.txt")).read() == "50\t2\t40\n30\t3\t44\n"
