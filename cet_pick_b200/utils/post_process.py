@@ -33,14 +33,23 @@ def tomo_post_process(dets, z_dim_tot=128):
 # points (K = 900 by default), float64 / int64 numpy like the reference; the connected components come from
 # scipy.sparse.csgraph, which is what the reference's sknetwork.topology.get_connected_components returns for a
 # square adjacency (labels numbered in order of each component's lowest point index).
-def _component_labels(points, distance_cutoff):
-    """labels[i] of the graph that links two picks when their Euclidean distance is <= distance_cutoff (:35-41, :55-61)"""
+def _component_labels(points, distance_cutoff, block=512):
+    """labels[i] of the graph that links two picks when their Euclidean distance is <= distance_cutoff (:35-41, :55-61).
+    The reference fills a dense n x n matrix row by row; here the links are collected block-wise into a sparse one
+    (same arithmetic per pair: sqrt of the integer / float sum of squares), so K = 10 000 picks need megabytes, not gigabytes."""
     from scipy import sparse
     from scipy.sparse.csgraph import connected_components
     p = np.asarray(points)
-    delta = p[:, None, :] - p[None, :, :]
-    near = np.sqrt(np.sum(delta ** 2, axis=2)) <= distance_cutoff          # the diagonal is always linked (distance 0)
-    return connected_components(sparse.csr_matrix(near.astype(np.float64)), directed=False, return_labels=True)[1]
+    n = p.shape[0]
+    rows, cols = [], []
+    for i0 in range(0, n, block):
+        delta = p[i0:i0 + block, None, :] - p[None, :, :]
+        r, c = np.nonzero(np.sqrt(np.sum(delta ** 2, axis=2)) <= distance_cutoff)     # the diagonal is always linked
+        rows.append(r + i0)
+        cols.append(c)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    adjacency = sparse.csr_matrix((np.ones(rows.size), (rows, cols)), shape=(n, n))
+    return connected_components(adjacency, directed=False, return_labels=True)[1]
 
 
 def k_x(y, a, b, c):
